@@ -1,0 +1,182 @@
+/* insta_b200 -- C ABI of the B200-native (sm_100a) implementation of INSTA's per-sample deformation-and-encoding
+ * hot path.  This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions.
+ *
+ * Conventions
+ *   - every function returns INSTA_OK (0) or a negative insta_status; insta_last_error() gives the message of the
+ *     last failure on the calling thread (the reference throws std::runtime_error via CUDA_CHECK_THROW instead;
+ *     src/main.cu:261 catches it).
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers.  Nothing is allocated inside a hot-path call.
+ *   - every hot-path entry takes the caller's cudaStream_t (as void*), is stream-ordered and never synchronises --
+ *     same contract as the reference hooks, which all run on Testbed::m_stream (testbed.cu:2488).
+ *   - one context per GPU; a context is bound to the device it was created on.
+ *
+ * Reference interface replaced by each entry point is cited beside it (paths relative to the INSTA repository;
+ * ngp/ = instant-ngp/, tcnn/ = instant-ngp/dependencies/tiny-cuda-nn/).
+ */
+#ifndef INSTA_B200_H
+#define INSTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define INSTA_API __declspec(dllexport)
+#else
+#define INSTA_API __attribute__((visibility("default")))
+#endif
+
+typedef struct insta_ctx insta_ctx;
+typedef void* insta_stream; /* cudaStream_t */
+
+typedef enum insta_status {
+	INSTA_OK = 0,
+	INSTA_ERR_INVALID = -1,   /* bad argument / state */
+	INSTA_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+	INSTA_ERR_IO = -3,        /* file could not be read / parsed */
+	INSTA_ERR_NO_DEVICE = -4, /* no sm_100 device: there is NO CPU fallback */
+	INSTA_ERR_CAPACITY = -5   /* frame cache (max_cached_bvh) exhausted */
+} insta_status;
+
+/* Plain-old-data parameters, filled from the reference's JSON keys.
+ *   INSTA keys read in src/core.cu:201-215 (configs/nerf/insta.json, main.json)
+ *   "encoding" block of configs/nerf/main.json:45-53 and ngp/src/testbed.cu:2246-2258 (per_level_scale). */
+typedef struct insta_params {
+	uint32_t struct_size;            /* = sizeof(insta_params); ABI versioning */
+	/* ---- INSTA keys ---- */
+	int32_t  disable_interp;         /* "disable_interp"  (core.cu:201) : 1 = never blend neighbour TBNs */
+	uint32_t max_cached_bvh;         /* "max_cached_bvh"  (core.cu:204) : capacity of the per-frame BVH cache, default 4000 */
+	uint32_t exp_params;             /* "exp_params"      (core.cu:210) : expression floats appended to each sample, 16 */
+	uint32_t geo_params;             /* "geo_params"      (core.cu:209) : 0 = off; >0 writes the cosine feature */
+	uint32_t n_primitives_per_leaf;  /* N_PRIMITIVES_LEAF (src/tiny_mesh.cu:28-32) : 2 in Release */
+	float    aabb_min[3], aabb_max[3]; /* Testbed::m_aabb used by `warp` to skip samples (core.cu:477); unit cube */
+	/* ---- "encoding" (HashGrid) ---- */
+	uint32_t n_levels;               /* 16 */
+	uint32_t n_features_per_level;   /* 8 (only 8 is implemented: one 128-bit load per corner) */
+	uint32_t log2_hashmap_size;      /* 18 */
+	uint32_t base_resolution;        /* 16 */
+	float    per_level_scale;        /* 0 = derive as testbed.cu:2246-2258 does: exp(log(2048*aabb_scale/base)/(n_levels-1)) */
+	uint32_t aabb_scale;             /* 1 */
+	/* ---- warp_random_samples RNG (ngp/src/testbed.cu:2185: default_rng_t{42}) ---- */
+	uint64_t rng_seed;
+} insta_params;
+
+INSTA_API void        insta_params_default(insta_params* p);
+INSTA_API const char* insta_last_error(void);
+INSTA_API const char* insta_version(void);
+
+/* rta::Core ctor + Testbed device setup.  device < 0 = current device.  Fails with INSTA_ERR_NO_DEVICE when no
+ * CUDA device of compute capability 10.x is present. */
+INSTA_API int  insta_ctx_create(const insta_params* p, int device, insta_ctx** out);
+INSTA_API void insta_ctx_destroy(insta_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Mesh ingest -- replaces rta::Core::load_meshes (src/core.cu:234-337), rta::TinyMesh (src/tiny_mesh.cu:39-178,
+ * 316-371), rta::Masking (src/masking.cpp:118-180) and ngp::TriangleBvh4::build (ngp/src/triangle_bvh.cu:548-631).
+ * Vertices are in ngp space, i.e. ALREADY offset by +0.5 (tiny_mesh.cu:63-74); the *_obj variants add it themselves.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* canonical template: topology, per-triangle FlameMasks ids (NULL = all Torso/15), adjacency, render AABB */
+INSTA_API int insta_set_canonical(insta_ctx* ctx, const float* h_verts, uint32_t n_verts, const uint32_t* h_faces,
+                                  uint32_t n_faces, const uint32_t* h_mask_ids);
+/* Masking ctor + TinyMesh ctor on "<dir>/canonical.obj" with region masks in "<mesh_masks_dir>/{lips,face,...}.obj" */
+INSTA_API int insta_load_canonical_obj(insta_ctx* ctx, const char* canonical_obj, const char* mesh_masks_dir);
+/* one tracked frame: triangles (+scaling vs canonical), BVH (reference-identical topology and leaf order),
+ * per-triangle TBN table; returns its frame index in *frame_index (== image index in the reference) */
+INSTA_API int insta_add_frame(insta_ctx* ctx, const float* h_verts, int32_t* frame_index);
+/* n frames at once, h_verts = [n][n_verts][3]; host BVH builds run on n_threads threads (0 = all cores), like the
+ * thread pool in core.cu:309 */
+INSTA_API int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t n_threads);
+INSTA_API int insta_add_frame_obj(insta_ctx* ctx, const char* obj_path, int32_t* frame_index);
+INSTA_API int insta_clear_frames(insta_ctx* ctx);
+INSTA_API uint32_t insta_n_frames(const insta_ctx* ctx);
+/* TinyMesh::m_aabb of the canonical mesh (tiny_mesh.cu:157-162) -> Testbed::m_render_aabb (core.cu:289) */
+INSTA_API int insta_get_render_aabb(const insta_ctx* ctx, float* h_aabb6);
+/* Testbed::m_aabb, tested inclusively by `warp` */
+INSTA_API int insta_set_aabb(insta_ctx* ctx, const float* h_aabb6);
+/* host copies for inspection / parity tests (any pointer may be NULL):
+ *   mask ids [n_faces], adjacency [n_faces*3] (-1 padded), BVH-order topology ids of a frame [n_faces] */
+INSTA_API int insta_get_topology(const insta_ctx* ctx, uint32_t* h_mask_ids, int32_t* h_adjacency);
+INSTA_API int insta_get_frame_bvh_order(const insta_ctx* ctx, int32_t frame, uint32_t* h_tri_ids, uint32_t* n_nodes);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stage 1 -- deformation.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* Replaces rta::Core::surface_closest_point (27-row path -> kernel `warp`, src/core.cu:339-344, 442-526, 581-608;
+ * called at ngp/src/testbed_nerf.cu:3290) when frame_id == -1 (frame = per-sample `holder`, float #4), and
+ * rta::Core::render_deformed (core.cu:346-348, 610-637; called at testbed_nerf.cu:2199-2200) when frame_id >= 0.
+ * d_coords: n records of stride_floats floats (NerfCoordinate + extra dims, ngp nerf.h:86-115), mutated IN PLACE:
+ * floats 0-2 <- canonical position, 8-10 <- canonical direction (stored (d+1)/2), the last exp_params floats <- 1.0
+ * unless the closest triangle is in the Lips region, last float <- cosine feature if geo_params > 0.
+ * Records with holder < 0, frame >= n_frames or position outside m_aabb are left untouched.
+ * d_tri_ids (nullable): topology id of the closest triangle per sample, -1 for skipped samples.
+ * d_coords must be 16-byte aligned. */
+INSTA_API int insta_deform_samples(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id,
+                                   int32_t* d_tri_ids, insta_stream stream);
+/* Replaces the 3-row path of surface_closest_point (kernel `warp_random_samples`, core.cu:528-579, 639-655; called
+ * at testbed_nerf.cu:2850 for the occupancy-grid refresh).  d_xyz: n x 3 floats in place.  d_frame_ids NULL = draw
+ * the frame per point exactly as the reference: pcg32(rng_seed).advance(i*(n_frames-1)).next_float()*(n_frames-1). */
+INSTA_API int insta_deform_points(insta_ctx* ctx, float* d_xyz, uint32_t n, const int32_t* d_frame_ids, int32_t* d_tri_ids,
+                                  insta_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stage 2 -- multiresolution hash grid (tcnn::GridEncodingTemplated<__half,3,8>, tcnn encodings/grid.h).
+ * The parameter table is BORROWED from the caller (trainer buffer order is the snapshot ABI, tcnn trainer.h:282-297):
+ * fp16, n_entries x 8, entry offsets per level as insta_grid_layout reports.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* ctor offset table (grid.h:874-939).  h_offsets: n_levels+1 (entries), h_scales / h_resolutions: n_levels; the scale
+ * is the value the device kernels use (evaluated once ON DEVICE with the reference kernel's expression, grid.h:188). */
+INSTA_API int      insta_grid_layout(const insta_ctx* ctx, uint32_t* h_offsets, float* h_scales, uint32_t* h_resolutions);
+INSTA_API uint32_t insta_grid_n_params(const insta_ctx* ctx); /* = n_entries * 8  (25,716,288 for the shipped config) */
+/* forward_impl / kernel_grid (grid.h:138-310, 941-1017).  d_pos: xyz at d_pos[i*pos_stride_floats + {0,1,2}];
+ * d_out_soa: fp16 [n_levels*8][n]  (out[i + (l*8+f)*n], grid.h:265 -- tcnn row-major == SoA) */
+INSTA_API int insta_hash_encode_fwd(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n,
+                                    const void* d_table_f16, void* d_out_soa_f16, insta_stream stream);
+/* backward_impl / kernel_grid_backward (grid.h:312-435, 1019-1110).  d_dLdy_soa: fp16 [n_levels*8][n];
+ * d_grad_table_f16: n_entries x 8 fp16, zeroed first when zero_first != 0 (EGradientMode::Overwrite, grid.h:1067) */
+INSTA_API int insta_hash_encode_bwd(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n,
+                                    const void* d_dLdy_soa_f16, void* d_grad_table_f16, int zero_first, insta_stream stream);
+/* parity diagnostic: global entry index of the 8 corners, d_slots[(i*n_levels + l)*8 + corner] (grid_index, grid.h:100) */
+INSTA_API int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, uint32_t* d_slots,
+                               insta_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-buffer convenience (the end-to-end path a caller without device buffers uses): H2D of the records, stage 1,
+ * stage 2, D2H of the mutated records and of the fp16 encodings, chunked and double-buffered on internal streams.
+ * h_coords / h_out_soa_f16 should be pinned (cudaHostAlloc / insta_host_alloc) for full PCIe speed.
+ * Blocks until the results are in host memory.
+ * ------------------------------------------------------------------------------------------------------------ */
+INSTA_API int insta_deform_encode_host(insta_ctx* ctx, float* h_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id,
+                                       const void* d_table_f16, void* h_out_soa_f16);
+INSTA_API int insta_host_alloc(void** p, uint64_t bytes);
+INSTA_API int insta_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-only utilities (no GPU needed): the host halves of the mesh ingest, exposed so that callers and tests can
+ * reuse / inspect them.  Layouts are the reference's: triangles = ngp::Triangle (48 B: a, b, c, scaling, id, mask_id;
+ * ngp triangle.cuh:234-238), nodes = ngp::TriangleBvhNode (32 B: min, max, left_idx, right_idx; triangle_bvh.cuh:29).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* ngp::TriangleBvh::build (ngp/src/triangle_bvh.cu:548-631): permutes h_tris IN PLACE into BVH order and writes the
+ * node array; *n_nodes receives the node count (INSTA_ERR_CAPACITY if max_nodes is too small). */
+INSTA_API int insta_host_bvh_build(void* h_tris, uint32_t n_tris, uint32_t n_primitives_per_leaf, void* h_nodes, uint32_t max_nodes,
+                                   uint32_t* n_nodes);
+/* TinyMesh::build_triangles (src/tiny_mesh.cu:134-155); h_canonical_tris NULL = canonical mesh itself (scaling 1) */
+INSTA_API int insta_host_build_triangles(const float* h_verts, const uint32_t* h_faces, uint32_t n_faces, const uint32_t* h_mask_ids,
+                                         const void* h_canonical_tris, void* h_tris_out);
+/* TinyMesh::get_triangle_3_neighbours (src/tiny_mesh.cu:316-371): h_out = n_faces x 3, -1 padded */
+INSTA_API int insta_host_adjacency(const uint32_t* h_faces, uint32_t n_faces, uint32_t n_verts, int32_t* h_out);
+/* TinyMesh::load + Masking (src/tiny_mesh.cu:53-84, src/masking.cpp:32-180): parses the OBJ (+0.5 offset applied) and
+ * the region masks.  Pass NULL outputs with the counts to size the buffers first. */
+INSTA_API int insta_host_load_canonical_obj(const char* canonical_obj, const char* mesh_masks_dir, float* h_verts, uint32_t* h_faces,
+                                            uint32_t* h_mask_ids, uint32_t* n_verts, uint32_t* n_faces);
+/* TinyMesh::m_aabb (src/tiny_mesh.cu:157-162) */
+INSTA_API int insta_host_mesh_aabb(const float* h_verts, uint32_t n_verts, float* h_aabb6);
+
+/* number of kernels this library has launched on behalf of ctx since creation (bench.py's gpu_launches) */
+INSTA_API uint64_t insta_launch_count(const insta_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTA_B200_H */

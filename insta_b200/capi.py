@@ -1,0 +1,301 @@
+"""ctypes binding of libinsta_b200.so (include/insta_b200.h) for the test-suite and bench.py.
+
+PyTorch is used only as the owner of device buffers and streams (`tensor.data_ptr()`, `current_stream()`); every
+computation goes through the C ABI.  There is no fallback: if the shared library is missing or no sm_100 GPU is
+present, loading / context creation raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+LIB_PATH = _build.LIB
+
+
+class InstaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("insta_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("disable_interp", C.c_int32),
+        ("max_cached_bvh", C.c_uint32),
+        ("exp_params", C.c_uint32),
+        ("geo_params", C.c_uint32),
+        ("n_primitives_per_leaf", C.c_uint32),
+        ("aabb_min", C.c_float * 3),
+        ("aabb_max", C.c_float * 3),
+        ("n_levels", C.c_uint32),
+        ("n_features_per_level", C.c_uint32),
+        ("log2_hashmap_size", C.c_uint32),
+        ("base_resolution", C.c_uint32),
+        ("per_level_scale", C.c_float),
+        ("aabb_scale", C.c_uint32),
+        ("rng_seed", C.c_uint64),
+    ]
+
+
+# every symbol include/insta_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
+EXPORTS = [
+    "insta_params_default", "insta_last_error", "insta_version", "insta_ctx_create", "insta_ctx_destroy",
+    "insta_set_canonical", "insta_load_canonical_obj", "insta_add_frame", "insta_add_frames", "insta_add_frame_obj",
+    "insta_clear_frames", "insta_n_frames", "insta_get_render_aabb", "insta_set_aabb", "insta_get_topology",
+    "insta_get_frame_bvh_order", "insta_deform_samples", "insta_deform_points", "insta_grid_layout", "insta_grid_n_params",
+    "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
+    "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
+    "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
+]
+
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """dlopen the in-tree library.  Raises if it is absent and cannot be built -- never falls back to anything."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise FileNotFoundError(LIB_PATH + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    lib.insta_last_error.restype = C.c_char_p
+    lib.insta_version.restype = C.c_char_p
+    lib.insta_n_frames.restype = C.c_uint32
+    lib.insta_grid_n_params.restype = C.c_uint32
+    lib.insta_launch_count.restype = C.c_uint64
+    lib.insta_ctx_destroy.restype = None
+    lib.insta_params_default.restype = None
+    for name in EXPORTS:
+        getattr(lib, name)  # AttributeError if the .so lost a symbol
+    _lib = lib
+    return lib
+
+
+def default_params():
+    p = Params()
+    load_library().insta_params_default(C.byref(p))
+    return p
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype)
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(stream=None):
+    import torch
+
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+class Context:
+    """Host-side mirror of the rta::Core hooks on top of the C ABI (same names as the reference where one exists)."""
+
+    def __init__(self, device=None, **overrides):
+        import torch
+
+        self.lib = load_library()
+        p = default_params()
+        for k, v in overrides.items():
+            if not hasattr(p, k):
+                raise KeyError(k)
+            setattr(p, k, v)
+        self.params = p
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = int(device)
+        h = C.c_void_p()
+        self._check(self.lib.insta_ctx_create(C.byref(p), C.c_int(self.device), C.byref(h)))
+        self.h = h
+        self.n_verts = self.n_faces = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise InstaError(rc, (self.lib.insta_last_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.insta_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mesh ingest (rta::Core::load_meshes) ----
+    def set_canonical(self, verts, faces, mask_ids=None):
+        verts, faces = _np(verts, np.float32), _np(faces, np.uint32)
+        m = _np(mask_ids, np.uint32) if mask_ids is not None else None
+        self._check(self.lib.insta_set_canonical(self.h, _vp(verts), C.c_uint32(len(verts)), _vp(faces), C.c_uint32(len(faces)), _vp(m) if m is not None else None))
+        self.n_verts, self.n_faces = len(verts), len(faces)
+
+    def load_canonical_obj(self, canonical_obj, mesh_masks_dir):
+        self._check(self.lib.insta_load_canonical_obj(self.h, canonical_obj.encode(), mesh_masks_dir.encode() if mesh_masks_dir else None))
+
+    def add_frame(self, verts):
+        verts = _np(verts, np.float32)
+        idx = C.c_int32(-1)
+        self._check(self.lib.insta_add_frame(self.h, _vp(verts), C.byref(idx)))
+        return idx.value
+
+    def add_frames(self, verts_all, n_threads=0):
+        verts_all = _np(verts_all, np.float32)
+        self._check(self.lib.insta_add_frames(self.h, _vp(verts_all), C.c_uint32(verts_all.shape[0]), C.c_uint32(n_threads)))
+
+    def clear_frames(self):
+        self._check(self.lib.insta_clear_frames(self.h))
+
+    @property
+    def n_frames(self):
+        return self.lib.insta_n_frames(self.h)
+
+    def render_aabb(self):
+        out = np.empty(6, np.float32)
+        self._check(self.lib.insta_get_render_aabb(self.h, _vp(out)))
+        return out
+
+    def set_aabb(self, aabb6):
+        a = _np(aabb6, np.float32)
+        self._check(self.lib.insta_set_aabb(self.h, _vp(a)))
+
+    def topology(self):
+        m = np.empty(self.n_faces, np.uint32)
+        adj = np.empty((self.n_faces, 3), np.int32)
+        self._check(self.lib.insta_get_topology(self.h, _vp(m), _vp(adj)))
+        return m, adj
+
+    def frame_bvh_order(self, frame):
+        ids = np.empty(self.n_faces, np.uint32)
+        nn = C.c_uint32(0)
+        self._check(self.lib.insta_get_frame_bvh_order(self.h, C.c_int32(frame), _vp(ids), C.byref(nn)))
+        return ids, nn.value
+
+    # ---- stage 1 ----
+    def surface_closest_point(self, coords, tri_ids=None, stream=None):
+        """rta::Core::surface_closest_point: [n, 27] records (frame = holder) or [n, 3] points (reference RNG frame draw)."""
+        n, m = coords.shape
+        assert coords.is_cuda and coords.is_contiguous() and coords.dtype.is_floating_point and coords.element_size() == 4
+        if m == 3:
+            self._check(self.lib.insta_deform_points(self.h, _dev(coords), C.c_uint32(n), None, _dev(tri_ids), _stream(stream)))
+        else:
+            self._check(self.lib.insta_deform_samples(self.h, _dev(coords), C.c_uint32(n), C.c_uint32(m), C.c_int32(-1), _dev(tri_ids), _stream(stream)))
+        return coords
+
+    def render_deformed(self, coords, frame_id, tri_ids=None, stream=None):
+        """rta::Core::render_deformed: one fixed frame (m_target_deform_frame) for every record."""
+        n, m = coords.shape
+        self._check(self.lib.insta_deform_samples(self.h, _dev(coords), C.c_uint32(n), C.c_uint32(m), C.c_int32(frame_id), _dev(tri_ids), _stream(stream)))
+        return coords
+
+    def deform_points(self, xyz, frame_ids=None, tri_ids=None, stream=None):
+        self._check(self.lib.insta_deform_points(self.h, _dev(xyz), C.c_uint32(xyz.shape[0]), _dev(frame_ids), _dev(tri_ids), _stream(stream)))
+        return xyz
+
+    # ---- stage 2 ----
+    def grid_layout(self):
+        L = self.params.n_levels
+        offs = np.empty(L + 1, np.uint32)
+        scales = np.empty(L, np.float32)
+        res = np.empty(L, np.uint32)
+        self._check(self.lib.insta_grid_layout(self.h, _vp(offs), _vp(scales), _vp(res)))
+        return offs, scales, res
+
+    @property
+    def grid_n_params(self):
+        return self.lib.insta_grid_n_params(self.h)
+
+    def hash_encode_fwd(self, pos, table, out, stream=None):
+        """pos: float32 [n, stride] (xyz = first three floats of each row); table: fp16 [entries, 8]; out: fp16 [L*8, n]."""
+        n, stride = pos.shape
+        self._check(self.lib.insta_hash_encode_fwd(self.h, _dev(pos), C.c_uint32(stride), C.c_uint32(n), _dev(table), _dev(out), _stream(stream)))
+        return out
+
+    def hash_encode_bwd(self, pos, dLdy, grad, zero_first=True, stream=None):
+        n, stride = pos.shape
+        self._check(self.lib.insta_hash_encode_bwd(self.h, _dev(pos), C.c_uint32(stride), C.c_uint32(n), _dev(dLdy), _dev(grad), C.c_int(int(zero_first)), _stream(stream)))
+        return grad
+
+    def hash_slots(self, pos, slots, stream=None):
+        n, stride = pos.shape
+        self._check(self.lib.insta_hash_slots(self.h, _dev(pos), C.c_uint32(stride), C.c_uint32(n), _dev(slots), _stream(stream)))
+        return slots
+
+    # ---- host-buffer path ----
+    def deform_encode_host(self, h_coords, frame_id, table, h_out):
+        """h_coords: pinned float32 torch tensor [n, stride] (mutated in place); h_out: pinned fp16 [L*8, n]."""
+        n, stride = h_coords.shape
+        self._check(self.lib.insta_deform_encode_host(self.h, C.c_void_p(h_coords.data_ptr()), C.c_uint32(n), C.c_uint32(stride), C.c_int32(frame_id),
+                                                      _dev(table), C.c_void_p(h_out.data_ptr())))
+
+    @property
+    def launch_count(self):
+        return self.lib.insta_launch_count(self.h)
+
+
+# ---- host-only utilities (no GPU) ----------------------------------------------------------------------------------
+TRI_DTYPE = np.dtype([("a", "<f4", 3), ("b", "<f4", 3), ("c", "<f4", 3), ("scaling", "<f4"), ("id", "<u4"), ("mask_id", "<u4")])
+NODE_DTYPE = np.dtype([("mn", "<f4", 3), ("mx", "<f4", 3), ("left_idx", "<i4"), ("right_idx", "<i4")])
+
+
+def _hcheck(rc):
+    if rc != 0:
+        raise InstaError(rc, (load_library().insta_last_error() or b"").decode())
+
+
+def host_build_triangles(verts, faces, mask_ids=None, canonical=None):
+    verts, faces = _np(verts, np.float32), _np(faces, np.uint32)
+    m = _np(mask_ids, np.uint32) if mask_ids is not None else None
+    out = np.zeros(len(faces), TRI_DTYPE)
+    _hcheck(load_library().insta_host_build_triangles(_vp(verts), _vp(faces), C.c_uint32(len(faces)), _vp(m) if m is not None else None,
+                                                      _vp(canonical) if canonical is not None else None, _vp(out)))
+    return out
+
+
+def host_bvh_build(tris, leaf_size=2):
+    t = np.ascontiguousarray(tris.copy())
+    nodes = np.zeros(4 * len(t) + 16, NODE_DTYPE)
+    nn = C.c_uint32(0)
+    _hcheck(load_library().insta_host_bvh_build(_vp(t), C.c_uint32(len(t)), C.c_uint32(leaf_size), _vp(nodes), C.c_uint32(len(nodes)), C.byref(nn)))
+    return nodes[: nn.value].copy(), t
+
+
+def host_adjacency(faces, n_verts):
+    faces = _np(faces, np.uint32)
+    out = np.empty((len(faces), 3), np.int32)
+    _hcheck(load_library().insta_host_adjacency(_vp(faces), C.c_uint32(len(faces)), C.c_uint32(n_verts), _vp(out)))
+    return out
+
+
+def host_load_canonical_obj(canonical_obj, mesh_masks_dir):
+    lib = load_library()
+    nv, nf = C.c_uint32(0), C.c_uint32(0)
+    md = mesh_masks_dir.encode() if mesh_masks_dir else None
+    _hcheck(lib.insta_host_load_canonical_obj(canonical_obj.encode(), md, None, None, None, C.byref(nv), C.byref(nf)))
+    verts = np.empty((nv.value, 3), np.float32)
+    faces = np.empty((nf.value, 3), np.uint32)
+    masks = np.empty(nf.value, np.uint32)
+    _hcheck(lib.insta_host_load_canonical_obj(canonical_obj.encode(), md, _vp(verts), _vp(faces), _vp(masks), C.byref(nv), C.byref(nf)))
+    return verts, faces, masks
+
+
+def host_mesh_aabb(verts):
+    verts = _np(verts, np.float32)
+    out = np.empty(6, np.float32)
+    _hcheck(load_library().insta_host_mesh_aabb(_vp(verts), C.c_uint32(len(verts)), _vp(out)))
+    return out

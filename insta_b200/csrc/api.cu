@@ -1,0 +1,519 @@
+// C ABI of libinsta_b200.so (include/insta_b200.h): context, mesh ingest and the thin launch wrappers.
+// Host code only; the kernels live in deform.cu and hashgrid.cu.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+#include "ctx.h"
+
+namespace insta {
+const char* last_error_cstr();
+
+int sync_frame_table(insta_ctx* ctx, cudaStream_t s) {
+	if (!ctx->frame_table_dirty) return INSTA_OK;
+	const uint32_t n = (uint32_t)ctx->frames.size();
+	if (n > ctx->frame_table_cap) {
+		// growing the table must not race with kernels still reading the old one
+		INSTA_CUDA(cudaDeviceSynchronize());
+		if (ctx->d_frame_table) cudaFree(ctx->d_frame_table);
+		ctx->frame_table_cap = std::max<uint32_t>(n, std::max<uint32_t>(64, ctx->frame_table_cap * 2));
+		INSTA_CUDA(cudaMalloc(&ctx->d_frame_table, sizeof(FrameDev) * ctx->frame_table_cap));
+	}
+	std::vector<FrameDev> host(n);
+	for (uint32_t i = 0; i < n; ++i) host[i] = ctx->frames[i].dev;
+	if (n) INSTA_CUDA(cudaMemcpyAsync(ctx->d_frame_table, host.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice, s));
+	INSTA_CUDA(cudaStreamSynchronize(s));  // `host` is pageable and goes out of scope
+	ctx->frame_table_dirty = false;
+	return INSTA_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Upload one prepared frame: BVH quads + BVH-order triangles from the host build, transform table computed on device.
+static int upload_frame(insta_ctx* ctx, const float* h_verts, const HostBvh& bvh, insta_ctx::Frame& fr) {
+	const size_t quads_b = align_up(bvh.quads.size() * sizeof(Quad), 256);
+	const size_t tris_b = align_up(bvh.tris.size() * sizeof(Tri), 256);
+	const size_t xf_b = align_up((size_t)ctx->n_faces * sizeof(TriXf), 256);
+	const size_t verts_b = align_up((size_t)ctx->n_verts * 12, 256);
+	INSTA_CUDA(cudaMalloc(&fr.slab, quads_b + tris_b + xf_b + verts_b));
+	unsigned char* base = (unsigned char*)fr.slab;
+	Quad* d_quads = (Quad*)base;
+	Tri* d_tris = (Tri*)(base + quads_b);
+	TriXf* d_xf = (TriXf*)(base + quads_b + tris_b);
+	float* d_verts = (float*)(base + quads_b + tris_b + xf_b);
+	cudaStream_t s = ctx->streams[0];
+	INSTA_CUDA(cudaMemcpyAsync(d_quads, bvh.quads.data(), bvh.quads.size() * sizeof(Quad), cudaMemcpyHostToDevice, s));
+	INSTA_CUDA(cudaMemcpyAsync(d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(Tri), cudaMemcpyHostToDevice, s));
+	INSTA_CUDA(cudaMemcpyAsync(d_verts, h_verts, (size_t)ctx->n_verts * 12, cudaMemcpyHostToDevice, s));
+	int rc = launch_build_xf(ctx, d_verts, d_xf, ctx->d_canon_area, nullptr, s);
+	if (rc) return rc;
+	INSTA_CUDA(cudaStreamSynchronize(s));
+	fr.dev.quads = d_quads;
+	fr.dev.tris = d_tris;
+	fr.dev.xf = d_xf;
+	fr.n_nodes = (uint32_t)bvh.nodes.size();
+	fr.n_quads = (uint32_t)bvh.quads.size();
+	fr.bvh_order_ids.resize(bvh.tris.size());
+	for (size_t i = 0; i < bvh.tris.size(); ++i) fr.bvh_order_ids[i] = bvh.tris[i].id;
+	return INSTA_OK;
+}
+
+static void prepare_frame(const insta_ctx* ctx, const float* h_verts, HostBvh& bvh) {
+	std::vector<Tri> tris(ctx->n_faces);
+	build_triangles(h_verts, ctx->faces.data(), ctx->n_faces, ctx->mask_ids.data(), ctx->canon_tris.data(), tris.data());
+	build_bvh(tris, ctx->p.n_primitives_per_leaf, bvh);
+}
+
+static int ensure_stage(insta_ctx* ctx, uint32_t chunk, uint32_t stride) {
+	if (ctx->stage_cap >= chunk && ctx->stage_stride >= stride) return INSTA_OK;
+	for (int k = 0; k < 2; ++k) {
+		if (ctx->d_stage_rec[k]) cudaFree(ctx->d_stage_rec[k]);
+		if (ctx->d_stage_enc[k]) cudaFree(ctx->d_stage_enc[k]);
+		ctx->d_stage_rec[k] = nullptr;
+		ctx->d_stage_enc[k] = nullptr;
+	}
+	for (int k = 0; k < 2; ++k) {
+		INSTA_CUDA(cudaMalloc(&ctx->d_stage_rec[k], (size_t)chunk * stride * 4));
+		INSTA_CUDA(cudaMalloc(&ctx->d_stage_enc[k], (size_t)chunk * ctx->levels.n_levels * 8 * 2));
+	}
+	ctx->stage_cap = chunk;
+	ctx->stage_stride = stride;
+	return INSTA_OK;
+}
+
+// TinyMesh::load (+0.5 offset) and Masking on the canonical OBJ; host only.
+static int load_canonical_obj_host(const char* canonical_obj, const char* mesh_masks_dir, std::vector<float>& verts, std::vector<uint32_t>& faces,
+                                   std::vector<uint32_t>& masks) {
+	std::vector<float> colors;
+	std::string err;
+	if (!load_obj(canonical_obj, verts, colors, faces, err)) INSTA_FAIL(INSTA_ERR_IO, err);
+	for (float& v : verts) v = v * 1.0f + 0.5f;  // MESH_SCALE = 1, offset 0.5 (tiny_mesh.cu:63-74)
+	masks.clear();
+	if (mesh_masks_dir) {
+		// regions loaded by Masking::mesh_to_mask (masking.cpp:150-157) with their FlameMasks enum values
+		static const std::pair<const char*, int> kRegions[] = {{"boundary", 0}, {"eye_region", 1}, {"face", 2}, {"left_ear", 4}, {"lips", 7}, {"right_ear", 10}};
+		std::vector<std::pair<int, std::vector<uint32_t>>> regions;
+		for (const auto& r : kRegions) {
+			std::vector<float> v2, c2;
+			std::vector<uint32_t> f2;
+			const std::string path = std::string(mesh_masks_dir) + "/" + r.first + ".obj";
+			if (!load_obj(path.c_str(), v2, c2, f2, err)) INSTA_FAIL(INSTA_ERR_IO, err);
+			std::vector<uint32_t> red;
+			for (size_t i = 0; i + 2 < c2.size(); i += 3)
+				if (c2[i] >= 1.0f && c2[i + 1] == 0.0f && c2[i + 2] == 0.0f) red.push_back((uint32_t)(i / 3));
+			regions.emplace_back(r.second, std::move(red));
+		}
+		masks_from_regions(faces.data(), (uint32_t)(faces.size() / 3), regions, masks);
+	}
+	return INSTA_OK;
+}
+
+}  // namespace insta
+
+using namespace insta;
+
+extern "C" {
+
+void insta_params_default(insta_params* p) {
+	if (!p) return;
+	memset(p, 0, sizeof(*p));
+	p->struct_size = sizeof(insta_params);
+	p->disable_interp = 0;
+	p->max_cached_bvh = 4000;  // configs/nerf/insta.json:4
+	p->exp_params = 16;        // configs/nerf/main.json:17
+	p->geo_params = 0;
+	p->n_primitives_per_leaf = 2;
+	for (int k = 0; k < 3; ++k) {
+		p->aabb_min[k] = 0.f;
+		p->aabb_max[k] = 1.f;
+	}
+	p->n_levels = 16;
+	p->n_features_per_level = 8;
+	p->log2_hashmap_size = 18;
+	p->base_resolution = 16;
+	p->per_level_scale = 0.f;
+	p->aabb_scale = 1;
+	p->rng_seed = 42;
+}
+
+const char* insta_last_error(void) { return last_error_cstr(); }
+const char* insta_version(void) { return "insta_b200 0.1 (sm_100a)"; }
+
+int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
+	if (!out) INSTA_FAIL(INSTA_ERR_INVALID, "out is null");
+	*out = nullptr;
+	insta_params def;
+	insta_params_default(&def);
+	if (p) {
+		if (p->struct_size != sizeof(insta_params)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_params.struct_size mismatch");
+		def = *p;
+	}
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+		cudaGetLastError();
+		INSTA_FAIL(INSTA_ERR_NO_DEVICE, "no CUDA device visible: insta_b200 has no CPU fallback");
+	}
+	if (device < 0) INSTA_CUDA(cudaGetDevice(&device));
+	INSTA_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	INSTA_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) INSTA_FAIL(INSTA_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library carries sm_100a code only");
+	insta_ctx* ctx = new insta_ctx();
+	ctx->p = def;
+	ctx->device = device;
+	ctx->sm_count = prop.multiProcessorCount;
+	for (int k = 0; k < 3; ++k) {
+		ctx->aabb[k] = def.aabb_min[k];
+		ctx->aabb[3 + k] = def.aabb_max[k];
+	}
+	for (int k = 0; k < 2; ++k) {
+		if (cudaStreamCreateWithFlags(&ctx->streams[k], cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&ctx->events[k], cudaEventDisableTiming) != cudaSuccess) {
+			set_error("stream/event creation failed");
+			insta_ctx_destroy(ctx);
+			return INSTA_ERR_CUDA;
+		}
+	}
+	int rc = init_grid_levels(ctx);
+	if (rc) {
+		insta_ctx_destroy(ctx);
+		return rc;
+	}
+	*out = ctx;
+	return INSTA_OK;
+}
+
+void insta_ctx_destroy(insta_ctx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	for (auto& f : ctx->frames)
+		if (f.slab) cudaFree(f.slab);
+	if (ctx->d_frame_table) cudaFree(ctx->d_frame_table);
+	if (ctx->d_faces) cudaFree(ctx->d_faces);
+	if (ctx->d_mask_ids) cudaFree(ctx->d_mask_ids);
+	if (ctx->d_adjacency) cudaFree(ctx->d_adjacency);
+	if (ctx->d_canon_area) cudaFree(ctx->d_canon_area);
+	if (ctx->d_canon_xf) cudaFree(ctx->d_canon_xf);
+	for (int k = 0; k < 2; ++k) {
+		if (ctx->d_stage_rec[k]) cudaFree(ctx->d_stage_rec[k]);
+		if (ctx->d_stage_enc[k]) cudaFree(ctx->d_stage_enc[k]);
+		if (ctx->streams[k]) cudaStreamDestroy(ctx->streams[k]);
+		if (ctx->events[k]) cudaEventDestroy(ctx->events[k]);
+	}
+	delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int insta_set_canonical(insta_ctx* ctx, const float* h_verts, uint32_t n_verts, const uint32_t* h_faces, uint32_t n_faces,
+                        const uint32_t* h_mask_ids) {
+	if (!ctx || !h_verts || !h_faces || n_verts == 0 || n_faces == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_set_canonical: bad arguments");
+	for (uint32_t i = 0; i < n_faces * 3; ++i)
+		if (h_faces[i] >= n_verts) INSTA_FAIL(INSTA_ERR_INVALID, "insta_set_canonical: face index out of range");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	int rc = insta_clear_frames(ctx);
+	if (rc) return rc;
+	ctx->n_verts = n_verts;
+	ctx->n_faces = n_faces;
+	ctx->canon_verts.assign(h_verts, h_verts + (size_t)n_verts * 3);
+	ctx->faces.assign(h_faces, h_faces + (size_t)n_faces * 3);
+	if (h_mask_ids) ctx->mask_ids.assign(h_mask_ids, h_mask_ids + n_faces);
+	else ctx->mask_ids.assign(n_faces, 15u);
+	ctx->canon_tris.resize(n_faces);
+	build_triangles(h_verts, h_faces, n_faces, ctx->mask_ids.data(), nullptr, ctx->canon_tris.data());
+	build_adjacency(h_faces, n_faces, n_verts, ctx->adjacency);
+	mesh_aabb(h_verts, n_verts, ctx->render_aabb);
+
+	for (void* p : {(void*)ctx->d_faces, (void*)ctx->d_mask_ids, (void*)ctx->d_adjacency, (void*)ctx->d_canon_area, (void*)ctx->d_canon_xf})
+		if (p) cudaFree(p);
+	ctx->d_faces = nullptr; ctx->d_mask_ids = nullptr; ctx->d_adjacency = nullptr; ctx->d_canon_area = nullptr; ctx->d_canon_xf = nullptr;
+	INSTA_CUDA(cudaMalloc(&ctx->d_faces, (size_t)n_faces * 12));
+	INSTA_CUDA(cudaMalloc(&ctx->d_mask_ids, (size_t)n_faces * 4));
+	INSTA_CUDA(cudaMalloc(&ctx->d_adjacency, (size_t)n_faces * 12));
+	INSTA_CUDA(cudaMalloc(&ctx->d_canon_area, (size_t)n_faces * 4));
+	INSTA_CUDA(cudaMalloc(&ctx->d_canon_xf, (size_t)n_faces * sizeof(TriXf)));
+	float* d_verts = nullptr;
+	INSTA_CUDA(cudaMalloc(&d_verts, (size_t)n_verts * 12));
+	cudaStream_t s = ctx->streams[0];
+	INSTA_CUDA(cudaMemcpyAsync(ctx->d_faces, h_faces, (size_t)n_faces * 12, cudaMemcpyHostToDevice, s));
+	INSTA_CUDA(cudaMemcpyAsync(ctx->d_mask_ids, ctx->mask_ids.data(), (size_t)n_faces * 4, cudaMemcpyHostToDevice, s));
+	INSTA_CUDA(cudaMemcpyAsync(ctx->d_adjacency, ctx->adjacency.data(), (size_t)n_faces * 12, cudaMemcpyHostToDevice, s));
+	INSTA_CUDA(cudaMemcpyAsync(d_verts, h_verts, (size_t)n_verts * 12, cudaMemcpyHostToDevice, s));
+	rc = launch_build_xf(ctx, d_verts, ctx->d_canon_xf, nullptr, ctx->d_canon_area, s);
+	cudaError_t e = cudaStreamSynchronize(s);
+	cudaFree(d_verts);
+	if (rc) return rc;
+	INSTA_CUDA(e);
+	return INSTA_OK;
+}
+
+int insta_load_canonical_obj(insta_ctx* ctx, const char* canonical_obj, const char* mesh_masks_dir) {
+	if (!ctx || !canonical_obj) INSTA_FAIL(INSTA_ERR_INVALID, "insta_load_canonical_obj: bad arguments");
+	std::vector<float> verts;
+	std::vector<uint32_t> faces, masks;
+	int rc = load_canonical_obj_host(canonical_obj, mesh_masks_dir, verts, faces, masks);
+	if (rc) return rc;
+	return insta_set_canonical(ctx, verts.data(), (uint32_t)(verts.size() / 3), faces.data(), (uint32_t)(faces.size() / 3),
+	                           masks.empty() ? nullptr : masks.data());
+}
+
+int insta_add_frame(insta_ctx* ctx, const float* h_verts, int32_t* frame_index) {
+	if (!ctx || !h_verts) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frame: bad arguments");
+	if (ctx->n_faces == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frame: set the canonical mesh first");
+	if (ctx->frames.size() >= ctx->p.max_cached_bvh) INSTA_FAIL(INSTA_ERR_CAPACITY, "insta_add_frame: max_cached_bvh frames already resident");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	HostBvh bvh;
+	prepare_frame(ctx, h_verts, bvh);
+	insta_ctx::Frame fr;
+	int rc = upload_frame(ctx, h_verts, bvh, fr);
+	if (rc) {
+		if (fr.slab) cudaFree(fr.slab);
+		return rc;
+	}
+	ctx->frames.push_back(std::move(fr));
+	ctx->frame_table_dirty = true;
+	if (frame_index) *frame_index = (int32_t)ctx->frames.size() - 1;
+	return INSTA_OK;
+}
+
+int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t n_threads) {
+	if (!ctx || !h_verts) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frames: bad arguments");
+	if (ctx->n_faces == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frames: set the canonical mesh first");
+	if (ctx->frames.size() + n > ctx->p.max_cached_bvh) INSTA_FAIL(INSTA_ERR_CAPACITY, "insta_add_frames: exceeds max_cached_bvh");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
+	n_threads = std::min(n_threads, std::max(1u, n));
+	const size_t per = (size_t)ctx->n_verts * 3;
+	// host BVH builds in parallel batches, uploads in order
+	const uint32_t batch = n_threads * 4;
+	for (uint32_t b0 = 0; b0 < n; b0 += batch) {
+		const uint32_t b1 = std::min(n, b0 + batch);
+		std::vector<HostBvh> built(b1 - b0);
+		std::atomic<uint32_t> next{b0};
+		std::vector<std::thread> pool;
+		for (uint32_t t = 0; t < n_threads; ++t)
+			pool.emplace_back([&]() {
+				for (uint32_t i; (i = next.fetch_add(1)) < b1;) prepare_frame(ctx, h_verts + per * i, built[i - b0]);
+			});
+		for (auto& t : pool) t.join();
+		for (uint32_t i = b0; i < b1; ++i) {
+			insta_ctx::Frame fr;
+			int rc = upload_frame(ctx, h_verts + per * i, built[i - b0], fr);
+			if (rc) {
+				if (fr.slab) cudaFree(fr.slab);
+				return rc;
+			}
+			ctx->frames.push_back(std::move(fr));
+		}
+	}
+	ctx->frame_table_dirty = true;
+	return INSTA_OK;
+}
+
+int insta_add_frame_obj(insta_ctx* ctx, const char* obj_path, int32_t* frame_index) {
+	if (!ctx || !obj_path) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frame_obj: bad arguments");
+	std::vector<float> verts, colors;
+	std::vector<uint32_t> faces;
+	std::string err;
+	if (!load_obj(obj_path, verts, colors, faces, err)) INSTA_FAIL(INSTA_ERR_IO, err);
+	if (verts.size() / 3 != ctx->n_verts) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frame_obj: vertex count differs from the canonical mesh");
+	for (float& v : verts) v = v * 1.0f + 0.5f;
+	return insta_add_frame(ctx, verts.data(), frame_index);
+}
+
+int insta_clear_frames(insta_ctx* ctx) {
+	if (!ctx) INSTA_FAIL(INSTA_ERR_INVALID, "ctx is null");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	INSTA_CUDA(cudaDeviceSynchronize());
+	for (auto& f : ctx->frames)
+		if (f.slab) cudaFree(f.slab);
+	ctx->frames.clear();
+	ctx->frame_table_dirty = true;
+	return INSTA_OK;
+}
+
+uint32_t insta_n_frames(const insta_ctx* ctx) { return ctx ? (uint32_t)ctx->frames.size() : 0; }
+
+int insta_get_render_aabb(const insta_ctx* ctx, float* h_aabb6) {
+	if (!ctx || !h_aabb6) INSTA_FAIL(INSTA_ERR_INVALID, "bad arguments");
+	memcpy(h_aabb6, ctx->render_aabb, 24);
+	return INSTA_OK;
+}
+
+int insta_set_aabb(insta_ctx* ctx, const float* h_aabb6) {
+	if (!ctx || !h_aabb6) INSTA_FAIL(INSTA_ERR_INVALID, "bad arguments");
+	memcpy(ctx->aabb, h_aabb6, 24);
+	return INSTA_OK;
+}
+
+int insta_get_topology(const insta_ctx* ctx, uint32_t* h_mask_ids, int32_t* h_adjacency) {
+	if (!ctx || ctx->n_faces == 0) INSTA_FAIL(INSTA_ERR_INVALID, "no canonical mesh");
+	if (h_mask_ids) memcpy(h_mask_ids, ctx->mask_ids.data(), (size_t)ctx->n_faces * 4);
+	if (h_adjacency) memcpy(h_adjacency, ctx->adjacency.data(), (size_t)ctx->n_faces * 12);
+	return INSTA_OK;
+}
+
+int insta_get_frame_bvh_order(const insta_ctx* ctx, int32_t frame, uint32_t* h_tri_ids, uint32_t* n_nodes) {
+	if (!ctx || frame < 0 || (size_t)frame >= ctx->frames.size()) INSTA_FAIL(INSTA_ERR_INVALID, "frame out of range");
+	const auto& f = ctx->frames[frame];
+	if (h_tri_ids) memcpy(h_tri_ids, f.bvh_order_ids.data(), f.bvh_order_ids.size() * 4);
+	if (n_nodes) *n_nodes = f.n_nodes;
+	return INSTA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int insta_deform_samples(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id, int32_t* d_tri_ids,
+                         insta_stream stream) {
+	if (!ctx || (!d_coords && n)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_samples: bad arguments");
+	const uint32_t extra = ctx->p.exp_params + ctx->p.geo_params;
+	if (stride_floats < 11 + extra) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_samples: stride smaller than NerfCoordinate + extra dims");
+	if (ctx->frames.empty()) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_samples: no frames loaded");
+	if (frame_id < -1) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_samples: frame_id must be >= -1");
+	int rc = sync_frame_table(ctx, (cudaStream_t)stream);
+	if (rc) return rc;
+	return launch_deform(ctx, d_coords, n, stride_floats, frame_id, nullptr, false, d_tri_ids, (cudaStream_t)stream);
+}
+
+int insta_deform_points(insta_ctx* ctx, float* d_xyz, uint32_t n, const int32_t* d_frame_ids, int32_t* d_tri_ids, insta_stream stream) {
+	if (!ctx || (!d_xyz && n)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_points: bad arguments");
+	if (ctx->frames.empty()) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_points: no frames loaded");
+	if (!d_frame_ids && ctx->frames.size() < 2) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_points: the reference's frame draw needs >= 2 frames");
+	int rc = sync_frame_table(ctx, (cudaStream_t)stream);
+	if (rc) return rc;
+	return launch_deform(ctx, d_xyz, n, 3, -1, d_frame_ids, true, d_tri_ids, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int insta_grid_layout(const insta_ctx* ctx, uint32_t* h_offsets, float* h_scales, uint32_t* h_resolutions) {
+	if (!ctx) INSTA_FAIL(INSTA_ERR_INVALID, "ctx is null");
+	const GridLevels& L = ctx->levels;
+	if (h_offsets) memcpy(h_offsets, L.offset, sizeof(uint32_t) * (L.n_levels + 1));
+	if (h_scales) memcpy(h_scales, L.scale, sizeof(float) * L.n_levels);
+	if (h_resolutions) memcpy(h_resolutions, L.res, sizeof(uint32_t) * L.n_levels);
+	return INSTA_OK;
+}
+
+uint32_t insta_grid_n_params(const insta_ctx* ctx) { return ctx ? ctx->levels.offset[ctx->levels.n_levels] * 8u : 0u; }
+
+int insta_hash_encode_fwd(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, const void* d_table_f16, void* d_out_soa_f16,
+                          insta_stream stream) {
+	if (!ctx || ((!d_pos || !d_table_f16 || !d_out_soa_f16) && n) || pos_stride_floats < 3) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_encode_fwd: bad arguments");
+	if (reinterpret_cast<uintptr_t>(d_table_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_encode_fwd: table must be 16-byte aligned");
+	return launch_hash_fwd(ctx, d_pos, pos_stride_floats, n, d_table_f16, d_out_soa_f16, (cudaStream_t)stream);
+}
+
+int insta_hash_encode_bwd(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, const void* d_dLdy_soa_f16,
+                          void* d_grad_table_f16, int zero_first, insta_stream stream) {
+	if (!ctx || !d_grad_table_f16 || ((!d_pos || !d_dLdy_soa_f16) && n) || pos_stride_floats < 3) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_encode_bwd: bad arguments");
+	if (reinterpret_cast<uintptr_t>(d_grad_table_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_encode_bwd: gradient table must be 16-byte aligned");
+	return launch_hash_bwd(ctx, d_pos, pos_stride_floats, n, d_dLdy_soa_f16, d_grad_table_f16, zero_first, (cudaStream_t)stream);
+}
+
+int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, uint32_t* d_slots, insta_stream stream) {
+	if (!ctx || ((!d_pos || !d_slots) && n) || pos_stride_floats < 3) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_slots: bad arguments");
+	return launch_hash_slots(ctx, d_pos, pos_stride_floats, n, d_slots, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-buffer path: chunks of the batch ping-pong between two streams so the H2D of chunk k+1 and the D2H of chunk
+// k-1 overlap the kernels of chunk k.  The SoA output is written per chunk with a 2-D copy (row pitch n).
+int insta_deform_encode_host(insta_ctx* ctx, float* h_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id, const void* d_table_f16,
+                             void* h_out_soa_f16) {
+	if (!ctx || !h_coords || !d_table_f16 || !h_out_soa_f16) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_encode_host: bad arguments");
+	if (ctx->frames.empty()) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_encode_host: no frames loaded");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	const uint32_t chunk = 1u << 19;  // 524,288 samples: 56.6 MB of records, 134 MB of encodings per chunk
+	int rc = ensure_stage(ctx, std::min(chunk, std::max(n, 1u)), stride_floats);
+	if (rc) return rc;
+	rc = sync_frame_table(ctx, ctx->streams[0]);
+	if (rc) return rc;
+	const uint32_t rows = ctx->levels.n_levels * 8;
+	uint32_t k = 0;
+	for (uint32_t first = 0; first < n; first += chunk, ++k) {
+		const uint32_t m = std::min(chunk, n - first);
+		const int b = k & 1;
+		cudaStream_t s = ctx->streams[b];
+		float* d_rec = ctx->d_stage_rec[b];
+		INSTA_CUDA(cudaMemcpyAsync(d_rec, h_coords + (size_t)first * stride_floats, (size_t)m * stride_floats * 4, cudaMemcpyHostToDevice, s));
+		rc = launch_deform(ctx, d_rec, m, stride_floats, frame_id, nullptr, false, nullptr, s);
+		if (rc) return rc;
+		rc = launch_hash_fwd(ctx, d_rec, stride_floats, m, d_table_f16, ctx->d_stage_enc[b], s);
+		if (rc) return rc;
+		INSTA_CUDA(cudaMemcpyAsync(h_coords + (size_t)first * stride_floats, d_rec, (size_t)m * stride_floats * 4, cudaMemcpyDeviceToHost, s));
+		INSTA_CUDA(cudaMemcpy2DAsync((__half*)h_out_soa_f16 + first, (size_t)n * 2, ctx->d_stage_enc[b], (size_t)m * 2, (size_t)m * 2, rows,
+		                             cudaMemcpyDeviceToHost, s));
+	}
+	INSTA_CUDA(cudaStreamSynchronize(ctx->streams[0]));
+	INSTA_CUDA(cudaStreamSynchronize(ctx->streams[1]));
+	return INSTA_OK;
+}
+
+int insta_host_alloc(void** p, uint64_t bytes) {
+	if (!p) INSTA_FAIL(INSTA_ERR_INVALID, "p is null");
+	INSTA_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+	return INSTA_OK;
+}
+
+int insta_host_free(void* p) {
+	INSTA_CUDA(cudaFreeHost(p));
+	return INSTA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-only utilities
+int insta_host_bvh_build(void* h_tris, uint32_t n_tris, uint32_t leaf, void* h_nodes, uint32_t max_nodes, uint32_t* n_nodes) {
+	if (!h_tris || n_tris == 0 || leaf == 0 || leaf > 7) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_bvh_build: bad arguments");
+	std::vector<Tri> tris((Tri*)h_tris, (Tri*)h_tris + n_tris);
+	HostBvh bvh;
+	build_bvh(tris, leaf, bvh);
+	if (n_nodes) *n_nodes = (uint32_t)bvh.nodes.size();
+	if (bvh.nodes.size() > max_nodes) INSTA_FAIL(INSTA_ERR_CAPACITY, "insta_host_bvh_build: node buffer too small");
+	if (h_nodes) memcpy(h_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node));
+	memcpy(h_tris, bvh.tris.data(), (size_t)n_tris * sizeof(Tri));
+	return INSTA_OK;
+}
+
+int insta_host_build_triangles(const float* h_verts, const uint32_t* h_faces, uint32_t n_faces, const uint32_t* h_mask_ids,
+                               const void* h_canonical_tris, void* h_tris_out) {
+	if (!h_verts || !h_faces || !h_tris_out) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_build_triangles: bad arguments");
+	build_triangles(h_verts, h_faces, n_faces, h_mask_ids, (const Tri*)h_canonical_tris, (Tri*)h_tris_out);
+	return INSTA_OK;
+}
+
+int insta_host_adjacency(const uint32_t* h_faces, uint32_t n_faces, uint32_t n_verts, int32_t* h_out) {
+	if (!h_faces || !h_out) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_adjacency: bad arguments");
+	std::vector<int32_t> adj;
+	build_adjacency(h_faces, n_faces, n_verts, adj);
+	memcpy(h_out, adj.data(), adj.size() * 4);
+	return INSTA_OK;
+}
+
+int insta_host_load_canonical_obj(const char* canonical_obj, const char* mesh_masks_dir, float* h_verts, uint32_t* h_faces, uint32_t* h_mask_ids,
+                                  uint32_t* n_verts, uint32_t* n_faces) {
+	if (!canonical_obj) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_load_canonical_obj: bad arguments");
+	std::vector<float> verts;
+	std::vector<uint32_t> faces, masks;
+	int rc = load_canonical_obj_host(canonical_obj, mesh_masks_dir, verts, faces, masks);
+	if (rc) return rc;
+	if (n_verts) *n_verts = (uint32_t)(verts.size() / 3);
+	if (n_faces) *n_faces = (uint32_t)(faces.size() / 3);
+	if (h_verts) memcpy(h_verts, verts.data(), verts.size() * 4);
+	if (h_faces) memcpy(h_faces, faces.data(), faces.size() * 4);
+	if (h_mask_ids) {
+		if (masks.empty()) masks.assign(faces.size() / 3, 15u);
+		memcpy(h_mask_ids, masks.data(), masks.size() * 4);
+	}
+	return INSTA_OK;
+}
+
+int insta_host_mesh_aabb(const float* h_verts, uint32_t n_verts, float* h_aabb6) {
+	if (!h_verts || !h_aabb6 || n_verts == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_mesh_aabb: bad arguments");
+	mesh_aabb(h_verts, n_verts, h_aabb6);
+	return INSTA_OK;
+}
+
+uint64_t insta_launch_count(const insta_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+}  // extern "C"

@@ -1,0 +1,158 @@
+// Internal definitions shared by the translation units of libinsta_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/insta_b200.h"
+
+namespace insta {
+
+// ---- error plumbing: status codes across the ABI, message kept per thread ---------------------------------
+void set_error(const std::string& msg);
+#define INSTA_FAIL(code, msg)            \
+	do {                                 \
+		::insta::set_error(msg);         \
+		return (code);                   \
+	} while (0)
+#define INSTA_CUDA(expr)                                                                                           \
+	do {                                                                                                           \
+		cudaError_t e__ = (expr);                                                                                  \
+		if (e__ != cudaSuccess) {                                                                                  \
+			::insta::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+			                   std::to_string(__LINE__) + ")");                                                    \
+			return INSTA_ERR_CUDA;                                                                                 \
+		}                                                                                                          \
+	} while (0)
+
+// ---- host-side mesh records -------------------------------------------------------------------------------
+// Byte-compatible with ngp::Triangle (ngp triangle.cuh:234-238) so that a caller may also hand over the
+// reference's own `triangles_gpu` buffers.
+struct Tri {
+	float a[3], b[3], c[3];
+	float scaling;
+	uint32_t id;
+	uint32_t mask_id;
+};
+static_assert(sizeof(Tri) == 48, "Tri must match ngp::Triangle");
+
+// Reference-layout BVH node (ngp triangle_bvh.cuh:29-33); used on the host during the build only.
+struct Node {
+	float mn[3], mx[3];
+	int32_t left_idx, right_idx;
+};
+
+// Device BVH node: the four children of one inner node of the reference's 4-ary tree, boxes stored SoA so that each
+// plane is one 128-bit load and the whole quad is exactly one 128-byte line.
+//   ref[k] >= 0 : index of the child's own Quad
+//   ref[k] <  0 : leaf, -(ref+1) = (first_triangle << 3) | count   (count <= 7)
+struct __align__(128) Quad {
+	float mnx[4], mny[4], mnz[4], mxx[4], mxy[4], mxz[4];
+	int32_t ref[4];
+	int32_t pad[4];
+};
+static_assert(sizeof(Quad) == 128, "Quad must be one cache line");
+
+// Per-triangle transform record (topology order): M = [ TBN * (scaling if mask_id == 1 else 1) | a ] exactly as
+// tri2projection builds it (include/rta/affine.cuh:26-39), plus the centroid used by the neighbour blend weights.
+struct __align__(16) TriXf {
+	float m[9];      // column-major 3x3
+	float a[3];      // translation (vertex a)
+	float c[3];      // centroid
+	uint32_t mask_id;
+};
+static_assert(sizeof(TriXf) == 64, "TriXf is four 128-bit loads");
+
+struct FrameDev {
+	const Quad* quads;
+	const Tri* tris;     // BVH order
+	const TriXf* xf;     // topology order
+	uint64_t pad;
+};
+
+struct HostBvh {
+	std::vector<Node> nodes;   // reference layout
+	std::vector<Quad> quads;   // device layout
+	std::vector<Tri> tris;     // BVH order
+};
+
+// mesh_host.cpp
+bool load_obj(const char* path, std::vector<float>& verts, std::vector<float>& colors, std::vector<uint32_t>& faces, std::string& err);
+void build_triangles(const float* verts, const uint32_t* faces, uint32_t n_faces, const uint32_t* mask_ids, const Tri* canonical, Tri* out);
+void build_adjacency(const uint32_t* faces, uint32_t n_faces, uint32_t n_verts, std::vector<int32_t>& out3);
+void masks_from_regions(const uint32_t* faces, uint32_t n_faces, const std::vector<std::pair<int, std::vector<uint32_t>>>& regions,
+                        std::vector<uint32_t>& out);
+void mesh_aabb(const float* verts, uint32_t n_verts, float* aabb6);
+void build_bvh(std::vector<Tri>& tris, uint32_t leaf_size, HostBvh& out);
+
+// ---- hash grid level descriptors (kernel parameter; <= 16 levels) --------------------------------------------
+constexpr int kMaxLevels = 16;
+struct GridLevels {
+	uint32_t n_levels;
+	uint32_t offset[kMaxLevels + 1];  // entries
+	uint32_t size[kMaxLevels];        // hashmap_size of the level (entries)
+	uint32_t res[kMaxLevels];         // grid_resolution
+	uint32_t mul1[kMaxLevels];        // dense stride of y (0 when the reference's loop stopped before it)
+	uint32_t mul2[kMaxLevels];        // dense stride of z (uint32 wrap-around preserved)
+	uint32_t hashed[kMaxLevels];      // 1 = fast_hash
+	float scale[kMaxLevels];
+};
+
+}  // namespace insta
+
+struct insta_ctx {
+	insta_params p{};
+	int device = 0;
+	int sm_count = 0;
+	// canonical
+	uint32_t n_verts = 0, n_faces = 0;
+	std::vector<float> canon_verts;
+	std::vector<uint32_t> faces, mask_ids;
+	std::vector<int32_t> adjacency;
+	std::vector<insta::Tri> canon_tris;  // topology order
+	float render_aabb[6] = {0, 0, 0, 1, 1, 1};
+	float aabb[6] = {0, 0, 0, 1, 1, 1};
+	uint32_t* d_faces = nullptr;
+	uint32_t* d_mask_ids = nullptr;
+	int32_t* d_adjacency = nullptr;
+	float* d_canon_area = nullptr;
+	insta::TriXf* d_canon_xf = nullptr;
+	// frames
+	struct Frame {
+		void* slab = nullptr;
+		insta::FrameDev dev{};
+		uint32_t n_nodes = 0, n_quads = 0;
+		std::vector<uint32_t> bvh_order_ids;
+	};
+	std::vector<Frame> frames;
+	insta::FrameDev* d_frame_table = nullptr;
+	uint32_t frame_table_cap = 0;
+	bool frame_table_dirty = false;
+	// grid
+	insta::GridLevels levels{};
+	// host-path staging
+	cudaStream_t streams[2] = {nullptr, nullptr};
+	cudaEvent_t events[2] = {nullptr, nullptr};
+	float* d_stage_rec[2] = {nullptr, nullptr};
+	void* d_stage_enc[2] = {nullptr, nullptr};
+	uint32_t stage_cap = 0, stage_stride = 0;
+	std::atomic<uint64_t> launches{0};
+	std::mutex mu;
+};
+
+namespace insta {
+// deform.cu
+int launch_build_xf(insta_ctx* ctx, const float* d_verts, TriXf* d_xf, const float* d_canon_area, float* d_area_out, cudaStream_t s);
+int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, int32_t frame_id, const int32_t* d_frame_ids,
+                  bool random_frames, int32_t* d_tri_ids, cudaStream_t s);
+// hashgrid.cu
+int init_grid_levels(insta_ctx* ctx);
+int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s);
+int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s);
+int launch_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, uint32_t* slots, cudaStream_t s);
+int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
+}  // namespace insta

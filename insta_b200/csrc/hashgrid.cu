@@ -1,0 +1,303 @@
+// Stage 2 of the INSTA hot path on sm_100a: multiresolution hash-grid encoding, forward and scatter-add backward.
+// Replaces tcnn::GridEncodingTemplated<__half,3,8>::forward_impl / backward_impl and the kernels kernel_grid /
+// kernel_grid_backward (tcnn include/tiny-cuda-nn/encodings/grid.h:138-310, 312-435, 874-1110), with fast_hash /
+// grid_index (grid.h:82-117) and pos_fract (tcnn common_device.h:415-431).
+//
+// Layout: the fp16 parameter table is borrowed from the caller in the reference's own order (entries x 8 features,
+// levels concatenated at the ctor's offsets), so a snapshot's params_binary can be used as is.  One entry = 16 bytes =
+// one 128-bit load per corner.  Forward: a thread owns one (sample pair, level); blockIdx.y = level so that all CTAs
+// resident at a time gather from the same <= 4 MB level table (L1-resident for the coarse levels, L2-resident for the
+// rest); outputs are written SoA with half2 (4-byte) coalesced streaming stores.
+//
+// Exactness: slot indices use the same uint32 arithmetic as grid_index, including its loop-exit rule and wrap-around;
+// the per-level scale is evaluated ON DEVICE with the reference kernel's expression (exp2f(l * log2(s)) * base - 1,
+// contracted by nvcc to one FFMA exactly as in the reference build) so floor() sees identical values; the
+// interpolation reproduces `result[f] += (half)(w * (float)table[f])` in corner order with fp16 accumulation.
+#include <cuda_fp16.h>
+
+#include <cmath>
+
+#include "ctx.h"
+
+namespace insta {
+namespace {
+
+constexpr int kFwdThreads = 256;
+constexpr int kBwdThreads = 256;
+
+__global__ void level_scale_kernel(uint32_t n_levels, float log2_per_level_scale, uint32_t base_resolution, float* out) {
+	const uint32_t level = threadIdx.x;
+	// same expression (and the same default contraction) as tcnn grid.h:188
+	if (level < n_levels) out[level] = exp2f(level * log2_per_level_scale) * base_resolution - 1.0f;
+}
+
+struct Corner {
+	uint32_t g[3];
+	float fr[3];
+};
+
+__device__ __forceinline__ Corner pos_fract3(float x, float y, float z, float scale) {
+	Corner c;
+	const float p[3] = {x, y, z};
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		const float v = fmaf(p[d], scale, 0.5f);
+		const float fl = floorf(v);
+		c.g[d] = (uint32_t)(int)fl;
+		c.fr[d] = v - fl;
+	}
+	return c;
+}
+
+template <bool HASHED>
+__device__ __forceinline__ uint32_t slot_of(uint32_t gx, uint32_t gy, uint32_t gz, uint32_t size, uint32_t mul1, uint32_t mul2) {
+	uint32_t idx;
+	if (HASHED) {
+		idx = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
+		return idx & (size - 1);  // hashed levels always have size == 2^log2_hashmap_size
+	}
+	idx = gx + gy * mul1 + gz * mul2;
+	return idx % size;
+}
+
+__device__ __forceinline__ uint4 ld_entry(const uint4* p) {
+	uint4 r;
+	asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_stream_u16(void* p, uint16_t v) { asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"(v) : "memory"); }
+
+// acc += (half2)(w * (float2)v)  per feature pair: fp32 multiply, round to fp16, fp16 add -- grid.h:257-259
+__device__ __forceinline__ void accum(__half2 acc[4], const uint4 v, float w) {
+	const uint32_t raw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw[k]));
+		acc[k] = __hadd2(acc[k], __floats2half2_rn(__fmul_rn(w, f.x), __fmul_rn(w, f.y)));
+	}
+}
+
+template <bool HASHED>
+__device__ __forceinline__ void encode_one(const uint4* __restrict__ table, const Corner& c, uint32_t size, uint32_t mul1, uint32_t mul2, __half2 acc[4]) {
+	uint4 v[8];
+	float w[8];
+#pragma unroll
+	for (uint32_t k = 0; k < 8; ++k) {
+		float wk = 1.0f;
+		uint32_t g[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			if ((k & (1u << d)) == 0) {
+				wk = __fmul_rn(wk, __fsub_rn(1.0f, c.fr[d]));
+				g[d] = c.g[d];
+			} else {
+				wk = __fmul_rn(wk, c.fr[d]);
+				g[d] = c.g[d] + 1;
+			}
+		}
+		w[k] = wk;
+		v[k] = ld_entry(table + slot_of<HASHED>(g[0], g[1], g[2], size, mul1, mul2));
+	}
+#pragma unroll
+	for (int k = 0; k < 4; ++k) acc[k] = __half2(__ushort_as_half(0), __ushort_as_half(0));
+#pragma unroll
+	for (int k = 0; k < 8; ++k) accum(acc, v[k], w[k]);
+}
+
+// grid: (ceil(n / 2 / kFwdThreads), n_levels); each thread encodes samples 2t and 2t+1 at level blockIdx.y
+template <bool HASHED>
+__device__ __forceinline__ void fwd_body(const GridLevels& L, uint32_t level, uint32_t n, const float* __restrict__ pos, uint32_t stride,
+                                         const uint4* __restrict__ table, __half* __restrict__ out) {
+	const uint32_t i0 = (blockIdx.x * kFwdThreads + threadIdx.x) * 2;
+	if (i0 >= n) return;
+	const bool two = i0 + 1 < n;
+	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
+	const float scale = L.scale[level];
+	table += L.offset[level];
+	const float* p0 = pos + (size_t)i0 * stride;
+	const float* p1 = p0 + (two ? stride : 0);
+	const Corner c0 = pos_fract3(__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2), scale);
+	const Corner c1 = pos_fract3(__ldg(p1), __ldg(p1 + 1), __ldg(p1 + 2), scale);
+	__half2 a0[4], a1[4];
+	encode_one<HASHED>(table, c0, size, mul1, mul2, a0);
+	encode_one<HASHED>(table, c1, size, mul1, mul2, a1);
+	__half* o = out + (size_t)(level * 8) * n + i0;
+	if (two && (n % 2u == 0)) {
+		// rows start at even element offsets -> 4-byte aligned pair stores
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const __half2 lo = __lows2half2(a0[k], a1[k]), hi = __highs2half2(a0[k], a1[k]);
+			st_stream_u32(o + (size_t)(2 * k) * n, *reinterpret_cast<const uint32_t*>(&lo));
+			st_stream_u32(o + (size_t)(2 * k + 1) * n, *reinterpret_cast<const uint32_t*>(&hi));
+		}
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			st_stream_u16(o + (size_t)(2 * k) * n, __half_as_ushort(__low2half(a0[k])));
+			st_stream_u16(o + (size_t)(2 * k + 1) * n, __half_as_ushort(__high2half(a0[k])));
+			if (two) {
+				st_stream_u16(o + (size_t)(2 * k) * n + 1, __half_as_ushort(__low2half(a1[k])));
+				st_stream_u16(o + (size_t)(2 * k + 1) * n + 1, __half_as_ushort(__high2half(a1[k])));
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kFwdThreads) hash_fwd_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
+                                                               uint32_t stride, const uint4* __restrict__ table, __half* __restrict__ out) {
+	const uint32_t level = blockIdx.y;
+	if (L.hashed[level]) fwd_body<true>(L, level, n, pos, stride, table, out);
+	else fwd_body<false>(L, level, n, pos, stride, table, out);
+}
+
+__global__ void __launch_bounds__(256) hash_slots_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
+                                                         uint32_t stride, uint32_t* __restrict__ slots) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t level = blockIdx.y;
+	if (i >= n) return;
+	const float* p = pos + (size_t)i * stride;
+	const Corner c = pos_fract3(__ldg(p), __ldg(p + 1), __ldg(p + 2), L.scale[level]);
+	for (uint32_t k = 0; k < 8; ++k) {
+		const uint32_t gx = c.g[0] + (k & 1u), gy = c.g[1] + ((k >> 1) & 1u), gz = c.g[2] + ((k >> 2) & 1u);
+		const uint32_t s = L.hashed[level] ? slot_of<true>(gx, gy, gz, L.size[level], 0, 0) : slot_of<false>(gx, gy, gz, L.size[level], L.mul1[level], L.mul2[level]);
+		slots[((size_t)i * L.n_levels + level) * 8 + k] = L.offset[level] + s;
+	}
+}
+
+// one 16-byte vector reduction per corner: 8 fp16 adds performed atomically at L2 (sm_90+)
+__device__ __forceinline__ void red_add_v4_f16x2(void* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+	asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// grid: (ceil(n / kBwdThreads), n_levels); thread = (sample, level), all 8 features
+template <bool HASHED>
+__device__ __forceinline__ void bwd_body(const GridLevels& L, uint32_t level, uint32_t n, const float* __restrict__ pos, uint32_t stride,
+                                         const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
+	const uint32_t i = blockIdx.x * kBwdThreads + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
+	grad += L.offset[level];
+	const float* p = pos + (size_t)i * stride;
+	const Corner c = pos_fract3(__ldg(p), __ldg(p + 1), __ldg(p + 2), L.scale[level]);
+	float g[8];
+#pragma unroll
+	for (int f = 0; f < 8; ++f) g[f] = __half2float(dLdy[(size_t)(level * 8 + f) * n + i]);
+	bool any = false;
+#pragma unroll
+	for (int f = 0; f < 8; ++f) any |= (g[f] != 0.0f);
+	if (!any) return;  // adding +0 to every slot is a no-op
+#pragma unroll
+	for (uint32_t k = 0; k < 8; ++k) {
+		float wk = 1.0f;
+		uint32_t q[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			if ((k & (1u << d)) == 0) {
+				wk = __fmul_rn(wk, __fsub_rn(1.0f, c.fr[d]));
+				q[d] = c.g[d];
+			} else {
+				wk = __fmul_rn(wk, c.fr[d]);
+				q[d] = c.g[d] + 1;
+			}
+		}
+		uint32_t packed[4];
+#pragma unroll
+		for (int h = 0; h < 4; ++h) {
+			const __half2 v = __floats2half2_rn(__fmul_rn(g[2 * h], wk), __fmul_rn(g[2 * h + 1], wk));  // grid.h:352
+			packed[h] = *reinterpret_cast<const uint32_t*>(&v);
+		}
+		red_add_v4_f16x2(grad + slot_of<HASHED>(q[0], q[1], q[2], size, mul1, mul2), packed[0], packed[1], packed[2], packed[3]);
+	}
+}
+
+__global__ void __launch_bounds__(kBwdThreads) hash_bwd_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
+                                                               uint32_t stride, const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
+	const uint32_t level = blockIdx.y;
+	if (L.hashed[level]) bwd_body<true>(L, level, n, pos, stride, dLdy, grad);
+	else bwd_body<false>(L, level, n, pos, stride, dLdy, grad);
+}
+
+}  // namespace
+
+// Offset table exactly as the ctor builds it (grid.h:898-922), with the per-level scale taken from the device.
+int init_grid_levels(insta_ctx* ctx) {
+	const insta_params& p = ctx->p;
+	if (p.n_levels == 0 || p.n_levels > (uint32_t)kMaxLevels) INSTA_FAIL(INSTA_ERR_INVALID, "n_levels must be in 1..16");
+	if (p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "only n_features_per_level == 8 is implemented");
+	if (p.log2_hashmap_size < 4 || p.log2_hashmap_size > 28) INSTA_FAIL(INSTA_ERR_INVALID, "log2_hashmap_size out of range");
+	float pls = p.per_level_scale;
+	if (pls <= 0.f) {
+		// ngp/src/testbed.cu:2246-2258: desired_resolution 2048
+		pls = std::exp(std::log(2048.0f * (float)p.aabb_scale / (float)p.base_resolution) / (float)(p.n_levels - 1));
+		ctx->p.per_level_scale = pls;
+	}
+	float* d_scales = nullptr;
+	INSTA_CUDA(cudaMalloc(&d_scales, sizeof(float) * kMaxLevels));
+	level_scale_kernel<<<1, 32>>>(p.n_levels, std::log2(pls), p.base_resolution, d_scales);
+	ctx->launches++;
+	float scales[kMaxLevels];
+	cudaError_t e = cudaMemcpy(scales, d_scales, sizeof(float) * kMaxLevels, cudaMemcpyDeviceToHost);
+	cudaFree(d_scales);
+	INSTA_CUDA(e);
+
+	GridLevels& L = ctx->levels;
+	L = GridLevels{};
+	L.n_levels = p.n_levels;
+	uint32_t offset = 0;
+	for (uint32_t l = 0; l < p.n_levels; ++l) {
+		const float scale = scales[l];
+		const uint32_t res = (uint32_t)std::ceil(scale) + 1;
+		const uint32_t max_params = 0xffffffffu / 2;
+		uint32_t params = std::pow((float)res, 3) > (float)max_params ? max_params : res * res * res;
+		params = (params + 7u) / 8u * 8u;
+		params = std::min(params, 1u << p.log2_hashmap_size);
+		// grid_index's loop (grid.h:105-110) in the same uint32 arithmetic, to learn which dims it accumulates
+		uint32_t stride = 1, mul[3] = {0, 0, 0};
+		for (uint32_t dim = 0; dim < 3 && stride <= params; ++dim) {
+			mul[dim] = stride;
+			stride *= res;
+		}
+		L.offset[l] = offset;
+		L.size[l] = params;
+		L.res[l] = res;
+		L.mul1[l] = mul[1];
+		L.mul2[l] = mul[2];
+		L.hashed[l] = params < stride ? 1u : 0u;
+		L.scale[l] = scale;
+		if (L.hashed[l] && (params & (params - 1)) != 0) INSTA_FAIL(INSTA_ERR_INVALID, "hashed level with a non power-of-two size");
+		offset += params;
+	}
+	L.offset[p.n_levels] = offset;
+	return INSTA_OK;
+}
+
+int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s) {
+	if (n == 0) return INSTA_OK;
+	const dim3 grid(((n + 1) / 2 + kFwdThreads - 1) / kFwdThreads, ctx->levels.n_levels);
+	hash_fwd_kernel<<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s) {
+	if (zero_first) INSTA_CUDA(cudaMemsetAsync(grad, 0, (size_t)ctx->levels.offset[ctx->levels.n_levels] * 16, s));
+	if (n == 0) return INSTA_OK;
+	const dim3 grid((n + kBwdThreads - 1) / kBwdThreads, ctx->levels.n_levels);
+	hash_bwd_kernel<<<grid, kBwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const __half*)dLdy, (uint4*)grad);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+int launch_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, uint32_t* slots, cudaStream_t s) {
+	if (n == 0) return INSTA_OK;
+	const dim3 grid((n + 255) / 256, ctx->levels.n_levels);
+	hash_slots_kernel<<<grid, 256, 0, s>>>(ctx->levels, n, d_pos, stride, slots);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+}  // namespace insta

@@ -1,0 +1,111 @@
+"""Synthetic inputs for the INSTA hot path (the avatar datasets are gated): the canonical FLAME template shipped in
+mesh_masks/canonical.obj (compacted to assets/flame_canonical.npz by tools/make_assets.py), randomly perturbed
+per-frame vertex sets, sample records, cameras and grid weights.  Definitions follow SURVEY.md 8(d).
+
+Everything here is deterministic numpy; nothing touches the GPU.
+"""
+import os
+
+import numpy as np
+
+_ASSET = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "flame_canonical.npz")
+
+N_EXTRA_DIMS = 16               # exp_params, configs/nerf/main.json:17
+RECORD_FLOATS = 11 + N_EXTRA_DIMS  # NerfCoordinate (nerf.h:86-115) + extra dims = 27 floats = 108 B
+
+
+def load_canonical():
+    """Returns (verts float32 [5023,3] already offset by +0.5 as TinyMesh::load does (tiny_mesh.cu:63-74),
+    faces uint32 [8090,3], regions {FlameMasks id: red vertex ids})."""
+    z = np.load(_ASSET)
+    verts = (z["verts"].astype(np.float32) * np.float32(1.0) + np.float32(0.5)).astype(np.float32)
+    regions = {int(k.split("_")[1]): z[k] for k in z.files if k.startswith("region_")}
+    return verts, z["faces"].astype(np.uint32), regions
+
+
+def mask_ids_from_regions(faces, regions):
+    """Per-triangle FlameMasks id, masking.cpp:118-148: start at Torso (15); regions in ascending id order; a face takes
+    the id of every region holding one of its vertices, later regions overwriting earlier ones."""
+    out = np.full(len(faces), 15, np.uint32)
+    for rid in sorted(regions):
+        sel = np.zeros(int(faces.max()) + 1, bool)
+        sel[regions[rid]] = True
+        out[sel[faces].any(axis=1)] = rid
+    return out
+
+
+def _vertex_smoother(faces, n_verts):
+    import scipy.sparse as sp
+
+    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]]).astype(np.int64)
+    e = np.concatenate([e, e[:, ::-1]])
+    A = sp.coo_matrix((np.ones(len(e), np.float64), (e[:, 0], e[:, 1])), shape=(n_verts, n_verts)).tocsr()
+    A.data[:] = 1.0
+    A = A + sp.identity(n_verts)
+    d = np.asarray(A.sum(axis=1)).ravel()
+    return sp.diags(1.0 / d) @ A
+
+
+class FrameSynth:
+    """v_f = R_f (v - c) + c + smooth(0.003 * N(0,1)),  R_f a random-axis rotation of <= 5 degrees, seed = frame id."""
+
+    def __init__(self, verts, faces, sigma=0.003, max_deg=5.0, smooth_iters=3):
+        self.verts = verts.astype(np.float32)
+        self.S = _vertex_smoother(faces, len(verts))
+        self.sigma, self.max_deg, self.iters = sigma, max_deg, smooth_iters
+        self.center = self.verts.mean(axis=0, dtype=np.float64)
+
+    def frame(self, f):
+        rng = np.random.default_rng(100003 + int(f))
+        noise = rng.standard_normal(self.verts.shape) * self.sigma
+        for _ in range(self.iters):
+            noise = self.S @ noise
+        axis = rng.standard_normal(3)
+        axis /= np.linalg.norm(axis)
+        ang = np.deg2rad(rng.uniform(-self.max_deg, self.max_deg))
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+        v = (self.verts.astype(np.float64) - self.center) @ R.T + self.center + noise
+        return v.astype(np.float32)
+
+
+def mesh_aabb(verts):
+    """TinyMesh render AABB: vertex bounds inflated by 0.15 * |diag| (tiny_mesh.cu:157-162); fp32."""
+    mn = verts.min(axis=0).astype(np.float32)
+    mx = verts.max(axis=0).astype(np.float32)
+    d = (mx - mn).astype(np.float32)
+    amount = np.float32(np.sqrt(np.float32(d[0] * d[0]) + (np.float32(d[1] * d[1]) + np.float32(d[2] * d[2])))) * np.float32(0.15)
+    return np.concatenate([mn - amount, mx + amount]).astype(np.float32)
+
+
+def make_records(n, aabb6, frame_ids, seed=7, pad_fraction=0.0):
+    """n sample records of 27 floats: pos ~ U(aabb), dt, holder = frame id, deformed_pos = pos, dir = (d+1)/2 with d uniform
+    on the sphere, 16 expression floats ~ N(0,1).  pad_fraction of the records get holder = -1 (padding, skipped)."""
+    rng = np.random.default_rng(seed)
+    rec = np.empty((n, RECORD_FLOATS), np.float32)
+    lo, hi = aabb6[:3].astype(np.float64), aabb6[3:].astype(np.float64)
+    pos = (lo + (hi - lo) * rng.random((n, 3))).astype(np.float32)
+    rec[:, 0:3] = pos
+    rec[:, 3] = np.float32(0.0)
+    rec[:, 4] = np.asarray(frame_ids, np.float32)
+    rec[:, 5:8] = pos
+    d = rng.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rec[:, 8:11] = ((d + 1.0) * 0.5).astype(np.float32)
+    rec[:, 11:] = rng.standard_normal((n, N_EXTRA_DIMS)).astype(np.float32)
+    if pad_fraction > 0:
+        rec[rng.random(n) < pad_fraction, 4] = -1.0
+    return rec
+
+
+def train_regime_frame_ids(n, n_frames):
+    """Runs of consecutive samples per frame (2^18 rays over n_frames images x ~16 samples/ray)."""
+    run = max(1, -(-n // n_frames))
+    return (np.arange(n) // run).astype(np.int32) % n_frames
+
+
+def make_grid_table(n_entries, seed=1337, scale=1.0):
+    """fp16 table [n_entries, 8] ~ U(-scale, scale).  tcnn initialises U(-1e-4, 1e-4) (grid.h:1275-1280); the default
+    here is the U(+-1) variant so encodings are non-trivial."""
+    rng = np.random.default_rng(seed)
+    return ((rng.random((n_entries, 8), dtype=np.float32) * 2 - 1) * np.float32(scale)).astype(np.float16)
