@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- deformed+encoded samples/s of the INSTA hot path (BVH + TBN + hash grid) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--regime train|render] [--frames F]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One step = stage 1 (insta_deform_samples) + stage 2 forward (insta_hash_encode_fwd) over one batch of 4,194,304 sample
+records (BASELINE.json configs[1]) that is already resident in HBM.  Rank 0 prints ONE JSON line.
+`--impl reference` times the reference's own CPU implementation of the path on the host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES = 1 << 22           # 4,194,304 = max_samples of a training step (ngp testbed_nerf.cu:3172)
+STRIDE = 27
+# algorithmic bytes per sample, SURVEY.md 8(d) / BASELINE.md 2.4
+BYTES_DEFORM = 1012
+BYTES_DEFORM_BLEND = 1300
+BYTES_ENCODE = 2316
+METRIC = "deformed+encoded samples/s (BVH+TBN+hash)"
+UNIT = "samples/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                inside = t0 - 0.05 <= ts <= t1 + 0.15
+                if inside:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:  # region shorter than the sampling period: fall back to every sample taken
+            for ts, line in self.lines:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_scene(n_frames, rank, world):
+    """Canonical mesh + this rank's shard of the synthetic frames (rank r holds frames r, r+R, ...: SURVEY.md 8e)."""
+    from insta_b200 import synth
+
+    verts, faces, regions = synth.load_canonical()
+    masks = synth.mask_ids_from_regions(faces, regions)
+    fs = synth.FrameSynth(verts, faces)
+    mine = list(range(rank, n_frames, world))
+    fv = np.stack([fs.frame(f) for f in mine]) if mine else np.zeros((0,) + verts.shape, np.float32)
+    return verts, faces, masks, fv
+
+
+def make_batch(verts, n, n_local_frames, regime, seed):
+    from insta_b200 import synth
+
+    aabb = synth.mesh_aabb(verts)
+    if regime == "render":
+        fids = np.zeros(n, np.int32)
+    else:
+        fids = synth.train_regime_frame_ids(n, n_local_frames)
+    return synth.make_records(n, aabb, fids, seed=seed, pad_fraction=0.0), aabb
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_leg(verts, faces, masks, frame_verts, n_sample, steps, warmup, regime):
+    """The reference's CPU implementation of the path on the host cores: its own host-compiled TriangleBvh /
+    closest_triangle / affine math (oracle/_ref/libref_host.so, kind 'reference') or the oracle port when that library
+    is absent, plus the CPU restatement of kernel_grid (the reference has no host hash grid).  All host threads."""
+    from insta_b200 import synth
+    from oracle import pyoracle
+
+    O = pyoracle.Oracle()
+    kind = "port"
+    W = O
+    if pyoracle.have_ref_host():
+        try:
+            W = pyoracle.RefHost()
+            kind = "reference"
+        except OSError:
+            W = O
+    canon = O.build_triangles(verts, faces, masks)
+    adj = O.adjacency(faces, len(verts))
+    nodes, tbvh, ttopo = [], [], []
+    for v in frame_verts:
+        t = O.build_triangles(v, faces, masks, canon)
+        nn, tb = W.bvh_build(t)
+        nodes.append(nn); tbvh.append(tb); ttopo.append(t)
+    layout = O.grid_layout()
+    table = synth.make_grid_table(int(layout[0][-1]))
+    rec0, _ = make_batch(verts, n_sample, len(frame_verts), regime, seed=7)
+    unit = np.array([0, 0, 0, 1, 1, 1], np.float32)
+    threads = W.max_threads
+    times = []
+    for it in range(warmup + steps):
+        rec = rec0.copy()
+        t0 = time.perf_counter()
+        W.warp(rec, STRIDE, -1 if regime != "render" else 0, nodes, tbvh, ttopo, canon, adj, unit, n_threads=threads)
+        O.grid_forward(rec, STRIDE, layout, table, n_threads=threads)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    total = float(np.sum(times))
+    return {"value": n_sample * len(times) / total, "unit": UNIT, "cores": int(threads), "kind": kind,
+            "sample": "%d of the %d records per step x %d steps, same seed/regime; stage 1 = %s, stage 2 = CPU restatement of kernel_grid" % (
+                n_sample, N_SAMPLES, len(times), "reference host code (libref_host.so)" if kind == "reference" else "oracle port")}, total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n_frames = min(args.frames, 64)  # host BVH builds only for the frames the bounded sample touches
+    verts, faces, masks, fv = build_scene(n_frames, 0, 1)
+    n_sample = args.cpu_sample
+    cb, sec_per_step = cpu_reference_leg(verts, faces, masks, list(fv), n_sample, args.steps, args.warmup, args.regime)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f16", "data": "synthetic",
+            "config": {"workload": workload_name(args, n_frames), "batch_samples": N_SAMPLES, "cpu_sample_per_step": n_sample},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(args, n_frames):
+    return "configs[1]: closest-triangle + TBN deformation + 16-level hash-grid encode, %d sample records x 27 floats, %s regime (%s), canonical.obj %d frames" % (
+        N_SAMPLES, args.regime, "runs of consecutive samples per frame" if args.regime == "train" else "single frame", n_frames)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from insta_b200 import capi, synth
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    capi.load_library(build_if_missing=False)
+    n_frames = args.frames if args.regime == "train" else 1
+    verts, faces, masks, fv = build_scene(n_frames, rank, world)
+    ctx = capi.Context(device=local)
+    ctx.set_canonical(verts, faces, masks)
+    ctx.add_frames(fv)
+    n_local = ctx.n_frames
+    layout = ctx.grid_layout()
+    n_entries = int(layout[0][-1])
+    table = torch.from_numpy(synth.make_grid_table(n_entries)).cuda()
+    rec_np, aabb = make_batch(verts, N_SAMPLES, n_local, args.regime, seed=7 + rank)
+    K, W = args.steps, args.warmup
+    n_buf = min(K + W, args.max_buffers)
+    # every step gets its own pristine copy of the batch (the hooks mutate records in place): inputs resident in HBM
+    pristine = torch.from_numpy(rec_np).cuda()
+    bufs = [pristine.clone() for _ in range(n_buf)]
+    out = torch.empty((128, N_SAMPLES), dtype=torch.float16, device="cuda")
+    frame_id = -1 if args.regime == "train" else 0
+    stream = torch.cuda.current_stream()
+
+    def step(buf, ev=None):
+        if ev:
+            ev[0].record(stream)
+        if frame_id < 0:
+            ctx.surface_closest_point(buf)
+        else:
+            ctx.render_deformed(buf, frame_id)
+        if ev:
+            ev[1].record(stream)
+        ctx.hash_encode_fwd(buf, table, out)
+        if ev:
+            ev[2].record(stream)
+
+    for w in range(W):
+        step(bufs[w % n_buf])
+    torch.cuda.synchronize()
+    # if there are fewer buffers than steps, re-fill them from the pristine copy outside the timed region
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for b in bufs:
+        b.copy_(pristine)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    launches0 = ctx.launch_count
+    barrier()
+    t0 = time.time()
+    done = 0
+    while done < K:
+        m = min(n_buf, K - done)
+        for k in range(m):
+            step(bufs[k], evs[done + k])
+        done += m
+        if done < K:  # only when --max-buffers < steps: refill is excluded from the event timing below
+            torch.cuda.synchronize()
+            for b in bufs:
+                b.copy_(pristine)
+            torch.cuda.synchronize()
+    barrier()
+    t1 = time.time()
+    launches = ctx.launch_count - launches0
+    t_deform = np.array([e[0].elapsed_time(e[1]) for e in evs])
+    t_encode = np.array([e[1].elapsed_time(e[2]) for e in evs])
+    step_ms = t_deform + t_encode
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms_max = float(t.item())
+    else:
+        total_ms_max = total_ms
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region) ----
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    h_rec0 = torch.from_numpy(rec_np).pin_memory()
+    h_rec = torch.empty_like(h_rec0).pin_memory()
+    h_out = torch.empty((128, N_SAMPLES), dtype=torch.float16).pin_memory()
+    e2e_t = []
+    for it in range(1 + e2e_steps):
+        h_rec.copy_(h_rec0)
+        barrier()
+        a = time.perf_counter()
+        ctx.deform_encode_host(h_rec, frame_id, table, h_out)
+        b = time.perf_counter()
+        if it >= 1:
+            e2e_t.append(b - a)
+    e2e_total = float(np.sum(e2e_t))
+    if world > 1:
+        t = torch.tensor([e2e_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = world * N_SAMPLES * len(e2e_t) / e2e_total
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # dominant kernel = the one with the larger share of the step
+        blend_frac = None
+        if t_encode.mean() >= t_deform.mean():
+            dom, dom_ms, dom_bytes = "hash_fwd_kernel", float(t_encode.mean()), BYTES_ENCODE * N_SAMPLES
+        else:
+            dom, dom_ms, dom_bytes = "deform_kernel", float(t_deform.mean()), BYTES_DEFORM * N_SAMPLES
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * N_SAMPLES * K / (total_ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f16", "data": "synthetic",
+            "config": {"workload": workload_name(args, n_frames), "batch_samples_per_gpu": N_SAMPLES, "frames_per_gpu": n_local,
+                       "l2": "inputs larger than L2 (453 MB records + 1.07 GB encodings per step, fresh record buffer each step)",
+                       "timing": "CUDA events on the launching stream per kernel, summed over steps, max over ranks"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
+                         "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},
+            "kernels_ms": {"deform_kernel": float(t_deform.mean()), "hash_fwd_kernel": float(t_encode.mean())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_SAMPLES * STRIDE * 4,
+                    "d2h_bytes_per_step": N_SAMPLES * STRIDE * 4 + N_SAMPLES * 128 * 2, "steps": len(e2e_t)},
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t1 - t0,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, _ = cpu_reference_leg(verts, faces, masks, list(fv[: min(len(fv), 64)]), args.cpu_sample, 3, 1, args.regime)
+                line["cpu_baseline"] = cb
+            except Exception as e:  # the checker is optional for the measurement itself
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        if world == 1 and args.ref_cuda:
+            try:
+                line["ref_cuda"] = ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args)
+            except Exception as e:
+                line["ref_cuda"] = {"error": repr(e)}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args):
+    """Reported beside ours: the reference's own CUDA kernels (`warp` + kernel_grid) recompiled for sm_100, same buffers."""
+    import torch
+
+    from oracle import pyoracle, pyrefcuda
+
+    if not pyrefcuda.available():
+        return {"unavailable": "oracle/_ref/libref_cuda.so not built"}
+    O = pyoracle.Oracle()
+    canon = O.build_triangles(verts, faces, masks)
+    adj = O.adjacency(faces, len(verts))
+    nodes, tbvh, ttopo = [], [], []
+    for v in fv:
+        t = O.build_triangles(v, faces, masks, canon)
+        nn, tb = O.bvh_build(t)
+        nodes.append(nn); tbvh.append(tb); ttopo.append(t)
+    R = pyrefcuda.RefCuda()
+    R.upload_scene(nodes, tbvh, ttopo, canon, adj)
+    pristine = torch.from_numpy(rec_np).cuda()
+    buf = pristine.clone()
+    fid = -1 if args.regime == "train" else 0
+    ts_w, ts_g = [], []
+    for it in range(2 + 5):
+        buf.copy_(pristine)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        R.warp(buf, STRIDE, fid)
+        e[1].record()
+        R.grid_forward(buf, STRIDE, table, out)
+        e[2].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            ts_w.append(e[0].elapsed_time(e[1]))
+            ts_g.append(e[1].elapsed_time(e[2]))
+    ms = float(np.mean(ts_w) + np.mean(ts_g))
+    return {"value": N_SAMPLES / (ms * 1e-3), "unit": UNIT, "warp_ms": float(np.mean(ts_w)), "kernel_grid_ms": float(np.mean(ts_g)),
+            "note": "reference `warp` (src/core.cu:442) + kernel_grid (tcnn grid.h:138), nvcc 12.9 -arch=sm_100, identical device buffers"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--regime", default="train", choices=["train", "render"])
+    ap.add_argument("--frames", type=int, default=1700, help="frames in the working set (max_images_gpu, configs/nerf/insta.json:5)")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 17, help="records per step of the CPU legs")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--max-buffers", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-cuda", action="store_true", default=True)
+    ap.add_argument("--no-ref-cuda", dest="ref_cuda", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#ifdef __F16C__
+#include <immintrin.h>
+#endif
 
 namespace {
 
@@ -317,7 +320,18 @@ inline uint16_t f64_to_f16(double x) {
 	if (base >= 31) return sign | 0x7c00u;
 	return sign | (uint16_t)((base << 10) | (q - 1024));
 }
-inline uint16_t hadd(uint16_t a, uint16_t b) { return f64_to_f16((double)orc_f16_to_f32(a) + (double)orc_f16_to_f32(b)); }
+inline uint16_t hadd_soft(uint16_t a, uint16_t b) { return f64_to_f16((double)orc_f16_to_f32(a) + (double)orc_f16_to_f32(b)); }
+#ifdef __F16C__
+// Hardware conversions (round-to-nearest-even, subnormals kept).  fp16 add = fp32 add + one conversion: rounding twice
+// is innocuous because fp32 carries 24 >= 2*11+2 significand bits.
+inline float h2f(uint16_t h) { return _cvtsh_ss(h); }
+inline uint16_t f2h(float f) { return _cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC); }
+inline uint16_t hadd(uint16_t a, uint16_t b) { return f2h(h2f(a) + h2f(b)); }
+#else
+inline float h2f(uint16_t h) { return orc_f16_to_f32(h); }
+inline uint16_t f2h(float f) { return orc_f32_to_f16(f); }
+inline uint16_t hadd(uint16_t a, uint16_t b) { return hadd_soft(a, b); }
+#endif
 
 // pos_fract, tcnn common_device.h:425-431.  `input * scale + 0.5f` is a single FFMA in the reference's CUDA build
 // (the only build of this function that exists), hence fmaf.
@@ -631,10 +645,29 @@ void orc_grid_forward(uint32_t n, const float* pos, uint32_t pos_stride, uint32_
 					else { w *= fr[d]; gl[d] = g[d] + 1; }
 				}
 				const uint16_t* e = table + ((size_t)offsets[l] + grid_entry(hs, resolutions[l], gl)) * 8;
-				for (int f = 0; f < 8; ++f) acc[f] = hadd(acc[f], orc_f32_to_f16(w * orc_f16_to_f32(e[f])));  // grid.h:257-259
+				for (int f = 0; f < 8; ++f) acc[f] = hadd(acc[f], f2h(w * h2f(e[f])));  // grid.h:257-259
 			}
 			for (int f = 0; f < 8; ++f) out[(size_t)i + (size_t)(l * 8 + f) * n] = acc[f];                   // grid.h:265
 		}
+}
+
+// software vs hardware fp16 paths (self-check for tests): returns the number of mismatches over a sweep
+uint32_t orc_f16_selfcheck(uint32_t n, uint32_t seed) {
+	uint32_t bad = 0, x = seed * 2654435761u + 1u;
+	for (uint32_t i = 0; i < n; ++i) {
+		x = x * 1664525u + 1013904223u;
+		uint16_t a = (uint16_t)(x >> 16);
+		x = x * 1664525u + 1013904223u;
+		uint16_t b = (uint16_t)(x >> 16);
+		if ((a & 0x7c00u) == 0x7c00u || (b & 0x7c00u) == 0x7c00u) continue;
+		if (hadd(a, b) != hadd_soft(a, b)) ++bad;
+		float f;
+		uint32_t u = x ^ (x << 13);
+		memcpy(&f, &u, 4);
+		if (f == f && f2h(f) != orc_f32_to_f16(f)) ++bad;
+		if (h2f(a) != orc_f16_to_f32(a)) ++bad;
+	}
+	return bad;
 }
 
 void orc_grid_backward(uint32_t n, const float* pos, uint32_t pos_stride, uint32_t n_levels, const uint32_t* offsets, const float* scales,

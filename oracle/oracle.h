@@ -76,6 +76,7 @@ void orc_grid_backward(uint32_t n, const float* pos, uint32_t pos_stride, uint32
                        const float* scales, const uint32_t* resolutions, const uint16_t* dLdy_soa_f16, double* grad_out,
                        uint32_t* hits_out /* nullable, per entry */);
 
+uint32_t orc_f16_selfcheck(uint32_t n, uint32_t seed);
 uint16_t orc_f32_to_f16(float x);
 float orc_f16_to_f32(uint16_t h);
 
