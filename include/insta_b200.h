@@ -61,6 +61,11 @@ typedef struct insta_params {
 	uint32_t aabb_scale;             /* 1 */
 	/* ---- warp_random_samples RNG (ngp/src/testbed.cu:2185: default_rng_t{42}) ---- */
 	uint64_t rng_seed;
+	/* ---- rounding flavour of the closest-triangle distance arithmetic (it breaks ties) ----
+	 * 0 = bit-for-bit what the reference's CUDA build computes (nvcc's FMA contraction of bvh.cuh / triangle.cuh), default;
+	 * 1 = bit-for-bit what the reference's HOST build of the same functions computes (nothing contracted). */
+	uint32_t arith;
+	uint32_t reserved_;
 } insta_params;
 
 INSTA_API void        insta_params_default(insta_params* p);

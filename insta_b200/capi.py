@@ -37,6 +37,8 @@ class Params(C.Structure):
         ("per_level_scale", C.c_float),
         ("aabb_scale", C.c_uint32),
         ("rng_seed", C.c_uint64),
+        ("arith", C.c_uint32),
+        ("reserved_", C.c_uint32),
     ]
 
 

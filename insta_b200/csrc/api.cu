@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -136,6 +137,7 @@ void insta_params_default(insta_params* p) {
 	p->per_level_scale = 0.f;
 	p->aabb_scale = 1;
 	p->rng_seed = 42;
+	p->arith = 0;
 }
 
 const char* insta_last_error(void) { return last_error_cstr(); }
@@ -160,6 +162,7 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 	cudaDeviceProp prop;
 	INSTA_CUDA(cudaGetDeviceProperties(&prop, device));
 	if (prop.major != 10) INSTA_FAIL(INSTA_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library carries sm_100a code only");
+	if (def.arith > 1) INSTA_FAIL(INSTA_ERR_INVALID, "insta_params.arith must be 0 (reference CUDA build) or 1 (reference host build)");
 	insta_ctx* ctx = new insta_ctx();
 	ctx->p = def;
 	ctx->device = device;
@@ -175,6 +178,15 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 			insta_ctx_destroy(ctx);
 			return INSTA_ERR_CUDA;
 		}
+	}
+	if (cudaMalloc(&ctx->d_counter, 32 * 128) != cudaSuccess) {
+		set_error("counter allocation failed");
+		insta_ctx_destroy(ctx);
+		return INSTA_ERR_CUDA;
+	}
+	{
+		const char* k = getenv("INSTA_DEFORM_KERNEL");
+		ctx->force_legacy_deform = k && std::string(k) == "legacy";
 	}
 	int rc = init_grid_levels(ctx);
 	if (rc) {
@@ -197,6 +209,7 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (ctx->d_adjacency) cudaFree(ctx->d_adjacency);
 	if (ctx->d_canon_area) cudaFree(ctx->d_canon_area);
 	if (ctx->d_canon_xf) cudaFree(ctx->d_canon_xf);
+	if (ctx->d_counter) cudaFree(ctx->d_counter);
 	for (int k = 0; k < 2; ++k) {
 		if (ctx->d_stage_rec[k]) cudaFree(ctx->d_stage_rec[k]);
 		if (ctx->d_stage_enc[k]) cudaFree(ctx->d_stage_enc[k]);
@@ -225,6 +238,12 @@ int insta_set_canonical(insta_ctx* ctx, const float* h_verts, uint32_t n_verts, 
 	build_triangles(h_verts, h_faces, n_faces, ctx->mask_ids.data(), nullptr, ctx->canon_tris.data());
 	build_adjacency(h_faces, n_faces, n_verts, ctx->adjacency);
 	mesh_aabb(h_verts, n_verts, ctx->render_aabb);
+	{
+		// inner levels of the 4-ary median-split tree: a node with more than leaf_size triangles is split into 4
+		uint32_t levels = 0;
+		for (uint64_t cnt = n_faces; cnt > ctx->p.n_primitives_per_leaf || levels == 0; cnt = (cnt + 3) / 4) ++levels;
+		ctx->stack_need = 3 * (levels > 0 ? levels - 1 : 0) + 4;
+	}
 
 	for (void* p : {(void*)ctx->d_faces, (void*)ctx->d_mask_ids, (void*)ctx->d_adjacency, (void*)ctx->d_canon_area, (void*)ctx->d_canon_xf})
 		if (p) cudaFree(p);

@@ -132,6 +132,10 @@ struct insta_ctx {
 	insta::FrameDev* d_frame_table = nullptr;
 	uint32_t frame_table_cap = 0;
 	bool frame_table_dirty = false;
+	uint32_t stack_need = 0;          // traversal stack entries a query can need for the loaded topology
+	bool force_legacy_deform = false; // INSTA_DEFORM_KERNEL=legacy: thread-per-query kernel (A/B measurements)
+	uint32_t* d_counter = nullptr;    // 32 sample counters (128 B apart) of the persistent deform kernel
+	std::atomic<uint32_t> counter_rr{0};
 	// grid
 	insta::GridLevels levels{};
 	// host-path staging

@@ -40,8 +40,46 @@ inline V3 normalized(V3 a) {
 inline V3 centroid(const orc_tri& t) { return (v3(t.a) + v3(t.b) + v3(t.c)) / 3.0f; }            // triangle.cuh:220
 inline float centroid_axis(const orc_tri& t, int ax) { return (t.a[ax] + t.b[ax] + t.c[ax]) / 3; }  // triangle.cuh:224
 
-// triangle.cuh:88-107
-inline float tri_distance_sq(const orc_tri& t, V3 pos) {
+// Arithmetic flavour of the two distance functions that decide the closest triangle:
+//   0 = the reference's HOST build (plain IEEE fp32, nothing contracted)               -- pinned here against libref_host.so
+//   1 = the reference's DEVICE build (nvcc 12.9 -O3, default -fmad=true): the FMUL/FADD pairs nvcc fuses into FFMA,
+//       read off the SASS of `warp` / `warp_random_samples` (identical in both kernels)  -- pinned on the GPU box against
+//       the reference's own CUDA kernels (tests/test_gpu_vs_ref_cuda.py)
+// fmaf() here is the exact single-rounding fused multiply-add.
+int g_arith = 0;
+
+// x0*y0 + (x1*y1 + x2*y2) as the device build evaluates it: pattern A fuses x and y and rounds the z product,
+// pattern B fuses x and z and rounds the y product.
+inline float dotA(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+inline float dotB(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.z, b.z, a.y * b.y)); }
+// a x b, each component fma(first product, -(second product rounded))
+inline V3 crossF(V3 a, V3 b) { return {fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))}; }
+
+// triangle.cuh:88-107, device-build contraction
+inline float tri_distance_sq_dev(const orc_tri& t, V3 pos) {
+	V3 a = v3(t.a), b = v3(t.b), c = v3(t.c);
+	V3 v21 = b - a, p1 = pos - a;
+	V3 v32 = c - b, p2 = pos - b;
+	V3 v13 = a - c, p3 = pos - c;
+	V3 nor = crossF(v21, v13);
+	if (sgn(dotA(crossF(v21, nor), p1)) + sgn(dotA(crossF(v32, nor), p2)) + sgn(dotA(crossF(v13, nor), p3)) < 2.0f) {
+		auto edge = [](V3 v, V3 q) {
+			float tt = clampf(dotB(v, q) / dotA(v, v), 0.0f, 1.0f);
+			V3 e = {fmaf(v.x, tt, -q.x), fmaf(v.y, tt, -q.y), fmaf(v.z, tt, -q.z)};
+			return dotA(e, e);
+		};
+		float m = edge(v21, p1);
+		float e2 = edge(v32, p2), e3 = edge(v13, p3);
+		if (e2 < m) m = e2;
+		if (e3 < m) m = e3;
+		return m;
+	}
+	float d = dotB(nor, p1);
+	return d * d / dotB(nor, nor);
+}
+
+// triangle.cuh:88-107, host build
+inline float tri_distance_sq_host(const orc_tri& t, V3 pos) {
 	V3 a = v3(t.a), b = v3(t.b), c = v3(t.c);
 	V3 v21 = b - a, p1 = pos - a;
 	V3 v32 = c - b, p2 = pos - b;
@@ -58,6 +96,7 @@ inline float tri_distance_sq(const orc_tri& t, V3 pos) {
 	}
 	return dot(nor, p1) * dot(nor, p1) / sqn(nor);
 }
+inline float tri_distance_sq(const orc_tri& t, V3 pos) { return g_arith ? tri_distance_sq_dev(t, pos) : tri_distance_sq_host(t, pos); }
 
 // bounding_box.cuh:228-230
 inline float box_distance_sq(const float* mn, const float* mx, V3 p) {
@@ -67,6 +106,7 @@ inline float box_distance_sq(const float* mn, const float* mx, V3 p) {
 		float m = std::max(lo, hi);
 		d[k] = std::max(m, 0.0f);
 	}
+	if (g_arith) return fmaf(d[0], d[0], fmaf(d[1], d[1], d[2] * d[2]));
 	return d[0] * d[0] + (d[1] * d[1] + d[2] * d[2]);
 }
 
@@ -230,6 +270,9 @@ struct Pcg32 {  // tcnn/dependencies/pcg32/pcg32.h
 }  // namespace
 
 extern "C" {
+
+void orc_set_arith(int mode) { g_arith = mode ? 1 : 0; }
+int orc_get_arith(void) { return g_arith; }
 
 int orc_max_threads(void) {
 #ifdef _OPENMP

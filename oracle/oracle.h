@@ -34,6 +34,9 @@ typedef struct orc_node {
 } orc_node;
 
 int orc_max_threads(void);
+/* 0 = reference HOST build arithmetic (default), 1 = reference DEVICE build (nvcc -fmad contraction); see oracle.cpp */
+void orc_set_arith(int mode);
+int orc_get_arith(void);
 
 /* ---- per-frame mesh preparation (tiny_mesh.cu:134-178, 316-371; masking.cpp:118-148) ---- */
 void orc_build_triangles(const float* verts, const uint32_t* faces, uint32_t n_faces, const uint32_t* mask_ids,

@@ -95,6 +95,11 @@ class Oracle(_Lib):
         L.orc_f16_to_f32.restype = C.c_float
         L.orc_f16_to_f32.argtypes = [C.c_uint16]
 
+    def set_arith(self, mode):
+        """'host' = arithmetic of the reference's host build (default), 'device' = of its CUDA build (FMA-contracted)."""
+        assert mode in ("host", "device")
+        self.lib.orc_set_arith(C.c_int(1 if mode == "device" else 0))
+
     # the warp entry point is named orc_warp in the oracle, ref_warp_cpu in the reference harness
     def build_triangles(self, verts, faces, mask_ids, canonical=None):
         verts = np.ascontiguousarray(verts, np.float32)

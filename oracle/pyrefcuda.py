@@ -64,3 +64,26 @@ class RefCuda:
                                             C.c_void_p(d_grad.data_ptr()), C.c_uint32(n_levels), C.c_uint32(log2_hashmap_size), C.c_uint32(base_resolution),
                                             C.c_float(per_level_scale), self._s())
         assert rc == 0, rc
+
+    def closest_triangle(self, d_pts, frame):
+        """reference closest_triangle (bvh.cuh:48) on the device for one uploaded frame -> (bvh-order idx, distance)."""
+        import torch
+
+        n = d_pts.shape[0]
+        idx = torch.empty(n, dtype=torch.int32, device="cuda")
+        dist = torch.empty(n, dtype=torch.float32, device="cuda")
+        rc = self.lib.refcuda_closest_triangle(C.c_uint32(n), C.c_void_p(d_pts.data_ptr()), C.c_void_p(self._keep[0][frame].data_ptr()),
+                                               C.c_void_p(self._keep[1][frame].data_ptr()), C.c_void_p(idx.data_ptr()), C.c_void_p(dist.data_ptr()), self._s())
+        assert rc == 0, rc
+        return idx, dist
+
+    def distances(self, d_pts, frame, tri_index, node_index):
+        import torch
+
+        n = d_pts.shape[0]
+        a = torch.empty(n, dtype=torch.float32, device="cuda")
+        b = torch.empty(n, dtype=torch.float32, device="cuda")
+        rc = self.lib.refcuda_distances(C.c_uint32(n), C.c_void_p(d_pts.data_ptr()), C.c_void_p(self._keep[1][frame].data_ptr() + 48 * tri_index),
+                                        C.c_void_p(self._keep[0][frame].data_ptr() + 32 * node_index), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), self._s())
+        assert rc == 0, rc
+        return a, b

@@ -53,7 +53,34 @@ static GridOffsetTable make_offsets(uint32_t n_levels, uint32_t log2_hashmap_siz
 	return t;
 }
 
+// glue kernels that call the reference's own device functions directly (for bit-level checks of ids and distances)
+__global__ void refcuda_closest_kernel(uint32_t n, const float* __restrict__ pts, const ngp::TriangleBvhNode* __restrict__ nodes,
+                                       const ngp::Triangle* __restrict__ tris, int* __restrict__ idx, float* __restrict__ dist) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	auto r = closest_triangle(Vector3f(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), nodes, tris);
+	idx[i] = r.first;
+	dist[i] = r.second;
+}
+__global__ void refcuda_distance_kernel(uint32_t n, const float* __restrict__ pts, const ngp::Triangle* __restrict__ tri, const ngp::TriangleBvhNode* __restrict__ node,
+                                        float* __restrict__ out_tri, float* __restrict__ out_box) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const Vector3f p(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+	out_tri[i] = tri->distance_sq(p);
+	out_box[i] = node->bb.distance_sq(p);
+}
+
 extern "C" {
+
+int refcuda_closest_triangle(uint32_t n, const float* d_pts, const void* d_nodes, const void* d_tris, int* d_idx, float* d_dist, cudaStream_t stream) {
+	linear_kernel(refcuda_closest_kernel, 0, stream, n, d_pts, (const ngp::TriangleBvhNode*)d_nodes, (const ngp::Triangle*)d_tris, d_idx, d_dist);
+	return (int)cudaGetLastError();
+}
+int refcuda_distances(uint32_t n, const float* d_pts, const void* d_tri, const void* d_node, float* d_out_tri, float* d_out_box, cudaStream_t stream) {
+	linear_kernel(refcuda_distance_kernel, 0, stream, n, d_pts, (const ngp::Triangle*)d_tri, (const ngp::TriangleBvhNode*)d_node, d_out_tri, d_out_box);
+	return (int)cudaGetLastError();
+}
 
 int refcuda_warp(float* d_samples, uint32_t n, uint32_t stride, int32_t frame_id, uint32_t n_meshes, void** d_nodes_ptrs, void** d_tris_bvh_ptrs,
                  void** d_tris_topo_ptrs, void* d_canon, int* d_adjacency, int disable_interp, const float* aabb6, uint32_t extra_dims, int use_geo,

@@ -33,19 +33,40 @@ def golden():
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stage1_ref.npz"))
 
 
-@pytest.fixture(scope="session")
-def gpu_ctx(scene):
-    """A context on cuda:0 holding the canonical mesh and the scene's frames.  Fails loudly when the CUDA library or the
-    device is missing -- GPU tests must never pass on a fallback."""
+def _make_ctx(scene, **kw):
     import torch
 
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from insta_b200 import capi
 
     capi.load_library(build_if_missing=False)
-    ctx = capi.Context(device=0)
+    ctx = capi.Context(device=0, **kw)
     ctx.set_canonical(scene.verts, scene.faces, scene.masks)
     for v in scene.frame_verts:
         ctx.add_frame(v)
+    return ctx
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(scene):
+    """A context on cuda:0 holding the canonical mesh and the scene's frames, default arithmetic (= the reference's CUDA
+    build).  Fails loudly when the CUDA library or the device is missing -- GPU tests must never pass on a fallback."""
+    ctx = _make_ctx(scene)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx_host(scene):
+    """Same, with arith = 1: the rounding of the reference's HOST build (what the committed golden vectors were made with)."""
+    ctx = _make_ctx(scene, arith=1)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(params=["device", "host"])
+def arith_pair(request, oracle, gpu_ctx, gpu_ctx_host):
+    """(context, oracle) set to the same arithmetic flavour."""
+    oracle.set_arith(request.param)
+    yield (gpu_ctx if request.param == "device" else gpu_ctx_host), oracle
+    oracle.set_arith("host")

@@ -1,5 +1,7 @@
-"""Stage 1 on the GPU, through the C ABI, against the oracle (which is pinned bit-for-bit to the reference's host code):
-closest-triangle topology ids bit-exact; canonical positions / directions within the stated fp32 tolerance."""
+"""Stage 1 on the GPU, through the C ABI, against the oracle: closest-triangle topology ids bit-exact; canonical positions /
+directions within the stated fp32 tolerance.  Every parity test runs in both arithmetic flavours: 'host' (oracle pinned
+bit-for-bit to the reference's host code in this repo's CPU tests) and 'device' (oracle pinned to the reference's CUDA
+kernels in tests/test_gpu_vs_ref_cuda.py); the product's default is 'device'."""
 import numpy as np
 import pytest
 
@@ -38,14 +40,16 @@ def _check(scene, oracle, rec, got, tri, want, want_tri, blend):
 
 
 @pytest.mark.parametrize("n", [8192, 1000, 1, 129])
-def test_warp_parity_holder_frames(gpu_ctx, scene, oracle, n):
+def test_warp_parity_holder_frames(arith_pair, scene, n):
+    gpu_ctx, oracle = arith_pair
     rec = scene.golden_records(8192)[:n] if n <= 8192 else None
     got, tri = _run(gpu_ctx, rec)
     want, want_tri = scene.oracle_warp(oracle, rec)
     _check(scene, oracle, rec, got, tri, want, want_tri, blend=True)
 
 
-def test_warp_matches_reference_golden(gpu_ctx, scene, golden):
+def test_warp_matches_reference_golden(gpu_ctx_host, scene, golden):
+    gpu_ctx = gpu_ctx_host
     """Straight against the vectors the reference's own code produced (tests/golden/stage1_ref.npz)."""
     rec = scene.golden_records()
     got, tri = _run(gpu_ctx, rec)
@@ -58,7 +62,8 @@ def test_warp_matches_reference_golden(gpu_ctx, scene, golden):
     assert np.abs(got[:, [0, 1, 2, 8, 9, 10]] - golden["render_rec"]).max() < POS_TOL_BLEND
 
 
-def test_tie_heavy_points(gpu_ctx, scene, oracle):
+def test_tie_heavy_points(arith_pair, scene):
+    gpu_ctx, oracle = arith_pair
     """Samples placed exactly on vertices, edge midpoints and centroids of the posed mesh: equal distances everywhere,
     the winner is decided by visit order alone."""
     from insta_b200 import synth
@@ -75,7 +80,8 @@ def test_tie_heavy_points(gpu_ctx, scene, oracle):
     assert np.abs(got[:, 0:3] - want[:, 0:3]).max() < POS_TOL_BLEND
 
 
-def test_skip_rules(gpu_ctx, scene, oracle):
+def test_skip_rules(arith_pair, scene):
+    gpu_ctx, oracle = arith_pair
     from insta_b200 import synth
 
     n = 2048
@@ -94,7 +100,8 @@ def test_skip_rules(gpu_ctx, scene, oracle):
     assert np.abs(got[~sk][:, 0:3] - want[~sk][:, 0:3]).max() < 2e-3  # far-away corner point: looser, ids are what matter
 
 
-def test_render_deformed_fixed_frame(gpu_ctx, scene, oracle):
+def test_render_deformed_fixed_frame(arith_pair, scene):
+    gpu_ctx, oracle = arith_pair
     rec = scene.golden_records(4096)
     for f in (0, 1):
         got, tri = _run(gpu_ctx, rec, frame_id=f)
@@ -102,7 +109,8 @@ def test_render_deformed_fixed_frame(gpu_ctx, scene, oracle):
         _check(scene, oracle, rec, got, tri, want, want_tri, blend=True)
 
 
-def test_points_path_explicit_and_rng_frames(gpu_ctx, scene, oracle):
+def test_points_path_explicit_and_rng_frames(arith_pair, scene):
+    gpu_ctx, oracle = arith_pair
     import torch
 
     n = 5000
@@ -129,6 +137,7 @@ def test_disable_interp_and_geo_and_strides(scene, oracle):
     from insta_b200 import capi, synth
 
     rec = scene.golden_records(4096)
+    oracle.set_arith("device")
     ctx = capi.Context(device=0, disable_interp=1, geo_params=1)
     try:
         ctx.set_canonical(scene.verts, scene.faces, scene.masks)
@@ -160,6 +169,7 @@ def test_disable_interp_and_geo_and_strides(scene, oracle):
         assert np.abs(d.cpu().numpy()[:, 0:3] - want[:, 0:3]).max() < POS_TOL_BLEND
     finally:
         ctx.close()
+        oracle.set_arith("host")
 
 
 def test_errors_are_status_codes(gpu_ctx):
@@ -174,7 +184,8 @@ def test_errors_are_status_codes(gpu_ctx):
     gpu_ctx.surface_closest_point(empty)  # n == 0 is a no-op
 
 
-def test_full_size_batch_properties(gpu_ctx, scene, oracle):
+def test_full_size_batch_properties(arith_pair, scene):
+    gpu_ctx, oracle = arith_pair
     """BASELINE config 2 size (4,194,304 records): checked through size-independent properties and an oracle subsample."""
     import torch
     from insta_b200 import synth
