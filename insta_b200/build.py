@@ -38,6 +38,8 @@ def build(force=False, verbose=False):
         common += ["-ccbin", cxx]
     if verbose:
         common += ["-Xptxas", "-v"]
+    if os.environ.get("INSTA_TUNE"):  # extra kernel variants for A/B measurements (tools/tune_deform.py)
+        common += ["-DINSTA_TUNE"]
     procs = []
     for s in srcs:
         o = os.path.join(LIB_DIR, os.path.basename(s) + ".o")

@@ -243,6 +243,8 @@ int insta_set_canonical(insta_ctx* ctx, const float* h_verts, uint32_t n_verts, 
 		uint32_t levels = 0;
 		for (uint64_t cnt = n_faces; cnt > ctx->p.n_primitives_per_leaf || levels == 0; cnt = (cnt + 3) / 4) ++levels;
 		ctx->stack_need = 3 * (levels > 0 ? levels - 1 : 0) + 4;
+		const char* wide = getenv("INSTA_DEFORM_STACK");
+		ctx->compact_entries = n_faces < 8192u && ctx->p.n_primitives_per_leaf <= 3u && !(wide && std::string(wide) == "wide");
 	}
 
 	for (void* p : {(void*)ctx->d_faces, (void*)ctx->d_mask_ids, (void*)ctx->d_adjacency, (void*)ctx->d_canon_area, (void*)ctx->d_canon_xf})

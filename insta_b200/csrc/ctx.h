@@ -53,7 +53,7 @@ struct Node {
 struct __align__(128) Quad {
 	float mnx[4], mny[4], mnz[4], mxx[4], mxy[4], mxz[4];
 	int32_t ref[4];
-	int32_t pad[4];
+	int32_t pad[4];  // the same references as 16-bit stack codes (bit 15 = leaf; quad index | first << 2 | count), -1 = n/a
 };
 static_assert(sizeof(Quad) == 128, "Quad must be one cache line");
 
@@ -133,6 +133,7 @@ struct insta_ctx {
 	uint32_t frame_table_cap = 0;
 	bool frame_table_dirty = false;
 	uint32_t stack_need = 0;          // traversal stack entries a query can need for the loaded topology
+	bool compact_entries = false;     // every reference of the loaded topology fits the 16-bit stack code
 	bool force_legacy_deform = false; // INSTA_DEFORM_KERNEL=legacy: thread-per-query kernel (A/B measurements)
 	uint32_t* d_counter = nullptr;    // 32 sample counters (128 B apart) of the persistent deform kernel
 	std::atomic<uint32_t> counter_rr{0};

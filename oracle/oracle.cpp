@@ -544,6 +544,56 @@ void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const 
 	}
 }
 
+
+// Diagnostic (design studies only): traversal statistics of closest_tri with the product's pop-time rule for inner nodes.
+// out8 = {expands, inner entries dropped at pop, leaf visits, triangle tests, leaf visits whose box distance exceeded
+//         `best` at pop (would be skippable), stack high-water mark, queries, 0}
+void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, double* out8) {
+	double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (int q = 0; q < n; ++q) {
+		V3 p = v3(pts + 3 * q);
+		int stack[64];
+		float sd[64];
+		int sp = 0;
+		stack[sp] = 0; sd[sp] = 0.f; ++sp;
+		float best = std::numeric_limits<float>::max();
+		while (sp > 0) {
+			--sp;
+			int idx = stack[sp];
+			float dpush = sd[sp];
+			const orc_node& nd = nodes[idx];
+			if (nd.left_idx < 0) {
+				acc[2] += 1;
+				if (dpush > best) acc[4] += 1;
+				int end = -nd.right_idx - 1;
+				for (int i = -nd.left_idx - 1; i < end; ++i) {
+					acc[3] += 1;
+					float d = tri_distance_sq(tris[i], p);
+					if (d <= best) best = d;
+				}
+			} else {
+				if (dpush > best) { acc[1] += 1; continue; }
+				acc[0] += 1;
+				float cd[4];
+				uint32_t ci[4];
+				for (uint32_t k = 0; k < 4; ++k) {
+					cd[k] = box_distance_sq(nodes[nd.left_idx + k].mn, nodes[nd.left_idx + k].mx, p);
+					ci[k] = nd.left_idx + k;
+				}
+				auto cas = [&](int i, int j) {
+					if (cd[i] < cd[j]) { std::swap(cd[i], cd[j]); std::swap(ci[i], ci[j]); }
+				};
+				cas(0, 2); cas(1, 3); cas(0, 1); cas(2, 3); cas(1, 2);
+				for (int k = 0; k < 4; ++k)
+					if (cd[k] <= best && sp < 63) { stack[sp] = (int)ci[k]; sd[sp] = cd[k]; ++sp; }
+				if (sp > acc[5]) acc[5] = sp;
+			}
+		}
+		acc[6] += 1;
+	}
+	for (int k = 0; k < 8; ++k) out8[k] = acc[k];
+}
+
 float orc_triangle_distance_sq(const orc_tri* t, const float* p) { return tri_distance_sq(*t, v3(p)); }
 float orc_bbox_distance_sq(const float* mn, const float* mx, const float* p) { return box_distance_sq(mn, mx, v3(p)); }
 void orc_tri2projection(const orc_tri* t, float* out16) { tri2proj(*t, out16); }

@@ -51,6 +51,8 @@ void orc_triangle_masks(const uint32_t* faces, uint32_t n_faces, const int32_t* 
 int orc_bvh_build(orc_tri* tris_inout, int n_tris, int leaf_size, orc_node* nodes_out, int max_nodes);
 void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, int* out_idx, float* out_dist,
                           int n_threads);
+/* diagnostic: traversal statistics (see oracle.cpp) */
+void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, double* out8);
 float orc_triangle_distance_sq(const orc_tri* t, const float* p);
 float orc_bbox_distance_sq(const float* mn, const float* mx, const float* p);
 void orc_tri2projection(const orc_tri* t, float* out16_colmajor);
