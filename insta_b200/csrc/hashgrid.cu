@@ -5,9 +5,9 @@
 //
 // Layout: the fp16 parameter table is borrowed from the caller in the reference's own order (entries x 8 features,
 // levels concatenated at the ctor's offsets), so a snapshot's params_binary can be used as is.  One entry = 16 bytes =
-// one 128-bit load per corner.  Forward: a thread owns one (sample pair, level); blockIdx.y = level so that all CTAs
-// resident at a time gather from the same <= 4 MB level table (L1-resident for the coarse levels, L2-resident for the
-// rest); outputs are written SoA with half2 (4-byte) coalesced streaming stores.
+// one 128-bit load per corner.  Forward: a CTA owns a tile of 64 samples and all levels (warp = level, lane = sample pair),
+// so the strided sample records are read once; the 49 MB table stays L2-resident (evict_last gathers, streaming loads /
+// stores for everything that is touched once); outputs are written SoA, one full 128-byte line per (tile, feature row).
 //
 // Exactness: slot indices use the same uint32 arithmetic as grid_index, including its loop-exit rule and wrap-around;
 // the per-level scale is evaluated ON DEVICE with the reference kernel's expression (exp2f(l * log2(s)) * base - 1,
@@ -22,8 +22,10 @@
 namespace insta {
 namespace {
 
-constexpr int kFwdThreads = 256;
-constexpr int kBwdThreads = 256;
+constexpr int kFwdWarps = 16;
+constexpr int kFwdThreads = kFwdWarps * 32;
+constexpr int kBwdThreads = kFwdThreads;
+constexpr uint32_t kTile = 64;  // samples per CTA: 32 lanes x 2
 
 __global__ void level_scale_kernel(uint32_t n_levels, float log2_per_level_scale, uint32_t base_resolution, float* out) {
 	const uint32_t level = threadIdx.x;
@@ -63,6 +65,11 @@ __device__ __forceinline__ uint32_t slot_of(uint32_t gx, uint32_t gy, uint32_t g
 __device__ __forceinline__ uint4 ld_entry(const uint4* p) {
 	uint4 r;
 	asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+	float r;
+	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
 	return r;
 }
 __device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -105,23 +112,22 @@ __device__ __forceinline__ void encode_one(const uint4* __restrict__ table, cons
 	for (int k = 0; k < 8; ++k) accum(acc, v[k], w[k]);
 }
 
-// grid: (ceil(n / 2 / kFwdThreads), n_levels); each thread encodes samples 2t and 2t+1 at level blockIdx.y
+// One CTA = one tile of kTile samples x ALL levels: warp w handles level w (levels w, w + kFwdWarps, ... when there are
+// more levels than warps), lane l the sample pair (2l, 2l+1) of the tile.  The tile's positions are read from the strided
+// records ONCE (staged in shared memory) -- with one level per CTA the 108-byte records streamed through L2 once per
+// level (16 x 453 MB; measured 7.3 GB of DRAM reads per 4M-sample launch, profiles/r1_hash_fwd_ncu_summary.txt).
 template <bool HASHED>
-__device__ __forceinline__ void fwd_body(const GridLevels& L, uint32_t level, uint32_t n, const float* __restrict__ pos, uint32_t stride,
-                                         const uint4* __restrict__ table, __half* __restrict__ out) {
-	const uint32_t i0 = (blockIdx.x * kFwdThreads + threadIdx.x) * 2;
-	if (i0 >= n) return;
-	const bool two = i0 + 1 < n;
+__device__ __forceinline__ void fwd_level(const GridLevels& L, uint32_t level, uint32_t n, uint32_t i0, bool one, bool two, const float* __restrict__ sp,
+                                          const uint4* __restrict__ table, __half* __restrict__ out) {
 	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
 	const float scale = L.scale[level];
 	table += L.offset[level];
-	const float* p0 = pos + (size_t)i0 * stride;
-	const float* p1 = p0 + (two ? stride : 0);
-	const Corner c0 = pos_fract3(__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2), scale);
-	const Corner c1 = pos_fract3(__ldg(p1), __ldg(p1 + 1), __ldg(p1 + 2), scale);
+	const Corner c0 = pos_fract3(sp[0], sp[1], sp[2], scale);
+	const Corner c1 = pos_fract3(sp[3], sp[4], sp[5], scale);
 	__half2 a0[4], a1[4];
 	encode_one<HASHED>(table, c0, size, mul1, mul2, a0);
 	encode_one<HASHED>(table, c1, size, mul1, mul2, a1);
+	if (!one) return;
 	__half* o = out + (size_t)(level * 8) * n + i0;
 	if (two && (n % 2u == 0)) {
 		// rows start at even element offsets -> 4-byte aligned pair stores
@@ -144,11 +150,27 @@ __device__ __forceinline__ void fwd_body(const GridLevels& L, uint32_t level, ui
 	}
 }
 
+// stage the xyz of the tile's samples: s_pos[3 * j + d], zero for samples past n
+__device__ __forceinline__ void stage_positions(float* s_pos, const float* __restrict__ pos, uint32_t stride, uint32_t n, uint32_t tile_first) {
+	for (uint32_t t = threadIdx.x; t < kTile * 3u; t += blockDim.x) {
+		const uint32_t j = t / 3u, d = t - 3u * j, i = tile_first + j;
+		s_pos[t] = i < n ? ld_stream_f32(pos + (size_t)i * stride + d) : 0.0f;
+	}
+	__syncthreads();
+}
+
 __global__ void __launch_bounds__(kFwdThreads) hash_fwd_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
                                                                uint32_t stride, const uint4* __restrict__ table, __half* __restrict__ out) {
-	const uint32_t level = blockIdx.y;
-	if (L.hashed[level]) fwd_body<true>(L, level, n, pos, stride, table, out);
-	else fwd_body<false>(L, level, n, pos, stride, table, out);
+	__shared__ float s_pos[kTile * 3];
+	const uint32_t tile_first = blockIdx.x * kTile;
+	stage_positions(s_pos, pos, stride, n, tile_first);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t i0 = tile_first + 2u * lane;
+	const bool one = i0 < n, two = i0 + 1 < n;
+	for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
+		if (L.hashed[level]) fwd_level<true>(L, level, n, i0, one, two, s_pos + 6 * lane, table, out);
+		else fwd_level<false>(L, level, n, i0, one, two, s_pos + 6 * lane, table, out);
+	}
 }
 
 __global__ void __launch_bounds__(256) hash_slots_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
@@ -170,23 +192,10 @@ __device__ __forceinline__ void red_add_v4_f16x2(void* addr, uint32_t a, uint32_
 	asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// grid: (ceil(n / kBwdThreads), n_levels); thread = (sample, level), all 8 features
+// Same tiling as the forward kernel: warp = level, lane = sample pair, positions staged once per tile.
 template <bool HASHED>
-__device__ __forceinline__ void bwd_body(const GridLevels& L, uint32_t level, uint32_t n, const float* __restrict__ pos, uint32_t stride,
-                                         const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
-	const uint32_t i = blockIdx.x * kBwdThreads + threadIdx.x;
-	if (i >= n) return;
-	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
-	grad += L.offset[level];
-	const float* p = pos + (size_t)i * stride;
-	const Corner c = pos_fract3(__ldg(p), __ldg(p + 1), __ldg(p + 2), L.scale[level]);
-	float g[8];
-#pragma unroll
-	for (int f = 0; f < 8; ++f) g[f] = __half2float(dLdy[(size_t)(level * 8 + f) * n + i]);
-	bool any = false;
-#pragma unroll
-	for (int f = 0; f < 8; ++f) any |= (g[f] != 0.0f);
-	if (!any) return;  // adding +0 to every slot is a no-op
+__device__ __forceinline__ void bwd_sample(const uint4* grad_base, const Corner& c, const float g[8], uint32_t size, uint32_t mul1, uint32_t mul2) {
+	uint4* grad = const_cast<uint4*>(grad_base);
 #pragma unroll
 	for (uint32_t k = 0; k < 8; ++k) {
 		float wk = 1.0f;
@@ -211,11 +220,52 @@ __device__ __forceinline__ void bwd_body(const GridLevels& L, uint32_t level, ui
 	}
 }
 
+template <bool HASHED>
+__device__ __forceinline__ void bwd_level(const GridLevels& L, uint32_t level, uint32_t n, uint32_t i0, bool one, bool two, const float* __restrict__ sp,
+                                          const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
+	if (!one) return;
+	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
+	const float scale = L.scale[level];
+	grad += L.offset[level];
+	float g0[8], g1[8];
+	const __half* row = dLdy + (size_t)(level * 8) * n + i0;
+	if (two && (n % 2u == 0)) {
+#pragma unroll
+		for (int f = 0; f < 8; ++f) {
+			const float2 v = __half22float2(*reinterpret_cast<const __half2*>(row + (size_t)f * n));
+			g0[f] = v.x;
+			g1[f] = v.y;
+		}
+	} else {
+#pragma unroll
+		for (int f = 0; f < 8; ++f) {
+			g0[f] = __half2float(row[(size_t)f * n]);
+			g1[f] = two ? __half2float(row[(size_t)f * n + 1]) : 0.0f;
+		}
+	}
+	bool any0 = false, any1 = false;
+#pragma unroll
+	for (int f = 0; f < 8; ++f) {
+		any0 |= (g0[f] != 0.0f);
+		any1 |= (g1[f] != 0.0f);
+	}
+	// adding +0 to every slot is a no-op
+	if (any0) bwd_sample<HASHED>(grad, pos_fract3(sp[0], sp[1], sp[2], scale), g0, size, mul1, mul2);
+	if (two && any1) bwd_sample<HASHED>(grad, pos_fract3(sp[3], sp[4], sp[5], scale), g1, size, mul1, mul2);
+}
+
 __global__ void __launch_bounds__(kBwdThreads) hash_bwd_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
                                                                uint32_t stride, const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
-	const uint32_t level = blockIdx.y;
-	if (L.hashed[level]) bwd_body<true>(L, level, n, pos, stride, dLdy, grad);
-	else bwd_body<false>(L, level, n, pos, stride, dLdy, grad);
+	__shared__ float s_pos[kTile * 3];
+	const uint32_t tile_first = blockIdx.x * kTile;
+	stage_positions(s_pos, pos, stride, n, tile_first);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t i0 = tile_first + 2u * lane;
+	const bool one = i0 < n, two = i0 + 1 < n;
+	for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
+		if (L.hashed[level]) bwd_level<true>(L, level, n, i0, one, two, s_pos + 6 * lane, dLdy, grad);
+		else bwd_level<false>(L, level, n, i0, one, two, s_pos + 6 * lane, dLdy, grad);
+	}
 }
 
 }  // namespace
@@ -274,7 +324,7 @@ int init_grid_levels(insta_ctx* ctx) {
 
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s) {
 	if (n == 0) return INSTA_OK;
-	const dim3 grid(((n + 1) / 2 + kFwdThreads - 1) / kFwdThreads, ctx->levels.n_levels);
+	const dim3 grid((n + kTile - 1) / kTile);
 	hash_fwd_kernel<<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
@@ -284,7 +334,7 @@ int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_
 int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s) {
 	if (zero_first) INSTA_CUDA(cudaMemsetAsync(grad, 0, (size_t)ctx->levels.offset[ctx->levels.n_levels] * 16, s));
 	if (n == 0) return INSTA_OK;
-	const dim3 grid((n + kBwdThreads - 1) / kBwdThreads, ctx->levels.n_levels);
+	const dim3 grid((n + kTile - 1) / kTile);
 	hash_bwd_kernel<<<grid, kBwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const __half*)dLdy, (uint4*)grad);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
