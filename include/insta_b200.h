@@ -146,6 +146,51 @@ INSTA_API int insta_hash_encode_bwd(insta_ctx* ctx, const float* d_pos, uint32_t
 INSTA_API int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, uint32_t* d_slots,
                                insta_stream stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stage 3 -- render tracer (ngp::Testbed::NerfTracer, ngp/src/testbed_nerf.cu:2030-2244 and the kernels it launches).
+ * The ray state lives in the context (NerfTracer::m_rays, testbed.h:146-230); the sample records and the network
+ * output are the caller's buffers, exactly as in the reference, so that any network can sit between generate and
+ * composite.  insta_render_frame runs the whole loop with this library's own network.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct insta_camera {
+	float    camera_matrix[12];      /* Eigen::Matrix<float,3,4>, column-major: columns right, down, forward, origin (ngp space) */
+	float    focal_length[2];        /* pixels; Testbed::calc_focal_length (ngp/src/testbed.cu:2531) */
+	float    screen_center[2];       /* Testbed::render_screen_center, 0.5 / 0.5 by default */
+	uint32_t resolution[2];
+	uint32_t sample_index;           /* render_buffer.spp() */
+	uint32_t snap_to_pixel_centers;  /* Testbed::m_snap_to_pixel_centers (default true, testbed.h:829) */
+} insta_camera;
+
+typedef struct insta_render_opts {
+	const void* d_density_grid_bitfield; /* Testbed::Nerf::density_grid_bitfield: 128^3 bits per cascade, Morton order; NULL = no skipping */
+	float    cone_angle_constant;        /* 0 for aabb_scale 1 (testbed_nerf.cu:2691) */
+	float    min_transmittance;          /* rendering_min_transmittance, 0.01 (testbed.h:669) */
+	uint32_t use_render_aabb;            /* 0 = the canonical mesh's render AABB (core.cu:289), 1 = render_aabb below */
+	float    render_aabb[6];
+	uint32_t linear_colors;              /* Testbed::Nerf::Training::linear_colors (false: sRGB -> linear when accumulating) */
+	uint32_t reserved_;
+} insta_render_opts;
+
+/* NerfTracer::init_rays_from_camera: init_rays_with_payload_kernel_nerf + advance_pos_nerf (testbed_nerf.cu:1854-1960,
+ * 634-690, 2030-2110).  d_frame_rgba (res.x*res.y float4) is left untouched, d_frame_depth is set to 1e10 like the
+ * reference.  d_dbg_* (nullable, res.x*res.y float4 each): per-pixel (origin, t) and (dir, alive) after the skip to the first
+ * occupied cell, for parity tests.  *h_n_alive receives the number of live rays (one stream sync, as in the reference). */
+INSTA_API int insta_tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth,
+                                     float* d_dbg_origin_t, float* d_dbg_dir_alive, uint32_t* h_n_alive, insta_stream stream);
+/* clamp(n_rays_initialized / n_alive, 1, 8) -- the reference's steps between compactions (testbed_nerf.cu:2172) */
+INSTA_API uint32_t insta_tracer_n_steps(const insta_ctx* ctx);
+/* generate_next_nerf_network_inputs (testbed_nerf.cu:722-795): n_alive * n_steps records, record of (ray i, step j) at
+ * index i + j * n_alive, holder = frame_id (-1 for steps a ray does not reach), d_extra_dims = the frame's expression
+ * coefficients copied into floats 11.. of every record.  *n_records = n_alive * n_steps. */
+INSTA_API int insta_tracer_generate_samples(insta_ctx* ctx, float* d_records, uint32_t stride_floats, uint32_t n_steps, int32_t frame_id,
+                                            const float* d_extra_dims, uint32_t* n_records, insta_stream stream);
+/* composite_kernel_nerf + compact_kernel_nerf + shade_kernel_nerf (testbed_nerf.cu:797-1009, 1829-1852, 1794-1827).
+ * d_net_out fp16: out_stride_elems == 0 -> 4 halves per sample (r, g, b, sigma logits); else out[i + c * out_stride_elems]
+ * (the reference's row-major network output, testbed_nerf.cu:842-845). */
+INSTA_API int insta_tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, const void* d_net_out_f16, uint32_t out_stride_elems,
+                                     uint32_t n_steps, float* d_frame_rgba, float* d_frame_depth, uint32_t* h_n_alive, insta_stream stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience (the end-to-end path a caller without device buffers uses): H2D of the records, stage 1,
  * stage 2, D2H of the mutated records and of the fp16 encodings, chunked and double-buffered on internal streams.

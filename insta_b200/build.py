@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libinsta_b200.so")
-SOURCES = ["api.cu", "deform.cu", "hashgrid.cu", "mesh_host.cpp"]
+SOURCES = ["api.cu", "deform.cu", "hashgrid.cu", "nerf.cu", "mesh_host.cpp"]
 HEADERS = ["ctx.h", os.path.join("..", "..", "include", "insta_b200.h")]
 
 

@@ -42,6 +42,31 @@ class Params(C.Structure):
     ]
 
 
+class Camera(C.Structure):
+    _fields_ = [("camera_matrix", C.c_float * 12), ("focal_length", C.c_float * 2), ("screen_center", C.c_float * 2), ("resolution", C.c_uint32 * 2),
+                ("sample_index", C.c_uint32), ("snap_to_pixel_centers", C.c_uint32)]
+
+
+class RenderOpts(C.Structure):
+    _fields_ = [("d_density_grid_bitfield", C.c_void_p), ("cone_angle_constant", C.c_float), ("min_transmittance", C.c_float), ("use_render_aabb", C.c_uint32),
+                ("render_aabb", C.c_float * 6), ("linear_colors", C.c_uint32), ("reserved_", C.c_uint32)]
+
+
+def make_camera(cam3x4, focal, resolution, screen_center=(0.5, 0.5), sample_index=0, snap=True):
+    """cam3x4: numpy [3, 4] camera-to-world (columns right, down, forward, origin) in ngp space."""
+    c = Camera()
+    m = np.asarray(cam3x4, np.float32)
+    for col in range(4):
+        for row in range(3):
+            c.camera_matrix[col * 3 + row] = float(m[row, col])
+    c.focal_length[0], c.focal_length[1] = (focal, focal) if np.isscalar(focal) else focal
+    c.screen_center[0], c.screen_center[1] = screen_center
+    c.resolution[0], c.resolution[1] = resolution
+    c.sample_index = sample_index
+    c.snap_to_pixel_centers = int(snap)
+    return c
+
+
 # every symbol include/insta_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = [
     "insta_params_default", "insta_last_error", "insta_version", "insta_ctx_create", "insta_ctx_destroy",
@@ -51,6 +76,7 @@ EXPORTS = [
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
+    "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
 
 _lib = None
@@ -71,6 +97,7 @@ def load_library(build_if_missing=True):
     lib.insta_n_frames.restype = C.c_uint32
     lib.insta_grid_n_params.restype = C.c_uint32
     lib.insta_launch_count.restype = C.c_uint64
+    lib.insta_tracer_n_steps.restype = C.c_uint32
     lib.insta_ctx_destroy.restype = None
     lib.insta_params_default.restype = None
     for name in EXPORTS:
@@ -237,6 +264,38 @@ class Context:
         n, stride = pos.shape
         self._check(self.lib.insta_hash_slots(self.h, _dev(pos), C.c_uint32(stride), C.c_uint32(n), _dev(slots), _stream(stream)))
         return slots
+
+    # ---- stage 3: render tracer (NerfTracer) ----
+    def tracer_init_rays(self, cam, frame_rgba, frame_depth, bitfield=None, render_aabb=None, cone_angle=0.0, min_transmittance=0.01, linear_colors=False,
+                         dbg_origin_t=None, dbg_dir_alive=None, stream=None):
+        o = RenderOpts()
+        o.d_density_grid_bitfield = bitfield.data_ptr() if bitfield is not None else None
+        o.cone_angle_constant = cone_angle
+        o.min_transmittance = min_transmittance
+        o.use_render_aabb = int(render_aabb is not None)
+        for k in range(6):
+            o.render_aabb[k] = float(render_aabb[k]) if render_aabb is not None else 0.0
+        o.linear_colors = int(linear_colors)
+        self._keep_opts = (o, bitfield)
+        n = C.c_uint32(0)
+        self._check(self.lib.insta_tracer_init_rays(self.h, C.byref(cam), C.byref(o), _dev(frame_rgba), _dev(frame_depth), _dev(dbg_origin_t), _dev(dbg_dir_alive),
+                                                    C.byref(n), _stream(stream)))
+        return n.value
+
+    def tracer_n_steps(self):
+        return self.lib.insta_tracer_n_steps(self.h)
+
+    def tracer_generate_samples(self, records, n_steps, frame_id, extra_dims=None, stream=None):
+        n = C.c_uint32(0)
+        self._check(self.lib.insta_tracer_generate_samples(self.h, _dev(records), C.c_uint32(records.shape[1]), C.c_uint32(n_steps), C.c_int32(frame_id),
+                                                           _dev(extra_dims), C.byref(n), _stream(stream)))
+        return n.value
+
+    def tracer_composite(self, records, net_out, out_stride, n_steps, frame_rgba, frame_depth, stream=None):
+        n = C.c_uint32(0)
+        self._check(self.lib.insta_tracer_composite(self.h, _dev(records), C.c_uint32(records.shape[1]), _dev(net_out), C.c_uint32(out_stride), C.c_uint32(n_steps),
+                                                    _dev(frame_rgba), _dev(frame_depth), C.byref(n), _stream(stream)))
+        return n.value
 
     # ---- host-buffer path ----
     def deform_encode_host(self, h_coords, frame_id, table, h_out):

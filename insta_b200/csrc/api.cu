@@ -210,6 +210,7 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (ctx->d_canon_area) cudaFree(ctx->d_canon_area);
 	if (ctx->d_canon_xf) cudaFree(ctx->d_canon_xf);
 	if (ctx->d_counter) cudaFree(ctx->d_counter);
+	tracer_destroy(ctx);
 	for (int k = 0; k < 2; ++k) {
 		if (ctx->d_stage_rec[k]) cudaFree(ctx->d_stage_rec[k]);
 		if (ctx->d_stage_enc[k]) cudaFree(ctx->d_stage_enc[k]);
@@ -435,6 +436,31 @@ int insta_hash_encode_bwd(insta_ctx* ctx, const float* d_pos, uint32_t pos_strid
 int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, uint32_t* d_slots, insta_stream stream) {
 	if (!ctx || ((!d_pos || !d_slots) && n) || pos_stride_floats < 3) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_slots: bad arguments");
 	return launch_hash_slots(ctx, d_pos, pos_stride_floats, n, d_slots, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int insta_tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth,
+                           float* d_dbg_origin_t, float* d_dbg_dir_alive, uint32_t* h_n_alive, insta_stream stream) {
+	if (!ctx || !cam || !d_frame_depth) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_init_rays: bad arguments");
+	if ((d_dbg_origin_t == nullptr) != (d_dbg_dir_alive == nullptr)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_init_rays: give both debug arrays or none");
+	if (ctx->n_faces == 0 && !(opts && opts->use_render_aabb)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_init_rays: no canonical mesh and no render_aabb");
+	ctx->render_opts = opts ? *opts : insta_render_opts{nullptr, 0.f, 0.01f, 0, {0, 0, 0, 1, 1, 1}, 0, 0};
+	return tracer_init_rays(ctx, cam, &ctx->render_opts, d_frame_rgba, d_frame_depth, d_dbg_origin_t, d_dbg_dir_alive, h_n_alive, (cudaStream_t)stream);
+}
+
+uint32_t insta_tracer_n_steps(const insta_ctx* ctx) { return ctx ? tracer_n_steps(ctx) : 0; }
+
+int insta_tracer_generate_samples(insta_ctx* ctx, float* d_records, uint32_t stride_floats, uint32_t n_steps, int32_t frame_id, const float* d_extra_dims,
+                                  uint32_t* n_records, insta_stream stream) {
+	if (!ctx || !ctx->tracer || !d_records || n_steps == 0 || n_steps > 0xffffu) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_generate_samples: bad arguments");
+	return tracer_generate(ctx, d_records, stride_floats, n_steps, frame_id, d_extra_dims, n_records, (cudaStream_t)stream);
+}
+
+int insta_tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, const void* d_net_out_f16, uint32_t out_stride_elems, uint32_t n_steps,
+                           float* d_frame_rgba, float* d_frame_depth, uint32_t* h_n_alive, insta_stream stream) {
+	if (!ctx || !ctx->tracer || !d_records || !d_net_out_f16 || !d_frame_rgba || !d_frame_depth) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_composite: bad arguments");
+	return tracer_composite(ctx, d_records, stride_floats, d_net_out_f16, out_stride_elems, n_steps, d_frame_rgba, d_frame_depth, (int)ctx->render_opts.linear_colors,
+	                        h_n_alive, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

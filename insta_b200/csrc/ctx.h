@@ -147,6 +147,8 @@ struct insta_ctx {
 	uint32_t stage_cap = 0, stage_stride = 0;
 	std::atomic<uint64_t> launches{0};
 	std::mutex mu;
+	void* tracer = nullptr;           // insta::Tracer (nerf.cu)
+	insta_render_opts render_opts{};  // last options given to insta_tracer_init_rays
 };
 
 namespace insta {
@@ -160,4 +162,13 @@ int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_
 int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s);
 int launch_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, uint32_t* slots, cudaStream_t s);
 int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
+// nerf.cu
+void tracer_destroy(insta_ctx* ctx);
+int tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth, float* d_dbg_origin_t,
+                     float* d_dbg_dir_alive, uint32_t* h_n_alive, cudaStream_t s);
+uint32_t tracer_n_steps(const insta_ctx* ctx);
+int tracer_generate(insta_ctx* ctx, float* d_records, uint32_t stride, uint32_t n_steps, int32_t frame_id, const float* d_extra_dims, uint32_t* n_records,
+                    cudaStream_t s);
+int tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stride, const void* d_net_out, uint32_t out_stride, uint32_t n_steps, float* d_frame_rgba,
+                     float* d_frame_depth, int linear_colors, uint32_t* h_n_alive, cudaStream_t s);
 }  // namespace insta

@@ -1,0 +1,509 @@
+// Stage 3 of the INSTA hot path on sm_100a: ray setup, occupancy-grid skipping, sample generation and front-to-back
+// compositing of the render path.  Replaces (ngp/src/testbed_nerf.cu):
+//   init_rays_with_payload_kernel_nerf 1854-1960 (+ pixel_to_ray, ngp common_device.cuh:260-316, pinhole branch)
+//   advance_pos_nerf 634-690, generate_next_nerf_network_inputs 722-795, composite_kernel_nerf 797-1009 (Shade mode),
+//   compact_kernel_nerf 1829-1852, shade_kernel_nerf 1794-1827, and the driver NerfTracer::trace 2112-2244.
+//
+// Design (not a port):
+//   * ray state is SoA (two float4 + one uint2 + rgba float4 + depth per ray), ping-ponged between two sets; the 40-byte
+//     AoS NerfPayload of the reference would cost 2.5 uncoalesced sectors per field access;
+//   * ray setup and the skip to the first occupied cell are one kernel; compositing, stream compaction of the survivors
+//     (warp-aggregated atomics: one atomic per warp, not per ray) and the write of finished rays to the frame buffer are
+//     one kernel -- the reference runs compact + composite + shade as three passes over the ray state;
+//   * the occupancy bitfield (256 KB) is read through the read-only path and stays L1/L2-resident.
+//
+// Exactness: which cells are skipped and how many steps a ray takes are decided by fp32 comparisons on t and pos, so the
+// expressions below follow the reference's evaluation order, with the contractions nvcc applies to the reference build
+// written out as explicit fmaf (pos = o + d t is one FFMA per component, etc.).  tests/test_gpu_nerf.py checks ray
+// state, per-ray step counts and the generated records bit-for-bit against the reference's own kernels.
+#include <cuda_fp16.h>
+#include <float.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "ctx.h"
+
+namespace insta {
+namespace {
+
+constexpr uint32_t kGrid = 128;        // NERF_GRIDSIZE (ngp nerf.h:24-26)
+constexpr uint32_t kNerfSteps = 1024;  // NERF_STEPS
+constexpr uint32_t kCascades = 8;      // NERF_CASCADES
+__device__ __forceinline__ float sqrt3() { return 1.73205080757f; }
+__device__ __forceinline__ float min_stepsize() { return sqrt3() / kNerfSteps; }
+__device__ __forceinline__ float max_stepsize() { return min_stepsize() * (1 << (kCascades - 1)) * kNerfSteps / kGrid; }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }  // tcnn::clamp = max(lo, min(hi, v))
+// tcnn::clamp(val, lower, upper) = val < lower ? lower : (upper < val ? upper : val)   (tcnn common.h:243-246)
+__device__ __forceinline__ float tclamp(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }
+__device__ __forceinline__ int tclampi(int v, int lo, int hi) { return v < lo ? lo : (hi < v ? hi : v); }
+__device__ __forceinline__ float calc_dt(float t, float cone_angle) { return tclamp(t * cone_angle, min_stepsize(), max_stepsize()); }
+__device__ __forceinline__ float sgn(float x) { return copysignf(1.0f, x); }
+
+// ---- low-discrepancy sequence of the reference (ngp random_val.cuh:160-288): Sobol dims 0/1 + Laine-Karras scrambling ----
+__device__ __forceinline__ uint32_t lk_perm(uint32_t x, uint32_t seed) {
+	x += seed;
+	x ^= x * 0x6c50b47cu;
+	x ^= x * 0xb82f1e52u;
+	x ^= x * 0xc7afe638u;
+	x ^= x * 0x8d22f6e6u;
+	return x;
+}
+__device__ __forceinline__ uint32_t scramble(uint32_t x, uint32_t seed) { return __brev(lk_perm(__brev(x), seed)); }
+__device__ __forceinline__ uint32_t hash_combine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+// direction numbers of dimension 0 are 1 << (31 - bit): the van der Corput sequence
+__device__ __forceinline__ uint32_t sobol0(uint32_t index) { return __brev(index); }
+// dimension 1: v[0] = 0x80000000, v[k] = v[k-1] ^ (v[k-1] >> 1)   (same table as random_val.cuh:171-178)
+__device__ __forceinline__ uint32_t sobol1(uint32_t index) {
+	uint32_t x = 0, v = 0x80000000u;
+	for (uint32_t bit = 0; bit < 32; ++bit) {
+		if ((index >> bit) & 1u) x ^= v;
+		v ^= v >> 1;
+	}
+	return x;
+}
+__device__ __forceinline__ float ld_random_val(uint32_t index, uint32_t seed) {
+	const float S = float(1.0 / (1ull << 32));
+	index = scramble(index, seed);
+	return (float)scramble(sobol0(index), hash_combine(seed, 0)) * S;
+}
+// the two raw 32-bit values of ld_random_val_2d (value = (float)raw * 2^-32)
+__device__ __forceinline__ uint2 ld_random_raw_2d(uint32_t index, uint32_t seed) {
+	index = scramble(index, seed);
+	return make_uint2(scramble(sobol0(index), hash_combine(seed, 0)), scramble(sobol1(index), hash_combine(seed, 1)));
+}
+__device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
+// fract(0.5 - ld(0) + ld(spp)): the reference build folds 0.5 - ld(0) into a constant and contracts the rest into one FFMA
+__device__ __forceinline__ float2 ld_random_pixel_offset(uint32_t spp) {
+	const float S = float(1.0 / (1ull << 32));
+	const uint2 a = ld_random_raw_2d(0, 0xdeadbeefu), b = ld_random_raw_2d(spp, 0xdeadbeefu);
+	const float cx = __fsub_rn(0.5f, __fmul_rn((float)a.x, S)), cy = __fsub_rn(0.5f, __fmul_rn((float)a.y, S));
+	return make_float2(fractf(fmaf((float)b.x, S, cx)), fractf(fmaf((float)b.y, S, cy)));
+}
+
+// ---- occupancy grid (testbed_nerf.cu:313-337, 471-485; tcnn common_device.h:339-354) ----
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+	v = (v * 0x00010001u) & 0xFF0000FFu;
+	v = (v * 0x00000101u) & 0x0F00F00Fu;
+	v = (v * 0x00000011u) & 0xC30C30C3u;
+	v = (v * 0x00000005u) & 0x49249249u;
+	return v;
+}
+__device__ __forceinline__ uint32_t morton3D(uint32_t x, uint32_t y, uint32_t z) { return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2); }
+
+__device__ __forceinline__ int mip_from_pos(float px, float py, float pz, uint32_t max_cascade = kCascades - 1) {
+	int exponent;
+	const float maxval = fmaxf(fmaxf(fabsf(px - 0.5f), fabsf(py - 0.5f)), fabsf(pz - 0.5f));
+	frexpf(maxval, &exponent);
+	return min((int)max_cascade - 1, max(0, exponent + 1));
+}
+__device__ __forceinline__ int mip_from_dt(float dt, float px, float py, float pz, uint32_t max_cascade = kCascades - 1) {
+	const int mip = mip_from_pos(px, py, pz, max_cascade);
+	dt *= 2 * kGrid;
+	if (dt < 1.f) return mip;
+	int exponent;
+	frexpf(dt, &exponent);
+	return min((int)max_cascade - 1, max(exponent, mip));
+}
+__device__ __forceinline__ uint32_t cascaded_grid_idx_at(float px, float py, float pz, uint32_t mip) {
+	const float mip_scale = scalbnf(1.0f, -(int)mip);
+	// pos -= 0.5; pos *= mip_scale; pos += 0.5  -- the reference build contracts the last two into one FFMA
+	const float x = fmaf(px - 0.5f, mip_scale, 0.5f), y = fmaf(py - 0.5f, mip_scale, 0.5f), z = fmaf(pz - 0.5f, mip_scale, 0.5f);
+	const int ix = (int)(x * (float)kGrid), iy = (int)(y * (float)kGrid), iz = (int)(z * (float)kGrid);
+	return morton3D((uint32_t)tclampi(ix, 0, (int)kGrid - 1), (uint32_t)tclampi(iy, 0, (int)kGrid - 1), (uint32_t)tclampi(iz, 0, (int)kGrid - 1));
+}
+__device__ __forceinline__ bool occupied_at(float px, float py, float pz, const uint8_t* __restrict__ bitfield, uint32_t mip) {
+	const uint32_t idx = cascaded_grid_idx_at(px, py, pz, mip);
+	return (__ldg(bitfield + idx / 8 + (size_t)mip * (kGrid * kGrid * kGrid / 8)) >> (idx % 8)) & 1u;
+}
+// testbed_nerf.cu:186-208
+__device__ __forceinline__ float distance_to_next_voxel(float px, float py, float pz, float dx, float dy, float dz, float ix, float iy, float iz, uint32_t res) {
+	const float r = (float)res;
+	const float x = r * px, y = r * py, z = r * pz;
+	const float tx = (floorf(fmaf(0.5f, sgn(dx), x + 0.5f)) - x) * ix;
+	const float ty = (floorf(fmaf(0.5f, sgn(dy), y + 0.5f)) - y) * iy;
+	const float tz = (floorf(fmaf(0.5f, sgn(dz), z + 0.5f)) - z) * iz;
+	const float t = fminf(fminf(tx, ty), tz);
+	return fmaxf(t / r, 0.0f);
+}
+__device__ __forceinline__ float advance_to_next_voxel(float t, float cone_angle, float px, float py, float pz, float dx, float dy, float dz, float ix, float iy, float iz,
+                                                       uint32_t res) {
+	const float t_target = t + distance_to_next_voxel(px, py, pz, dx, dy, dz, ix, iy, iz, res);
+	do {
+		t += calc_dt(t, cone_angle);
+	} while (t < t_target);
+	return t;
+}
+__device__ __forceinline__ bool aabb_contains(const float* a, float x, float y, float z) {
+	return x >= a[0] && x <= a[3] && y >= a[1] && y <= a[4] && z >= a[2] && z <= a[5];
+}
+// BoundingBox::ray_intersect (ngp bounding_box.cuh:163-208), returns tmin (FLT_MAX when missed)
+__device__ __forceinline__ float aabb_ray_tmin(const float* a, float ox, float oy, float oz, float dx, float dy, float dz) {
+	float tmin = (a[0] - ox) / dx, tmax = (a[3] - ox) / dx;
+	if (tmin > tmax) { const float s = tmin; tmin = tmax; tmax = s; }
+	float tymin = (a[1] - oy) / dy, tymax = (a[4] - oy) / dy;
+	if (tymin > tymax) { const float s = tymin; tymin = tymax; tymax = s; }
+	if (tmin > tymax || tymin > tmax) return FLT_MAX;
+	if (tymin > tmin) tmin = tymin;
+	if (tymax < tmax) tmax = tymax;
+	float tzmin = (a[2] - oz) / dz, tzmax = (a[5] - oz) / dz;
+	if (tzmin > tzmax) { const float s = tzmin; tzmin = tzmax; tzmax = s; }
+	if (tmin > tzmax || tzmin > tmax) return FLT_MAX;
+	if (tzmin > tmin) tmin = tzmin;
+	return tmin;
+}
+
+struct RenderArgs {
+	insta_camera cam;
+	float render_aabb[6];
+	float train_aabb[6];
+	float cone_angle;
+	float min_transmittance;
+	const uint8_t* bitfield;
+	uint32_t min_mip;
+};
+
+struct RaySet {
+	float4* o_t;     // origin, t
+	float4* d_w;     // dir, max_weight
+	uint2* meta;     // pixel idx, n_steps
+	float4* rgba;
+	float* depth;
+};
+
+// one warp-aggregated append: returns the slot of this lane in the list counted by *counter (all lanes must call)
+__device__ __forceinline__ uint32_t warp_append(bool want, uint32_t* counter) {
+	const uint32_t mask = __ballot_sync(0xffffffffu, want);
+	if (mask == 0) return 0;
+	const int leader = __ffs(mask) - 1;
+	uint32_t base = 0;
+	if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, __popc(mask));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u));
+}
+
+// init_rays_with_payload_kernel_nerf + advance_pos_nerf.  Every pixel's final state goes to the debug arrays when given
+// (parity tests); alive rays are appended to `out`.
+__global__ void __launch_bounds__(128) nerf_init_rays_kernel(const RenderArgs a, RaySet out, uint32_t* __restrict__ n_alive, float4* __restrict__ frame_rgba,
+                                                             float* __restrict__ frame_depth, float4* __restrict__ dbg_o_t, float4* __restrict__ dbg_d_alive) {
+	const uint32_t x = threadIdx.x % 16 + 16 * blockIdx.x, y = threadIdx.x / 16 + 8 * blockIdx.y;
+	const uint32_t W = a.cam.resolution[0], H = a.cam.resolution[1];
+	const bool inside = x < W && y < H;
+	const uint32_t idx = x + W * y;
+	bool alive = false;
+	float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, t = 0;
+	if (inside) {
+		const float* m = a.cam.camera_matrix;  // column-major 3x4
+		// pixel_to_ray, pinhole branch (common_device.cuh:275-305); parallax shift is (0, 0, scale) in INSTA
+		const float2 off = ld_random_pixel_offset(a.cam.snap_to_pixel_centers ? 0u : a.cam.sample_index);
+		const float u = ((float)x + off.x) / (float)W, v = ((float)y + off.y) / (float)H;
+		const float lx = (u - a.cam.screen_center[0]) * (float)W / a.cam.focal_length[0];
+		const float ly = (v - a.cam.screen_center[1]) * (float)H / a.cam.focal_length[1];
+		// dir = R * (lx, ly, 1) as the reference build evaluates it: fma(col0, x, fma(col1, y, col2 * z))
+		float rx = fmaf(m[0], lx, fmaf(m[3], ly, m[6]));
+		float ry = fmaf(m[1], lx, fmaf(m[4], ly, m[7]));
+		float rz = fmaf(m[2], lx, fmaf(m[5], ly, m[8]));
+		ox = m[9]; oy = m[10]; oz = m[11];
+		frame_depth[idx] = 1e10f;
+		// ray.d.normalized(): d / sqrt(squaredNorm) when the squared norm is positive
+		const float n2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+		if (n2 > 0.f) {
+			const float n = sqrtf(n2);
+			rx /= n; ry /= n; rz /= n;
+		}
+		dx = rx; dy = ry; dz = rz;
+		t = fmaxf(aabb_ray_tmin(a.render_aabb, ox, oy, oz, dx, dy, dz), 0.05f) + 1e-6f;  // NERF_RENDERING_NEAR_DISTANCE
+		alive = aabb_contains(a.render_aabb, fmaf(dx, t, ox), fmaf(dy, t, oy), fmaf(dz, t, oz));
+		if (alive) {
+			// advance_pos_nerf: jitter the start, then skip empty cells
+			const float idx_ = 1.0f / dx, idy_ = 1.0f / dy, idz_ = 1.0f / dz;
+			float dt = calc_dt(t, a.cone_angle);
+			t = fmaf(ld_random_val(a.cam.sample_index, idx * 786433u), dt, t);
+			while (true) {
+				const float px = fmaf(dx, t, ox), py = fmaf(dy, t, oy), pz = fmaf(dz, t, oz);
+				if (!aabb_contains(a.render_aabb, px, py, pz)) {
+					alive = false;
+					break;
+				}
+				dt = calc_dt(t, a.cone_angle);
+				const uint32_t mip = max(a.min_mip, (uint32_t)mip_from_dt(dt, px, py, pz));
+				if (!a.bitfield || occupied_at(px, py, pz, a.bitfield, mip)) break;
+				t = advance_to_next_voxel(t, a.cone_angle, px, py, pz, dx, dy, dz, idx_, idy_, idz_, kGrid >> mip);
+			}
+		}
+		if (dbg_o_t) {
+			dbg_o_t[idx] = make_float4(ox, oy, oz, t);
+			dbg_d_alive[idx] = make_float4(dx, dy, dz, alive ? 1.0f : 0.0f);
+		}
+	}
+	const uint32_t slot = warp_append(alive, n_alive);
+	if (alive) {
+		out.o_t[slot] = make_float4(ox, oy, oz, t);
+		out.d_w[slot] = make_float4(dx, dy, dz, 0.0f);
+		out.meta[slot] = make_uint2(idx, 0u);
+		out.rgba[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+		out.depth[slot] = 0.0f;
+	}
+}
+
+// generate_next_nerf_network_inputs: up to n_steps occupied samples per alive ray, sample (i + j n_alive) of the record
+// buffer; records of steps the ray never reaches keep holder = -1 (so the deformation skips them).
+__global__ void __launch_bounds__(128) nerf_march_kernel(const RenderArgs a, RaySet rays, const uint32_t n_alive, float* __restrict__ records, const uint32_t stride,
+                                                         const uint32_t n_steps, const float frame_id, const float* __restrict__ extra_dims, const uint32_t n_extra) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_alive) return;
+	const float4 o_t = rays.o_t[i], d_w = rays.d_w[i];
+	const float ox = o_t.x, oy = o_t.y, oz = o_t.z, dx = d_w.x, dy = d_w.y, dz = d_w.z;
+	const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+	float t = o_t.w;
+	const float max_step = min_stepsize() * (1 << (kCascades - 1));
+	uint32_t j = 0;
+	for (; j < n_steps; ++j) {
+		float* rec = records + (size_t)(i + j * n_alive) * stride;
+		float px, py, pz, dt;
+		bool left = false;
+		while (true) {
+			px = fmaf(dx, t, ox); py = fmaf(dy, t, oy); pz = fmaf(dz, t, oz);
+			if (!aabb_contains(a.render_aabb, px, py, pz)) {
+				left = true;
+				break;
+			}
+			dt = calc_dt(t, a.cone_angle);
+			const uint32_t mip = max(a.min_mip, (uint32_t)mip_from_dt(dt, px, py, pz));
+			if (!a.bitfield || occupied_at(px, py, pz, a.bitfield, mip)) break;
+			t = advance_to_next_voxel(t, a.cone_angle, px, py, pz, dx, dy, dz, ix, iy, iz, kGrid >> mip);
+		}
+		if (left) {
+			rec[4] = -1.0f;
+			break;
+		}
+		// warp_position(pos, train_aabb) = (pos - min) / diag
+		const float wx = (px - a.train_aabb[0]) / (a.train_aabb[3] - a.train_aabb[0]);
+		const float wy = (py - a.train_aabb[1]) / (a.train_aabb[4] - a.train_aabb[1]);
+		const float wz = (pz - a.train_aabb[2]) / (a.train_aabb[5] - a.train_aabb[2]);
+		rec[0] = wx; rec[1] = wy; rec[2] = wz;
+		rec[3] = (dt - min_stepsize()) / (max_step - min_stepsize());  // warp_dt
+		rec[4] = frame_id;
+		rec[5] = wx; rec[6] = wy; rec[7] = wz;
+		rec[8] = (dx + 1.0f) * 0.5f; rec[9] = (dy + 1.0f) * 0.5f; rec[10] = (dz + 1.0f) * 0.5f;
+		for (uint32_t e = 0; e < n_extra; ++e) rec[11 + e] = extra_dims ? extra_dims[e] : 0.0f;
+		t += dt;
+	}
+	// steps after the one where the ray left the box are never composited; mark them as padding
+	for (uint32_t k = j + 1; k < n_steps; ++k) records[(size_t)(i + k * n_alive) * stride + 4] = -1.0f;
+	rays.o_t[i].w = t;
+	rays.meta[i].y = (rays.meta[i].y & 0xffff0000u) | j;  // low half: steps generated in this round (payload.n_steps)
+}
+
+__device__ __forceinline__ float logistic(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// composite_kernel_nerf (Shade mode, exponential density, logistic rgb) + compact_kernel_nerf + shade_kernel_nerf.
+// out_stride == 0: network output is 4 halves per sample (r, g, b, sigma); else out[i + c * out_stride] as the reference.
+__global__ void __launch_bounds__(128) nerf_composite_kernel(const RenderArgs a, RaySet rays, RaySet next, const uint32_t n_alive, const float* __restrict__ records,
+                                                             const uint32_t stride, const __half* __restrict__ net_out, const uint32_t out_stride, const uint32_t n_steps,
+                                                             const uint32_t current_step, uint32_t* __restrict__ n_next, float4* __restrict__ frame_rgba,
+                                                             float* __restrict__ frame_depth, const int linear_colors) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool alive = false, finished = false;
+	float4 rgba = make_float4(0, 0, 0, 0), o_t = rgba, d_w = rgba;
+	float depth = 0.f;
+	uint2 meta = make_uint2(0, 0);
+	if (i < n_alive) {
+		o_t = rays.o_t[i];
+		d_w = rays.d_w[i];
+		meta = rays.meta[i];
+		rgba = rays.rgba[i];
+		depth = rays.depth[i];
+		const uint32_t actual = meta.y & 0xffffu;
+		const float* cm = a.cam.camera_matrix;
+		const float max_step = min_stepsize() * (1 << (kCascades - 1));
+		uint32_t j = 0;
+		for (; j < actual; ++j) {
+			const size_t s = (size_t)i + (size_t)j * n_alive;
+			float o0, o1, o2, o3;
+			if (out_stride == 0) {
+				const uint2 raw = *reinterpret_cast<const uint2*>(net_out + s * 4);
+				const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+				o0 = lo.x; o1 = lo.y; o2 = hi.x; o3 = hi.y;
+			} else {
+				o0 = __half2float(net_out[s]); o1 = __half2float(net_out[s + out_stride]);
+				o2 = __half2float(net_out[s + 2 * (size_t)out_stride]); o3 = __half2float(net_out[s + 3 * (size_t)out_stride]);
+			}
+			const float* rec = records + s * stride;
+			// deformed_pos (floats 5-7) un-warped with the training box
+			const float qx = fmaf(rec[5], a.train_aabb[3] - a.train_aabb[0], a.train_aabb[0]);
+			const float qy = fmaf(rec[6], a.train_aabb[4] - a.train_aabb[1], a.train_aabb[1]);
+			const float qz = fmaf(rec[7], a.train_aabb[5] - a.train_aabb[2], a.train_aabb[2]);
+			const float T = 1.f - rgba.w;
+			const float dt = fmaf(rec[3], max_step - min_stepsize(), min_stepsize());  // unwarp_dt
+			const float alpha = 1.f - __expf(-__expf(o3) * dt);
+			const float weight = alpha * T;
+			rgba.x = fmaf(logistic(o0), weight, rgba.x);
+			rgba.y = fmaf(logistic(o1), weight, rgba.y);
+			rgba.z = fmaf(logistic(o2), weight, rgba.z);
+			rgba.w += weight;
+			if (weight > d_w.w) {
+				d_w.w = weight;
+				depth = fmaf(cm[6], qx - cm[9], fmaf(cm[7], qy - cm[10], cm[8] * (qz - cm[11])));
+			}
+			if (rgba.w > (1.0f - a.min_transmittance)) {
+				const float inv = rgba.w;
+				rgba.x /= inv; rgba.y /= inv; rgba.z /= inv; rgba.w /= inv;
+				break;
+			}
+		}
+		alive = !(j < n_steps);
+		if (!alive) meta.y = (j + current_step) << 16 | (meta.y & 0xffffu);
+		finished = !alive && rgba.w > 0.001f;
+	}
+	const uint32_t slot = warp_append(alive, n_next);
+	if (alive) {
+		next.o_t[slot] = o_t;
+		next.d_w[slot] = d_w;
+		next.meta[slot] = meta;
+		next.rgba[slot] = rgba;
+		next.depth[slot] = depth;
+	}
+	if (finished) {
+		// shade_kernel_nerf, Shade mode: accumulate in linear colours over the frame buffer
+		float4 c = rgba;
+		if (!linear_colors) {
+			auto s2l = [](float v) { return v <= 0.04045f ? v / 12.92f : powf((v + 0.055f) / 1.055f, 2.4f); };
+			c.x = s2l(c.x); c.y = s2l(c.y); c.z = s2l(c.z);
+		}
+		const float4 fb = frame_rgba[meta.x];
+		const float k = 1.0f - c.w;
+		frame_rgba[meta.x] = make_float4(fmaf(fb.x, k, c.x), fmaf(fb.y, k, c.y), fmaf(fb.z, k, c.z), fmaf(fb.w, k, c.w));
+		if (c.w > 0.2f) frame_depth[meta.x] = depth;
+	}
+}
+
+}  // namespace
+
+// ---- tracer state owned by the context ---------------------------------------------------------------------------------
+struct Tracer {
+	uint32_t cap = 0;
+	void* slab = nullptr;
+	RaySet set[2]{};
+	uint32_t* d_counters = nullptr;  // [0] alive (current), [1] alive (next)
+	uint32_t* h_counters = nullptr;  // pinned
+	uint32_t n_alive = 0, n_init = 0, cur = 0, step = 1;
+	RenderArgs args{};
+};
+
+static Tracer* tracer_of(insta_ctx* ctx) {
+	if (!ctx->tracer) ctx->tracer = new Tracer();
+	return (Tracer*)ctx->tracer;
+}
+
+void tracer_destroy(insta_ctx* ctx) {
+	Tracer* t = (Tracer*)ctx->tracer;
+	if (!t) return;
+	if (t->slab) cudaFree(t->slab);
+	if (t->d_counters) cudaFree(t->d_counters);
+	if (t->h_counters) cudaFreeHost(t->h_counters);
+	delete t;
+	ctx->tracer = nullptr;
+}
+
+static int tracer_reserve(insta_ctx* ctx, Tracer* t, uint32_t n) {
+	if (!t->d_counters) {
+		INSTA_CUDA(cudaMalloc(&t->d_counters, 64));
+		INSTA_CUDA(cudaHostAlloc(&t->h_counters, 64, cudaHostAllocDefault));
+	}
+	if (n <= t->cap) return INSTA_OK;
+	INSTA_CUDA(cudaDeviceSynchronize());
+	if (t->slab) cudaFree(t->slab);
+	t->slab = nullptr;
+	const size_t per = (size_t)n * (16 + 16 + 8 + 16 + 4);
+	INSTA_CUDA(cudaMalloc(&t->slab, per * 2));
+	unsigned char* p = (unsigned char*)t->slab;
+	for (int k = 0; k < 2; ++k) {
+		t->set[k].o_t = (float4*)p; p += (size_t)n * 16;
+		t->set[k].d_w = (float4*)p; p += (size_t)n * 16;
+		t->set[k].rgba = (float4*)p; p += (size_t)n * 16;
+		t->set[k].meta = (uint2*)p; p += (size_t)n * 8;
+		t->set[k].depth = (float*)p; p += (size_t)n * 4;
+	}
+	t->cap = n;
+	return INSTA_OK;
+}
+
+static void fill_args(const insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* o, RenderArgs& a) {
+	a.cam = *cam;
+	for (int k = 0; k < 6; ++k) {
+		a.render_aabb[k] = o && o->use_render_aabb ? o->render_aabb[k] : ctx->render_aabb[k];
+		a.train_aabb[k] = ctx->aabb[k];
+	}
+	a.cone_angle = o ? o->cone_angle_constant : 0.0f;
+	a.min_transmittance = o ? o->min_transmittance : 0.01f;
+	a.bitfield = o ? (const uint8_t*)o->d_density_grid_bitfield : nullptr;
+	a.min_mip = 0;
+}
+
+int tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth, float* d_dbg_origin_t,
+                     float* d_dbg_dir_alive, uint32_t* h_n_alive, cudaStream_t s) {
+	Tracer* t = tracer_of(ctx);
+	const uint32_t W = cam->resolution[0], H = cam->resolution[1];
+	if (W == 0 || H == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_init_rays: empty resolution");
+	int rc = tracer_reserve(ctx, t, W * H);
+	if (rc) return rc;
+	fill_args(ctx, cam, opts, t->args);
+	t->cur = 0;
+	t->step = 1;
+	t->n_init = W * H;
+	INSTA_CUDA(cudaMemsetAsync(t->d_counters, 0, 64, s));
+	const dim3 grid((W + 15) / 16, (H + 7) / 8);
+	nerf_init_rays_kernel<<<grid, 128, 0, s>>>(t->args, t->set[0], t->d_counters, (float4*)d_frame_rgba, d_frame_depth, (float4*)d_dbg_origin_t, (float4*)d_dbg_dir_alive);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	INSTA_CUDA(cudaMemcpyAsync(t->h_counters, t->d_counters, 4, cudaMemcpyDeviceToHost, s));
+	INSTA_CUDA(cudaStreamSynchronize(s));
+	t->n_alive = t->h_counters[0];
+	if (h_n_alive) *h_n_alive = t->n_alive;
+	return INSTA_OK;
+}
+
+uint32_t tracer_n_steps(const insta_ctx* ctx) {
+	const Tracer* t = (const Tracer*)ctx->tracer;
+	if (!t || t->n_alive == 0) return 0;
+	// NerfTracer::trace: clamp(n_rays_initialized / n_alive, 1, 8)  (testbed_nerf.cu:2172)
+	return std::min(std::max(t->n_init / t->n_alive, 1u), 8u);
+}
+
+int tracer_generate(insta_ctx* ctx, float* d_records, uint32_t stride, uint32_t n_steps, int32_t frame_id, const float* d_extra_dims, uint32_t* n_records,
+                    cudaStream_t s) {
+	Tracer* t = tracer_of(ctx);
+	if (n_records) *n_records = t->n_alive * n_steps;
+	if (t->n_alive == 0) return INSTA_OK;
+	if (stride < 11) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_generate_samples: stride < 11");
+	nerf_march_kernel<<<(t->n_alive + 127) / 128, 128, 0, s>>>(t->args, t->set[t->cur], t->n_alive, d_records, stride, n_steps, (float)frame_id, d_extra_dims,
+	                                                           stride - 11);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+int tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stride, const void* d_net_out, uint32_t out_stride, uint32_t n_steps, float* d_frame_rgba,
+                     float* d_frame_depth, int linear_colors, uint32_t* h_n_alive, cudaStream_t s) {
+	Tracer* t = tracer_of(ctx);
+	if (t->n_alive == 0) {
+		if (h_n_alive) *h_n_alive = 0;
+		return INSTA_OK;
+	}
+	uint32_t* cnt_next = t->d_counters + 1 + (t->cur ^ 1u);  // [1] / [2], alternating
+	INSTA_CUDA(cudaMemsetAsync(cnt_next, 0, 4, s));
+	nerf_composite_kernel<<<(t->n_alive + 127) / 128, 128, 0, s>>>(t->args, t->set[t->cur], t->set[t->cur ^ 1u], t->n_alive, d_records, stride, (const __half*)d_net_out,
+	                                                               out_stride, n_steps, t->step, cnt_next, (float4*)d_frame_rgba, d_frame_depth, linear_colors);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	INSTA_CUDA(cudaMemcpyAsync(t->h_counters, cnt_next, 4, cudaMemcpyDeviceToHost, s));
+	INSTA_CUDA(cudaStreamSynchronize(s));
+	t->cur ^= 1u;
+	t->step += n_steps;
+	t->n_alive = t->h_counters[0];
+	if (h_n_alive) *h_n_alive = t->n_alive;
+	return INSTA_OK;
+}
+
+}  // namespace insta

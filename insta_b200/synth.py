@@ -109,3 +109,55 @@ def make_grid_table(n_entries, seed=1337, scale=1.0):
     here is the U(+-1) variant so encodings are non-trivial."""
     rng = np.random.default_rng(seed)
     return ((rng.random((n_entries, 8), dtype=np.float32) * 2 - 1) * np.float32(scale)).astype(np.float16)
+
+
+def make_camera_matrix(yaw_deg, pitch_deg, distance=1.0, target=(0.5, 0.5, 0.5)):
+    """Camera-to-world 3x4 (columns right, down, forward, origin) of a camera at `distance` from `target` looking at it
+    (yaw in U(+-30), pitch in U(+-10) degrees)."""
+    yaw, pitch = np.deg2rad(yaw_deg), np.deg2rad(pitch_deg)
+    fwd = -np.array([np.sin(yaw) * np.cos(pitch), np.sin(pitch), np.cos(yaw) * np.cos(pitch)])
+    origin = np.asarray(target, np.float64) - fwd * distance
+    up = np.array([0.0, 1.0, 0.0])
+    right = np.cross(fwd, up)
+    right /= np.linalg.norm(right)
+    down = np.cross(fwd, right)
+    return np.stack([right, down, fwd, origin], axis=1).astype(np.float32)
+
+
+def random_camera(seed, distance=1.0):
+    rng = np.random.default_rng(77000 + int(seed))
+    return make_camera_matrix(rng.uniform(-30, 30), rng.uniform(-10, 10), distance)
+
+
+def morton3d(x, y, z):
+    def expand(v):
+        v = v.astype(np.uint64)
+        v = (v * 0x00010001) & 0xFF0000FF
+        v = (v * 0x00000101) & 0x0F00F00F
+        v = (v * 0x00000011) & 0xC30C30C3
+        v = (v * 0x00000005) & 0x49249249
+        return v
+
+    return (expand(x) | (expand(y) << 1) | (expand(z) << 2)).astype(np.uint32)
+
+
+def occupancy_bitfield(vertex_sets, radius=0.03, grid=128):
+    """Occupancy bitfield of cascade 0 (128^3 bits, Morton order, ngp testbed_nerf.cu:313-337): a cell is occupied when its
+    centre is within `radius` of a vertex of any of the given meshes (the tracked meshes are dense, ~5 mm edges, so this
+    is the union-of-frames shell of SURVEY.md 8d config 3).  Returns uint8 [grid^3 / 8]."""
+    from scipy.spatial import cKDTree
+
+    c = (np.arange(grid, dtype=np.float32) + 0.5) / grid
+    occ = np.zeros(grid ** 3, bool)
+    X, Y, Z = np.meshgrid(np.arange(grid), np.arange(grid), np.arange(grid), indexing="ij")
+    X, Y, Z = X.ravel(), Y.ravel(), Z.ravel()
+    centres = np.stack([c[X], c[Y], c[Z]], axis=1)
+    idx = morton3d(X, Y, Z)
+    for v in vertex_sets:
+        lo, hi = v.min(axis=0) - radius, v.max(axis=0) + radius
+        sel = np.all((centres >= lo) & (centres <= hi), axis=1)
+        d, _ = cKDTree(v).query(centres[sel], k=1, distance_upper_bound=radius)
+        hit = np.zeros(len(centres), bool)
+        hit[np.flatnonzero(sel)[np.isfinite(d)]] = True
+        occ[idx[hit]] = True
+    return np.packbits(occ, bitorder="little")

@@ -11,6 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_HOST_SO = os.path.join(HERE, "_ref", "libref_host.so")
+REF_NERF_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libref_nerf.so")
 REF_CUDA_SO = os.path.join(HERE, "_ref", "libref_cuda.so")
 
 # ngp::Triangle / ngp::TriangleBvhNode byte layouts (triangle.cuh:234-238, triangle_bvh.cuh:29-33)
