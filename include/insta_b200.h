@@ -192,6 +192,21 @@ INSTA_API int insta_tracer_composite(insta_ctx* ctx, const float* d_records, uin
                                      uint32_t n_steps, float* d_frame_rgba, float* d_frame_depth, uint32_t* h_n_alive, insta_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Network -- ngp::NerfNetwork<__half> (ngp/include/neural-graphics-primitives/nerf_network.h) with the shipped
+ * configuration (configs/nerf/main.json:33-69): HashGrid 16x8 -> (+16 expression rows) -> density MLP 144-64-64-16 ->
+ * (16 density outputs | SH degree 4 of the direction) -> colour MLP 32-64-64-64-16.  d_params_f16 is the trainer's fp16
+ * parameter buffer in its own order (density MLP, colour MLP, grid; nerf_network.h:492-525; weights row-major
+ * [out][in], tcnn src/fully_fused_mlp.cu:662-681), i.e. exactly `params_binary` of a snapshot.
+ * ------------------------------------------------------------------------------------------------------------ */
+INSTA_API uint32_t insta_network_n_params(const insta_ctx* ctx); /* 25,600 + grid = 25,741,888 for the shipped config */
+/* NerfNetwork::inference_mixed_precision_impl (nerf_network.h:159-232): one fused kernel (encode + both MLPs + SH).
+ * d_records: n sample records (position floats 0-2, direction floats 8-10 stored as (d+1)/2, the last exp_params floats =
+ * expression coefficients).  Output fp16: out_stride_elems == 0 -> 4 halves per sample (r, g, b, sigma logits);
+ * else out[i + c * out_stride_elems], c = 0..3 -- the reference's row-major rgbsigma matrix (testbed_nerf.cu:2197). */
+INSTA_API int insta_network_inference(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_out_f16,
+                                      uint32_t out_stride_elems, insta_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience (the end-to-end path a caller without device buffers uses): H2D of the records, stage 1,
  * stage 2, D2H of the mutated records and of the fp16 encodings, chunked and double-buffered on internal streams.
  * h_coords / h_out_soa_f16 should be pinned (cudaHostAlloc / insta_host_alloc) for full PCIe speed.

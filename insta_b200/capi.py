@@ -76,6 +76,7 @@ EXPORTS = [
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
+    "insta_network_n_params", "insta_network_inference",
     "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
 
@@ -98,6 +99,7 @@ def load_library(build_if_missing=True):
     lib.insta_grid_n_params.restype = C.c_uint32
     lib.insta_launch_count.restype = C.c_uint64
     lib.insta_tracer_n_steps.restype = C.c_uint32
+    lib.insta_network_n_params.restype = C.c_uint32
     lib.insta_ctx_destroy.restype = None
     lib.insta_params_default.restype = None
     for name in EXPORTS:
@@ -264,6 +266,18 @@ class Context:
         n, stride = pos.shape
         self._check(self.lib.insta_hash_slots(self.h, _dev(pos), C.c_uint32(stride), C.c_uint32(n), _dev(slots), _stream(stream)))
         return slots
+
+    # ---- network ----
+    @property
+    def network_n_params(self):
+        return self.lib.insta_network_n_params(self.h)
+
+    def network_inference(self, records, params, out, out_stride=0, n=None, stream=None):
+        """records float32 [n, stride]; params fp16 [network_n_params]; out fp16 [n, 4] (out_stride 0) or [rows, out_stride]."""
+        n = records.shape[0] if n is None else n
+        self._check(self.lib.insta_network_inference(self.h, _dev(records), C.c_uint32(records.shape[1]), C.c_uint32(n), _dev(params), _dev(out),
+                                                     C.c_uint32(out_stride), _stream(stream)))
+        return out
 
     # ---- stage 3: render tracer (NerfTracer) ----
     def tracer_init_rays(self, cam, frame_rgba, frame_depth, bitfield=None, render_aabb=None, cone_angle=0.0, min_transmittance=0.01, linear_colors=False,

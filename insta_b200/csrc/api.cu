@@ -439,6 +439,19 @@ int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_flo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+uint32_t insta_network_n_params(const insta_ctx* ctx) { return ctx ? network_n_params(ctx) : 0; }
+
+int insta_network_inference(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_out_f16,
+                            uint32_t out_stride_elems, insta_stream stream) {
+	if (!ctx || ((!d_records || !d_params_f16 || !d_out_f16) && n)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: bad arguments");
+	if (stride_floats < 11 + ctx->p.exp_params + ctx->p.geo_params) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: stride smaller than NerfCoordinate + extra dims");
+	if (reinterpret_cast<uintptr_t>(d_params_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: parameters must be 16-byte aligned");
+	if (ctx->p.n_levels != 16 || ctx->p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: the density MLP expects 16 levels x 8 features");
+	if (out_stride_elems != 0 && out_stride_elems < n) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: out_stride_elems < n");
+	return launch_network_fwd(ctx, d_records, stride_floats, n, d_params_f16, d_out_f16, out_stride_elems, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 int insta_tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth,
                            float* d_dbg_origin_t, float* d_dbg_dir_alive, uint32_t* h_n_alive, insta_stream stream) {
 	if (!ctx || !cam || !d_frame_depth) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_init_rays: bad arguments");

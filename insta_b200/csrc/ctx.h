@@ -162,6 +162,9 @@ int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_
 int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s);
 int launch_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, uint32_t* slots, cudaStream_t s);
 int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
+// mlp.cu
+uint32_t network_n_params(const insta_ctx* ctx);
+int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s);
 // nerf.cu
 void tracer_destroy(insta_ctx* ctx);
 int tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth, float* d_dbg_origin_t,

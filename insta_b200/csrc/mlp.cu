@@ -1,0 +1,398 @@
+// The NeRF network of the INSTA hot path on sm_100a, inference direction: hash-grid encoding, density MLP, spherical
+// harmonics of the view direction and colour MLP fused into ONE persistent kernel.  Replaces
+//   ngp::NerfNetwork::inference_mixed_precision_impl (ngp nerf_network.h:159-232) and what it launches:
+//   kernel_grid (tcnn encodings/grid.h:138-310), extract_expressions (nerf_network.h:86-105), kernel_mlp_fused x2
+//   (tcnn src/fully_fused_mlp.cu:500-634), kernel_sh (tcnn encodings/spherical_harmonics.h:47-153), extract_density (34-46).
+// The reference materialises the 128 x N fp16 feature matrix (+ 16 expression rows) in HBM -- 1.2 GB per 4M-sample batch
+// written by the encoder and read back by the MLP; here the features go from the gathers straight into the shared-memory
+// operand tile of the first GEMM and never leave the SM.
+//
+// Structure of a CTA (persistent, one per SM, 384 threads):
+//   warps 4-11 "encoders": per 128-sample tile, 2 threads per sample x 8 levels each: 8 corner gathers (128-bit loads, table
+//              L2-resident), trilinear interpolation with the reference's fp16 accumulation, one 16-byte store per level
+//              into the K-major operand tile A0 (double buffered); the 16 expression floats fill K = 128..143.
+//   warps 0-3  "MLP": one elected thread issues tcgen05.mma (M = 128 samples, N = 64 / 16, K = 16 per instruction, fp16
+//              operands from shared memory, fp32 accumulators in TENSOR MEMORY); all four warps run the epilogues
+//              (tcgen05.ld of their 32 TMEM lanes, ReLU, fp16, store as the next layer's operand tile).
+//   density MLP 144 -> 64 -> 64 -> 16, colour MLP (16 density features | 16 SH) 32 -> 64 -> 64 -> 64 -> 16 (3 used): seven
+//   dependent GEMMs per tile (~51 kFLOP/sample), hidden behind the gathers of the next tile through the mbarrier ring.
+// Operand tiles use the canonical no-swizzle K-major UMMA layout: 8 rows x 16 bytes core matrices, 128 bytes apart along
+// M/N (SBO), row-count x 16 bytes apart along K (LBO); a thread that owns a row writes 16-byte chunks that are conflict-free
+// across the warp.
+//
+// Numerics: activations are rounded to fp16 between layers exactly where the reference stores them (its wmma accumulators are
+// fp16 as well, so it rounds more often); accumulation here is fp32.  tests/test_gpu_network.py compares against an fp32
+// PyTorch evaluation of the same fp16 weights / fp16 activations; tolerance stated there.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "ctx.h"
+#include "grid_device.cuh"
+
+namespace insta {
+namespace {
+using namespace griddev;
+
+constexpr int kTileM = 128;
+constexpr int kMlpWarps = 4, kEncWarps = 8;
+constexpr int kMlpThreads = kMlpWarps * 32, kEncThreads = kEncWarps * 32, kNetThreads = kMlpThreads + kEncThreads;
+constexpr int kWidth = 64;        // n_neurons
+constexpr int kInDensity = 144;   // 128 grid features + 16 expression dims
+constexpr int kInRgb = 32;        // 16 density outputs + 16 SH
+constexpr int kOutPad = 16;       // padded output width
+constexpr uint32_t kTmemCols = 64;
+
+// parameter offsets (halves) in the trainer's order: density MLP, rgb MLP, grid (ngp nerf_network.h:492-525)
+constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kWidth * kInDensity, kOffW3 = kOffW2 + kWidth * kWidth;
+constexpr uint32_t kOffV1 = kOffW3 + kOutPad * kWidth, kOffV2 = kOffV1 + kWidth * kInRgb, kOffV3 = kOffV2 + kWidth * kWidth;
+constexpr uint32_t kOffV4 = kOffV3 + kWidth * kWidth, kOffGrid = kOffV4 + kOutPad * kWidth;
+static_assert(kOffGrid == 25600, "MLP parameter count of the shipped config");
+
+// shared-memory map (bytes)
+constexpr uint32_t kChunkA = kTileM * 16;                       // one K-chunk (8 halves) of a 128-row operand tile
+constexpr uint32_t kBytesA0 = (kInDensity / 8) * kChunkA;       // 36,864
+constexpr uint32_t kBytesH = (kWidth / 8) * kChunkA;            // 16,384
+constexpr uint32_t kBytesA3 = (kInRgb / 8) * kChunkA;           // 8,192
+constexpr uint32_t kSmA0 = 0;                                   // two buffers
+constexpr uint32_t kSmH = kSmA0 + 2 * kBytesA0;                 // two buffers
+constexpr uint32_t kSmA3 = kSmH + 2 * kBytesH;
+constexpr uint32_t kSmW1 = kSmA3 + kBytesA3;
+constexpr uint32_t kSmW2 = kSmW1 + kWidth * kInDensity * 2;
+constexpr uint32_t kSmW3 = kSmW2 + kWidth * kWidth * 2;
+constexpr uint32_t kSmV1 = kSmW3 + kOutPad * kWidth * 2;
+constexpr uint32_t kSmV2 = kSmV1 + kWidth * kInRgb * 2;
+constexpr uint32_t kSmV3 = kSmV2 + kWidth * kWidth * 2;
+constexpr uint32_t kSmV4 = kSmV3 + kWidth * kWidth * 2;
+constexpr uint32_t kSmBar = kSmV4 + kOutPad * kWidth * 2;       // 5 mbarriers + tmem base
+constexpr uint32_t kSmTotal = kSmBar + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mlp_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMlpThreads) : "memory"); }
+
+// K-major, no swizzle: start address, LBO (K direction), SBO (M/N direction), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+	return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16: D = F32, A = B = F16, both K-major, dense
+__device__ __forceinline__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+	    "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[128 x N] (TMEM) = A[128 x K] * B[N x K]^T, operands in the canonical layout described in the header
+template <int N, int K>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t mma_bar) {
+	constexpr uint32_t idesc = umma_idesc(kTileM, N);
+#pragma unroll
+	for (int j = 0; j < K / 16; ++j) {
+		const uint64_t ad = umma_desc(a_saddr + j * 2 * kChunkA, kChunkA, 128);
+		const uint64_t bd = umma_desc(b_saddr + j * 2 * (N * 16), N * 16, 128);
+		umma_f16(tmem, ad, bd, idesc, j > 0 ? 1u : 0u);
+	}
+	umma_commit(mma_bar);
+}
+
+// 32 lanes x 32 bit, 16 consecutive columns per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+	uint32_t r[16];
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+	               "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+	             : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+	const __half2 h = __floats2half2_rn(a, b);
+	return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// TMEM accumulators of this thread's row -> ReLU -> fp16 -> operand tile of the next layer (N_COLS / 8 chunks of 16 bytes)
+template <int N_COLS, bool RELU>
+__device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, unsigned char* tile, uint32_t row, float* keep0 /* nullable: receives column 0 as fp16-rounded */) {
+	unsigned char* dst = tile + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+	for (int c0 = 0; c0 < N_COLS; c0 += 16) {
+		float v[16];
+		tmem_ld16(taddr + c0, v);
+		if (RELU) {
+#pragma unroll
+			for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.0f);
+		}
+		const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+		const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+		*reinterpret_cast<uint4*>(dst + (c0 / 8) * kChunkA) = lo;
+		*reinterpret_cast<uint4*>(dst + (c0 / 8 + 1) * kChunkA) = hi;
+		if (keep0 && c0 == 0) *keep0 = __half2float(__float2half_rn(v[0]));
+	}
+}
+
+// degree-4 spherical harmonics of dir * 2 - 1 (tcnn spherical_harmonics.h:62-100), 16 coefficients as fp16
+__device__ __forceinline__ void sh4(float x, float y, float z, uint4& lo, uint4& hi) {
+	const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+	float o[16];
+	o[0] = 0.28209479177387814f;
+	o[1] = -0.48860251190291987f * y;
+	o[2] = 0.48860251190291987f * z;
+	o[3] = -0.48860251190291987f * x;
+	o[4] = 1.0925484305920792f * xy;
+	o[5] = -1.0925484305920792f * yz;
+	o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+	o[7] = -1.0925484305920792f * xz;
+	o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+	o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+	o[10] = 2.8906114426405538f * xy * z;
+	o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+	o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+	o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+	o[14] = 1.4453057213202769f * z * (x2 - y2);
+	o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+	lo = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+	hi = make_uint4(pack2(o[8], o[9]), pack2(o[10], o[11]), pack2(o[12], o[13]), pack2(o[14], o[15]));
+}
+
+// weights [N][K] row-major (tcnn fully_fused_mlp.cu:662-681) -> canonical K-major operand layout
+__device__ __forceinline__ void stage_weights(unsigned char* dst, const __half* __restrict__ w, int N, int K) {
+	const int chunks = N * (K / 8);
+	for (int t = threadIdx.x; t < chunks; t += blockDim.x) {
+		const int n = t / (K / 8), kc = t - n * (K / 8);
+		const uint4 v = __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * K + kc * 8));
+		*reinterpret_cast<uint4*>(dst + kc * (N * 16) + (n >> 3) * 128 + (n & 7) * 16) = v;
+	}
+}
+
+struct NetArgs {
+	const float* records;
+	uint32_t stride, n, n_extra;
+	const __half* params;   // MLP weights then the grid table
+	__half* out;
+	uint32_t out_stride;    // 0: 4 halves per sample; else out[i + c * out_stride]
+	GridLevels L;
+};
+
+__global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const __grid_constant__ NetArgs a) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const uint32_t sbase = smem_u32(smem);
+	const uint32_t bar_full0 = sbase + kSmBar, bar_empty0 = sbase + kSmBar + 16, bar_mma = sbase + kSmBar + 32;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 40);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t n_tiles = (a.n + kTileM - 1) / kTileM;
+
+	// ---- one-time setup: weights, barriers, tensor memory ----
+	stage_weights(smem + kSmW1, a.params + kOffW1, kWidth, kInDensity);
+	stage_weights(smem + kSmW2, a.params + kOffW2, kWidth, kWidth);
+	stage_weights(smem + kSmW3, a.params + kOffW3, kOutPad, kWidth);
+	stage_weights(smem + kSmV1, a.params + kOffV1, kWidth, kInRgb);
+	stage_weights(smem + kSmV2, a.params + kOffV2, kWidth, kWidth);
+	stage_weights(smem + kSmV3, a.params + kOffV3, kWidth, kWidth);
+	stage_weights(smem + kSmV4, a.params + kOffV4, kOutPad, kWidth);
+	if (threadIdx.x == 0) {
+		mbar_init(bar_full0, kEncWarps);
+		mbar_init(bar_full0 + 8, kEncWarps);
+		mbar_init(bar_empty0, 1);
+		mbar_init(bar_empty0 + 8, 1);
+		mbar_init(bar_mma, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 0) {
+		__syncwarp();
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	fence_proxy_async();  // the staged weights are read by the tensor core through the async proxy
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp >= kMlpWarps) {
+		// =================================== encoders ===================================
+		const uint32_t e = threadIdx.x - kMlpThreads;
+		const uint32_t row = e & (kTileM - 1), half_id = e >> 7;  // levels [8 half_id, 8 half_id + 8)
+		const uint4* table = reinterpret_cast<const uint4*>(a.params + kOffGrid);
+		uint32_t it = 0;
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+			const uint32_t b = it & 1u;
+			mbar_wait(bar_empty0 + 8 * b, ((it >> 1) & 1u) ^ 1u);
+			unsigned char* A0 = smem + kSmA0 + b * kBytesA0 + (row >> 3) * 128 + (row & 7) * 16;
+			const uint32_t i = tile * kTileM + row;
+			if (i < a.n) {
+				const float* rec = a.records + (size_t)i * a.stride;
+				const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
+#pragma unroll 2
+				for (uint32_t l = 0; l < 8; ++l) {
+					const uint32_t level = half_id * 8 + l;
+					__half2 acc[4] = {__half2(), __half2(), __half2(), __half2()};
+					if (level < a.L.n_levels) {
+						const Corner c = pos_fract3(px, py, pz, a.L.scale[level]);
+						if (a.L.hashed[level]) encode_one<true>(table + a.L.offset[level], c, a.L.size[level], 0, 0, acc);
+						else encode_one<false>(table + a.L.offset[level], c, a.L.size[level], a.L.mul1[level], a.L.mul2[level], acc);
+					}
+					*reinterpret_cast<uint4*>(A0 + level * kChunkA) =
+					    make_uint4(*reinterpret_cast<uint32_t*>(&acc[0]), *reinterpret_cast<uint32_t*>(&acc[1]), *reinterpret_cast<uint32_t*>(&acc[2]),
+					               *reinterpret_cast<uint32_t*>(&acc[3]));
+				}
+				// expression dims: floats [stride - n_extra, stride) -> K = 128 + 8 half_id .. (extract_expressions)
+				float ex[8];
+#pragma unroll
+				for (uint32_t k = 0; k < 8; ++k) {
+					const uint32_t d = half_id * 8 + k;
+					ex[k] = d < a.n_extra ? __ldg(rec + a.stride - a.n_extra + d) : 0.0f;
+				}
+				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = make_uint4(pack2(ex[0], ex[1]), pack2(ex[2], ex[3]), pack2(ex[4], ex[5]), pack2(ex[6], ex[7]));
+			} else {
+				const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+				for (uint32_t l = 0; l < 8; ++l) *reinterpret_cast<uint4*>(A0 + (half_id * 8 + l) * kChunkA) = z;
+				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = z;
+			}
+			fence_proxy_async();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_full0 + 8 * b);
+		}
+	} else {
+		// =================================== MLP warps ===================================
+		const uint32_t row = threadIdx.x;                        // == TMEM lane
+		const uint32_t taddr = tmem_base + ((warp * 32u) << 16);  // this warp's lane quadrant
+		unsigned char* H0 = smem + kSmH;
+		unsigned char* H1 = smem + kSmH + kBytesH;
+		unsigned char* A3 = smem + kSmA3;
+		const uint32_t sH0 = sbase + kSmH, sH1 = sH0 + kBytesH, sA3 = sbase + kSmA3;
+		uint32_t mma_phase = 0, it = 0;
+		const bool issuer = threadIdx.x == 0;
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+			const uint32_t b = it & 1u;
+			const uint32_t i = tile * kTileM + row;
+			// SH of the view direction while the first GEMM is in flight
+			float dx = 0.5f, dy = 0.5f, dz = 0.5f;
+			if (i < a.n) {
+				const float* rec = a.records + (size_t)i * a.stride;
+				dx = __ldg(rec + 8); dy = __ldg(rec + 9); dz = __ldg(rec + 10);
+			}
+			// ---- density layer 1: A0 (144) -> 64 ----
+			mbar_wait(bar_full0 + 8 * b, (it >> 1) & 1u);
+			tc_fence_after();
+			if (issuer) issue_gemm<kWidth, kInDensity>(tmem_base, sbase + kSmA0 + b * kBytesA0, sbase + kSmW1, bar_mma);
+			{
+				uint4 lo, hi;
+				sh4(dx * 2.f - 1.f, dy * 2.f - 1.f, dz * 2.f - 1.f, lo, hi);
+				unsigned char* dst = A3 + (row >> 3) * 128 + (row & 7) * 16;
+				*reinterpret_cast<uint4*>(dst + 2 * kChunkA) = lo;
+				*reinterpret_cast<uint4*>(dst + 3 * kChunkA) = hi;
+			}
+			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+			tc_fence_after();
+			if (issuer) mbar_arrive(bar_empty0 + 8 * b);  // A0[b] has been consumed: the encoders may refill it
+			epilogue_to_tile<kWidth, true>(taddr, H0, row, nullptr);
+			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			// ---- density layer 2: 64 -> 64 ----
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sbase + kSmW2, bar_mma);
+			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+			tc_fence_after();
+			epilogue_to_tile<kWidth, true>(taddr, H1, row, nullptr);
+			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			// ---- density output: 64 -> 16, no activation; column 0 is the density logit ----
+			if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH1, sbase + kSmW3, bar_mma);
+			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+			tc_fence_after();
+			float sigma = 0.f;
+			epilogue_to_tile<kOutPad, false>(taddr, A3, row, &sigma);
+			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			// ---- colour layer 1: (16 density | 16 SH) -> 64 ----
+			if (issuer) issue_gemm<kWidth, kInRgb>(tmem_base, sA3, sbase + kSmV1, bar_mma);
+			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+			tc_fence_after();
+			epilogue_to_tile<kWidth, true>(taddr, H0, row, nullptr);
+			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			// ---- colour layers 2, 3 ----
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sbase + kSmV2, bar_mma);
+			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+			tc_fence_after();
+			epilogue_to_tile<kWidth, true>(taddr, H1, row, nullptr);
+			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH1, sbase + kSmV3, bar_mma);
+			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+			tc_fence_after();
+			epilogue_to_tile<kWidth, true>(taddr, H0, row, nullptr);
+			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			// ---- colour output: 64 -> 16 (3 used) ----
+			if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH0, sbase + kSmV4, bar_mma);
+			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
+			tc_fence_after();
+			float o[16];
+			tmem_ld16(taddr, o);
+			tc_fence_before();
+			if (i < a.n) {
+				const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], sigma);
+				if (a.out_stride == 0) {
+					*reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
+				} else {
+					a.out[i] = __low2half(rg);
+					a.out[i + (size_t)a.out_stride] = __high2half(rg);
+					a.out[i + 2 * (size_t)a.out_stride] = __low2half(bs);
+					a.out[i + 3 * (size_t)a.out_stride] = __high2half(bs);
+				}
+			}
+			// the next tile's first GEMM overwrites the accumulator columns: all reads above must have completed
+			mlp_bar_sync();
+		}
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
+}  // namespace
+
+uint32_t network_n_params(const insta_ctx* ctx) { return kOffGrid + ctx->levels.offset[ctx->levels.n_levels] * 8u; }
+
+int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s) {
+	if (n == 0) return INSTA_OK;
+	NetArgs a{};
+	a.records = d_records;
+	a.stride = stride;
+	a.n = n;
+	a.n_extra = ctx->p.exp_params + ctx->p.geo_params;
+	a.params = (const __half*)d_params;
+	a.out = (__half*)d_out;
+	a.out_stride = out_stride;
+	a.L = ctx->levels;
+	if (a.n_extra > 16) INSTA_FAIL(INSTA_ERR_INVALID, "network: more than 16 extra dims are not supported by the density MLP input (144 = 128 + 16)");
+	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+	const uint32_t n_tiles = (n + kTileM - 1) / kTileM;
+	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
+	nerf_network_fwd_kernel<<<grid, kNetThreads, kSmTotal, s>>>(a);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+}  // namespace insta
