@@ -172,6 +172,20 @@ typedef struct insta_render_opts {
 	uint32_t reserved_;
 } insta_render_opts;
 
+typedef struct insta_render_stats {
+	uint32_t iterations; /* march iterations (= stream syncs) */
+	uint32_t reserved_;
+	uint64_t samples;    /* sample records generated (incl. padding of rays that left the box) */
+} insta_render_stats;
+
+/* Testbed::render_nerf (ngp/src/testbed_nerf.cu:2320-2440): rays from the camera, march / deform with frame frame_id
+ * (rta::Core::render_deformed; frame_id < 0 = no deformation) / network / composite until no ray is alive, result
+ * accumulated into d_frame_rgba (res.x*res.y float4, zeroed first) and d_frame_depth.  d_extra_dims: the frame's exp_params
+ * expression coefficients (Testbed::get_inference_extra_dims), NULL = zeros.  Synchronises the stream once per march
+ * iteration like NerfTracer::trace (testbed_nerf.cu:2164-2165). */
+INSTA_API int insta_render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, const void* d_params_f16,
+                                 const float* d_extra_dims, float* d_frame_rgba, float* d_frame_depth, insta_render_stats* h_stats, insta_stream stream);
+
 /* NerfTracer::init_rays_from_camera: init_rays_with_payload_kernel_nerf + advance_pos_nerf (testbed_nerf.cu:1854-1960,
  * 634-690, 2030-2110).  d_frame_rgba (res.x*res.y float4) is left untouched, d_frame_depth is set to 1e10 like the
  * reference.  d_dbg_* (nullable, res.x*res.y float4 each): per-pixel (origin, t) and (dir, alive) after the skip to the first

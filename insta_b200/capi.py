@@ -47,6 +47,10 @@ class Camera(C.Structure):
                 ("sample_index", C.c_uint32), ("snap_to_pixel_centers", C.c_uint32)]
 
 
+class RenderStats(C.Structure):
+    _fields_ = [("iterations", C.c_uint32), ("reserved_", C.c_uint32), ("samples", C.c_uint64)]
+
+
 class RenderOpts(C.Structure):
     _fields_ = [("d_density_grid_bitfield", C.c_void_p), ("cone_angle_constant", C.c_float), ("min_transmittance", C.c_float), ("use_render_aabb", C.c_uint32),
                 ("render_aabb", C.c_float * 6), ("linear_colors", C.c_uint32), ("reserved_", C.c_uint32)]
@@ -77,7 +81,7 @@ EXPORTS = [
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
     "insta_network_n_params", "insta_network_inference",
-    "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
+    "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
 
 _lib = None
@@ -295,6 +299,26 @@ class Context:
         self._check(self.lib.insta_tracer_init_rays(self.h, C.byref(cam), C.byref(o), _dev(frame_rgba), _dev(frame_depth), _dev(dbg_origin_t), _dev(dbg_dir_alive),
                                                     C.byref(n), _stream(stream)))
         return n.value
+
+    def _opts(self, bitfield, render_aabb, cone_angle, min_transmittance, linear_colors):
+        o = RenderOpts()
+        o.d_density_grid_bitfield = bitfield.data_ptr() if bitfield is not None else None
+        o.cone_angle_constant = cone_angle
+        o.min_transmittance = min_transmittance
+        o.use_render_aabb = int(render_aabb is not None)
+        for k in range(6):
+            o.render_aabb[k] = float(render_aabb[k]) if render_aabb is not None else 0.0
+        o.linear_colors = int(linear_colors)
+        return o
+
+    def render_frame(self, cam, frame_id, params, frame_rgba, frame_depth, bitfield=None, extra_dims=None, render_aabb=None, cone_angle=0.0,
+                     min_transmittance=0.01, linear_colors=False, stream=None):
+        """Testbed::render_nerf with this library's deformation + network; returns (iterations, samples)."""
+        o = self._opts(bitfield, render_aabb, cone_angle, min_transmittance, linear_colors)
+        st = RenderStats()
+        self._check(self.lib.insta_render_frame(self.h, C.byref(cam), C.byref(o), C.c_int32(frame_id), _dev(params), _dev(extra_dims), _dev(frame_rgba),
+                                                _dev(frame_depth), C.byref(st), _stream(stream)))
+        return st.iterations, st.samples
 
     def tracer_n_steps(self):
         return self.lib.insta_tracer_n_steps(self.h)

@@ -461,6 +461,16 @@ int insta_tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_
 	return tracer_init_rays(ctx, cam, &ctx->render_opts, d_frame_rgba, d_frame_depth, d_dbg_origin_t, d_dbg_dir_alive, h_n_alive, (cudaStream_t)stream);
 }
 
+int insta_render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, const void* d_params_f16, const float* d_extra_dims,
+                       float* d_frame_rgba, float* d_frame_depth, insta_render_stats* h_stats, insta_stream stream) {
+	if (!ctx || !cam || !d_params_f16 || !d_frame_rgba || !d_frame_depth) INSTA_FAIL(INSTA_ERR_INVALID, "insta_render_frame: bad arguments");
+	if (ctx->n_faces == 0 && !(opts && opts->use_render_aabb)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_render_frame: no canonical mesh and no render_aabb");
+	if (frame_id >= (int32_t)ctx->frames.size()) INSTA_FAIL(INSTA_ERR_INVALID, "insta_render_frame: frame_id out of range");
+	if (reinterpret_cast<uintptr_t>(d_params_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_render_frame: parameters must be 16-byte aligned");
+	ctx->render_opts = opts ? *opts : insta_render_opts{nullptr, 0.f, 0.01f, 0, {0, 0, 0, 1, 1, 1}, 0, 0};
+	return render_frame(ctx, cam, &ctx->render_opts, frame_id, d_params_f16, d_extra_dims, d_frame_rgba, d_frame_depth, h_stats, (cudaStream_t)stream);
+}
+
 uint32_t insta_tracer_n_steps(const insta_ctx* ctx) { return ctx ? tracer_n_steps(ctx) : 0; }
 
 int insta_tracer_generate_samples(insta_ctx* ctx, float* d_records, uint32_t stride_floats, uint32_t n_steps, int32_t frame_id, const float* d_extra_dims,

@@ -174,4 +174,6 @@ int tracer_generate(insta_ctx* ctx, float* d_records, uint32_t stride, uint32_t 
                     cudaStream_t s);
 int tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stride, const void* d_net_out, uint32_t out_stride, uint32_t n_steps, float* d_frame_rgba,
                      float* d_frame_depth, int linear_colors, uint32_t* h_n_alive, cudaStream_t s);
+int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, const void* d_params, const float* d_extra_dims,
+                 float* d_frame_rgba, float* d_frame_depth, insta_render_stats* stats, cudaStream_t s);
 }  // namespace insta

@@ -383,6 +383,10 @@ __global__ void __launch_bounds__(128) nerf_composite_kernel(const RenderArgs a,
 // ---- tracer state owned by the context ---------------------------------------------------------------------------------
 struct Tracer {
 	uint32_t cap = 0;
+	float* d_records = nullptr;   // render_frame scratch: n_pixels records
+	void* d_net_out = nullptr;    // n_pixels x 4 halves
+	float* d_zero_extra = nullptr;
+	uint32_t scratch_cap = 0, scratch_stride = 0;
 	void* slab = nullptr;
 	RaySet set[2]{};
 	uint32_t* d_counters = nullptr;  // [0] alive (current), [1] alive (next)
@@ -400,6 +404,9 @@ void tracer_destroy(insta_ctx* ctx) {
 	Tracer* t = (Tracer*)ctx->tracer;
 	if (!t) return;
 	if (t->slab) cudaFree(t->slab);
+	if (t->d_records) cudaFree(t->d_records);
+	if (t->d_net_out) cudaFree(t->d_net_out);
+	if (t->d_zero_extra) cudaFree(t->d_zero_extra);
 	if (t->d_counters) cudaFree(t->d_counters);
 	if (t->h_counters) cudaFreeHost(t->h_counters);
 	delete t;
@@ -503,6 +510,64 @@ int tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stride, co
 	t->step += n_steps;
 	t->n_alive = t->h_counters[0];
 	if (h_n_alive) *h_n_alive = t->n_alive;
+	return INSTA_OK;
+}
+
+
+// Testbed::render_nerf -> NerfTracer::init_rays_from_camera + trace + shade (testbed_nerf.cu:2320-2440, 2112-2244) with this
+// library's own deformation and network between generate and composite.  One stream sync per march iteration (the live-ray
+// count decides the number of steps of the next one), as in the reference.
+int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, const void* d_params, const float* d_extra_dims,
+                 float* d_frame_rgba, float* d_frame_depth, insta_render_stats* stats, cudaStream_t s) {
+	Tracer* t = tracer_of(ctx);
+	const uint32_t n_pix = cam->resolution[0] * cam->resolution[1];
+	const uint32_t stride = 11 + ctx->p.exp_params + ctx->p.geo_params;
+	if (n_pix > t->scratch_cap || stride != t->scratch_stride) {
+		INSTA_CUDA(cudaDeviceSynchronize());
+		if (t->d_records) cudaFree(t->d_records);
+		if (t->d_net_out) cudaFree(t->d_net_out);
+		t->d_records = nullptr;
+		t->d_net_out = nullptr;
+		INSTA_CUDA(cudaMalloc(&t->d_records, (size_t)n_pix * stride * 4));
+		INSTA_CUDA(cudaMalloc(&t->d_net_out, (size_t)n_pix * 8));
+		t->scratch_cap = n_pix;
+		t->scratch_stride = stride;
+	}
+	if (!t->d_zero_extra) {
+		INSTA_CUDA(cudaMalloc(&t->d_zero_extra, 64 * 4));
+		INSTA_CUDA(cudaMemset(t->d_zero_extra, 0, 64 * 4));
+	}
+	INSTA_CUDA(cudaMemsetAsync(d_frame_rgba, 0, (size_t)n_pix * 16, s));
+	uint32_t n_alive = 0;
+	int rc = tracer_init_rays(ctx, cam, opts, d_frame_rgba, d_frame_depth, nullptr, nullptr, &n_alive, s);
+	if (rc) return rc;
+	uint32_t iterations = 0;
+	uint64_t samples = 0;
+	const bool deform = frame_id >= 0 && !ctx->frames.empty();
+	if (deform) {
+		rc = sync_frame_table(ctx, s);
+		if (rc) return rc;
+	}
+	while (n_alive > 0) {
+		const uint32_t ns = tracer_n_steps(ctx);
+		uint32_t n_rec = 0;
+		rc = tracer_generate(ctx, t->d_records, stride, ns, frame_id, d_extra_dims ? d_extra_dims : t->d_zero_extra, &n_rec, s);
+		if (rc) return rc;
+		if (deform) {
+			rc = launch_deform(ctx, t->d_records, n_rec, stride, frame_id, nullptr, false, nullptr, s);
+			if (rc) return rc;
+		}
+		rc = launch_network_fwd(ctx, t->d_records, stride, n_rec, d_params, t->d_net_out, 0, s);
+		if (rc) return rc;
+		rc = tracer_composite(ctx, t->d_records, stride, t->d_net_out, 0, ns, d_frame_rgba, d_frame_depth, opts ? (int)opts->linear_colors : 0, &n_alive, s);
+		if (rc) return rc;
+		++iterations;
+		samples += n_rec;
+	}
+	if (stats) {
+		stats->iterations = iterations;
+		stats->samples = samples;
+	}
 	return INSTA_OK;
 }
 

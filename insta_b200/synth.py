@@ -161,3 +161,21 @@ def occupancy_bitfield(vertex_sets, radius=0.03, grid=128):
         hit[np.flatnonzero(sel)[np.isfinite(d)]] = True
         occ[idx[hit]] = True
     return np.packbits(occ, bitorder="little")
+
+
+MLP_SHAPES = [(64, 144), (64, 64), (16, 64), (64, 32), (64, 64), (64, 64), (16, 64)]  # [out, in] per layer: density MLP, colour MLP
+N_MLP_PARAMS = sum(o * i for o, i in MLP_SHAPES)  # 25,600
+
+
+def make_network_params(n_params, seed=5, grid_scale=1.0):
+    """fp16 parameter vector in the trainer's order (nerf_network.h:492-525): density MLP (64x144, 64x64, 16x64), colour MLP
+    (64x32, 64x64, 64x64, 16x64), weights row-major [out][in] Xavier-uniform like tcnn (gpu_matrix.h:292-304), then the
+    grid table ~ U(+-grid_scale) (tcnn initialises U(+-1e-4); the default makes encodings non-trivial)."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for o, i in MLP_SHAPES:
+        s = np.sqrt(6.0 / (i + o))
+        parts.append(((rng.random((o, i)) * 2 - 1) * s).astype(np.float16).ravel())
+    n_grid = n_params - N_MLP_PARAMS
+    parts.append(((rng.random(n_grid, dtype=np.float32) * 2 - 1) * np.float32(grid_scale)).astype(np.float16))
+    return np.concatenate(parts)

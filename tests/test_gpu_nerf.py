@@ -126,5 +126,50 @@ def test_march_and_composite_vs_reference(gpu_ctx, scene, refnerf):
     assert torch.equal(fr[:, 3] > 0, rfr[:, 3] > 0)
     assert float((fr - rfr).abs().max()) < 1e-3
     hit = rfr[:, 3] > 0.2
+    assert int(hit.sum()) > 500
     assert float((fd[hit] - rfd[hit]).abs().max()) < 1e-4
     assert torch.equal(fd[~hit], rfd[~hit])
+
+
+def test_render_frame_vs_reference_tracer(gpu_ctx, scene, refnerf):
+    """insta_render_frame (our tracer + deformation + fused network) against the REFERENCE's tracer kernels driving the same
+    deformation and network between generate and composite: identical sample sets => frames within the RGBA / depth tolerance."""
+    import torch
+
+    from insta_b200 import capi, synth
+
+    cam = synth.random_camera(3)
+    bf = _bitfield(scene)
+    n = RES[0] * RES[1]
+    aabb = gpu_ctx.render_aabb()
+    extra = torch.linspace(-1, 1, 16, device="cuda")
+    pn = synth.make_network_params(gpu_ctx.network_n_params, seed=9)
+    # density logits of a random network are ~0 (sigma = exp(logit) ~ 1, alpha per step ~ 0.002): make row 0 of the density
+    # output layer positive so that the logit grows with the (non-negative) hidden activations and rays saturate
+    pn[13312:13312 + 64] = np.float16(0.6)
+    params = torch.from_numpy(pn).cuda()
+    fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+    iters, samples = gpu_ctx.render_frame(capi.make_camera(cam, FOCAL, RES), 1, params, fr, fd, bitfield=bf, extra_dims=extra)
+    assert iters > 3 and samples > 10000
+    rfr, rfd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+    rrec = torch.zeros((n * 8, 27), device="cuda")
+    rout = torch.zeros((16, n * 8), dtype=torch.float16, device="cuda")
+    refnerf.init_rays(cam, FOCAL, (0.5, 0.5), RES, 0, True, aabb, [0, 0, 0, 1, 1, 1], bf, 0.0, 0.01, rfr, rfd)
+    ref_iters = 0
+    while True:
+        na, ns = refnerf.compact_and_generate(rrec, 16, extra, 1)
+        if na == 0:
+            break
+        m = na * ns
+        gpu_ctx.render_deformed(rrec[:m], 1)
+        gpu_ctx.network_inference(rrec, params, rout, out_stride=rout.shape[1], n=m)
+        refnerf.composite(rrec, 16, rout, rout.shape[1], ns)
+        ref_iters += 1
+    refnerf.shade(rfr, rfd)
+    torch.cuda.synchronize()
+    assert ref_iters == iters
+    assert torch.equal(fr[:, 3] > 0, rfr[:, 3] > 0)
+    assert float((fr - rfr).abs().max()) < 1e-3
+    hit = rfr[:, 3] > 0.2
+    assert int(hit.sum()) > 500
+    assert float((fd[hit] - rfd[hit]).abs().max()) < 1e-4

@@ -9,17 +9,9 @@ pytestmark = pytest.mark.gpu
 
 
 def make_params(n_params, seed=5, grid_scale=1.0):
-    """fp16 parameter vector in the trainer's order: density MLP (64x144, 64x64, 16x64), colour MLP (64x32, 64x64, 64x64,
-    16x64) Xavier-uniform like tcnn (gpu_matrix.h:292-304), then the grid table ~ U(+-grid_scale)."""
-    rng = np.random.default_rng(seed)
-    shapes = [(64, 144), (64, 64), (16, 64), (64, 32), (64, 64), (64, 64), (16, 64)]
-    parts = []
-    for o, i in shapes:
-        s = np.sqrt(6.0 / (i + o))
-        parts.append(((rng.random((o, i)) * 2 - 1) * s).astype(np.float16).ravel())
-    n_grid = n_params - sum(p.size for p in parts)
-    parts.append(((rng.random(n_grid, dtype=np.float32) * 2 - 1) * grid_scale).astype(np.float16))
-    return np.concatenate(parts), shapes
+    from insta_b200 import synth
+
+    return synth.make_network_params(n_params, seed, grid_scale), synth.MLP_SHAPES
 
 
 def torch_reference(ctx, rec, params, shapes):
