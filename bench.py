@@ -300,6 +300,17 @@ def run_ours(args):
         e2e_total = float(t.item())
     e2e_value = world * N_SAMPLES * len(e2e_t) / e2e_total
 
+    net = rnd = None
+    if not args.no_render:
+        net = network_leg(ctx, rec_np, args) if rank == 0 else None
+        rnd = render_leg(ctx, verts, fv, args, rank, world)
+        if world > 1:
+            # frames are sharded over ranks: aggregate frames/s = sum over ranks, ms/frame reported = max over ranks
+            t = torch.tensor([rnd["ms_per_frame"] if rnd else 0.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rnd:
+                rnd["ms_per_frame_max_over_ranks"] = float(t.item())
+                rnd["aggregate_frames_per_s"] = world * 1e3 / float(t.item())
     if rank == 0:
         peak, peak_src = measured_peaks()
         # dominant kernel = the one with the larger share of the step
@@ -329,6 +340,9 @@ def run_ours(args):
                 line["cpu_baseline"] = cb
             except Exception as e:  # the checker is optional for the measurement itself
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        if not args.no_render:
+            line["network"] = net
+            line["render"] = rnd
         if world == 1 and args.ref_cuda:
             try:
                 line["ref_cuda"] = ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args)
@@ -338,6 +352,65 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def render_leg(ctx, verts, fv, args, rank, world):
+    """ms/frame of a full 512x512 render (BASELINE.json metric, second half; configs[2]): random cameras, random-init grid / MLP
+    weights, occupancy shell of the local frames, frames sharded over ranks (no collective).  CUDA events around each
+    insta_render_frame call (it synchronises once per march iteration internally, like the reference)."""
+    import torch
+
+    from insta_b200 import capi, synth
+
+    res = (args.render_res, args.render_res)
+    n_local = min(ctx.n_frames, args.render_frames)
+    if n_local == 0:
+        return None
+    bf = torch.from_numpy(synth.occupancy_bitfield([fv[k] for k in range(min(len(fv), 8))], radius=0.03)).cuda()
+    pn = synth.make_network_params(ctx.network_n_params, seed=1337)
+    pn[13312:13312 + 64] = np.float16(0.6)  # positive density-logit row: rays saturate as with a trained model
+    params = torch.from_numpy(pn).cuda()
+    n = res[0] * res[1]
+    fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+    extra = torch.zeros(16, device="cuda")
+    focal = 1200.0 * res[0] / 512.0
+    ms, samples, iters = [], [], []
+    for k in range(2 + n_local):
+        f = k % min(n_local, 8)
+        cam = capi.make_camera(synth.random_camera(1000 * rank + k), focal, res)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        it, smp = ctx.render_frame(cam, f, params, fr, fd, bitfield=bf, extra_dims=extra)
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= 2:
+            ms.append(e0.elapsed_time(e1)); samples.append(smp); iters.append(it)
+    return {"ms_per_frame": float(np.mean(ms)), "ms_per_frame_min": float(np.min(ms)), "resolution": list(res), "frames_timed": len(ms),
+            "samples_per_frame": float(np.mean(samples)), "march_iterations_per_frame": float(np.mean(iters)),
+            "hit_fraction": float((fr[:, 3] > 0.2).float().mean()), "note": "deform + fused encode/MLP (tcgen05) + composite per iteration; one stream sync per iteration"}
+
+
+def network_leg(ctx, rec_np, args):
+    """The fused encode + MLP kernel alone on the 4M-sample batch (what the reference does with kernel_grid + 2 x kernel_mlp_fused + glue)."""
+    import torch
+
+    from insta_b200 import synth
+
+    rec = torch.from_numpy(rec_np).cuda()
+    params = torch.from_numpy(synth.make_network_params(ctx.network_n_params, seed=1337)).cuda()
+    out = torch.empty((rec.shape[0], 4), dtype=torch.float16, device="cuda")
+    ts = []
+    for k in range(3 + 5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.network_inference(rec, params, out)
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    return {"ms": ms, "samples_per_s": rec.shape[0] / (ms * 1e-3), "tflops": rec.shape[0] * 51200 / (ms * 1e-3) / 1e12,
+            "gather_gbs": rec.shape[0] * 2048 / (ms * 1e-3) / 1e9, "note": "hash grid + density MLP + SH + colour MLP in one tcgen05 kernel, 4 halves out per sample"}
 
 
 def ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args):
@@ -391,6 +464,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--max-buffers", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the network / 512^2 render legs")
+    ap.add_argument("--render-res", type=int, default=512)
+    ap.add_argument("--render-frames", type=int, default=8)
     ap.add_argument("--ref-cuda", action="store_true", default=True)
     ap.add_argument("--no-ref-cuda", dest="ref_cuda", action="store_false")
     args = ap.parse_args()
