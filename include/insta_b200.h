@@ -221,6 +221,77 @@ INSTA_API int insta_network_inference(insta_ctx* ctx, const float* d_records, ui
                                       uint32_t out_stride_elems, insta_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Stage 3 -- training step pieces (ngp::Testbed::train_nerf_step, ngp/src/testbed_nerf.cu:3170-3426).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* ngp::TrainingImageMetadata + TrainingXForm of one training image (ngp nerf_loader.h:48-64, common.h:168-171) */
+typedef struct insta_train_image {
+	const void*  d_pixels;         /* RGBA, image_data_type; negative red (0x00FF00FF for bytes) = masked away */
+	const void*  d_seg_mask;       /* nullable; RGBA8, red channel = region id (read_seg_mask, common_device.cuh:687) */
+	const float* d_depth;          /* nullable */
+	const float* d_rays;           /* nullable; explicit per-pixel rays: origin + unnormalised direction, 6 floats */
+	uint32_t resolution[2];
+	float    focal_length[2];
+	float    principal_point[2];
+	float    xform[12];            /* camera to world 3x4, column-major (start == end: no rolling shutter) */
+	uint32_t image_data_type;      /* ngp EImageDataType: 1 = Byte, 2 = Half, 3 = Float */
+	uint32_t reserved_;
+} insta_train_image;
+/* Testbed::load_nerf -> dataset.metadata_gpu / transforms_gpu (testbed_nerf.cu:2698-2760) */
+INSTA_API int insta_training_set_images(insta_ctx* ctx, const insta_train_image* h_images, uint32_t n_images);
+
+/* The buffers and scalars train_nerf_step hands to its kernels.  All d_* are the caller's device buffers. */
+typedef struct insta_train_step {
+	uint32_t n_rays;               /* n_rays_per_batch, <= 2^18 (testbed_nerf.cu:2910) */
+	uint32_t n_rays_total;         /* rays consumed by earlier steps (image choice, testbed_nerf.cu:1102) */
+	uint32_t max_samples;          /* capacity of d_coords in samples (max_inference, 16 * 2^18) */
+	uint32_t target_batch_size;    /* samples of the compacted batch, 2^18 (testbed.h:857) */
+	uint32_t stride_floats;        /* 11 + exp_params */
+	uint32_t snap_to_pixel_centers;/* training.snap_to_pixel_centers (true) */
+	uint32_t random_bg_color;      /* training.random_bg_color (true) */
+	uint32_t penalize_density_alpha; /* "penalize_density_alpha" (core.cu:191) */
+	uint64_t rng_seed;             /* Testbed::m_rng = default_rng_t{seed} ... */
+	uint64_t rng_advances;         /* ... advanced once per finished step (testbed_nerf.cu:3419) */
+	float    cone_angle_constant;
+	float    loss_scale;           /* LOSS_SCALE = 128 (testbed.h:256) */
+	float    background_color[3];
+	float    depth_weight;         /* "depth_weight" -> depth_supervision_lambda (core.cu:208) */
+	float    seg_weight;           /* "seg_weight" -> seg_mask_supervision_lambda (core.cu:189) */
+	float    near_distance;        /* training.near_distance */
+	float    beta_loss;            /* "beta_loss" (core.cu:193) */
+	const void*  d_density_grid_bitfield;
+	const float* d_extra_dims;     /* n_images x exp_params expression coefficients (extra_dims_gpu) */
+	float*    d_coords;            /* max_samples records */
+	uint32_t* d_counters;          /* [0] rays accepted, [1] samples generated, [2] samples after compaction */
+	uint32_t* d_ray_indices;       /* n_rays */
+	float*    d_rays;              /* n_rays x 6 */
+	uint32_t* d_numsteps;          /* n_rays x 2: (count, base) */
+} insta_train_step;
+/* generate_training_samples_nerf (testbed_nerf.cu:1105-1285); zeroes d_counters first */
+INSTA_API int insta_generate_training_samples(insta_ctx* ctx, const insta_train_step* step, insta_stream stream);
+/* compute_loss_kernel_train_nerf + fill_rollover(_and_rescale) (testbed_nerf.cu:1305-1643, 3353-3361).
+ * d_net_out_f16: out_width halves per generated sample (r, g, b, sigma logits first); d_dloss_f16: out_width halves per
+ * compacted sample; d_coords_compacted: target_batch_size records; d_loss (nullable): per-ray loss / n_rays;
+ * d_mean_density: Testbed::Nerf::density_grid_mean (one float). */
+INSTA_API int insta_compute_loss(insta_ctx* ctx, const insta_train_step* step, const void* d_net_out_f16, uint32_t out_width, float* d_coords_compacted,
+                                 void* d_dloss_f16, float* d_loss, const float* d_mean_density, insta_stream stream);
+
+/* tcnn::EmaOptimizer{AdamOptimizer} step (tcnn optimizers/adam.h:48-114, 157-190; ema.h:64-77, 103-135) over the trainer's
+ * buffers (tcnn trainer.h:282-297): fp32 master params, fp16 params, fp16 gradients (scaled by loss_scale), Adam moments,
+ * per-parameter step counters, fp16 EMA params (the inference / snapshot weights). */
+typedef struct insta_optimizer {
+	float learning_rate, beta1, beta2, epsilon, l2_reg, ema_decay, loss_scale; /* configs/nerf/main.json:21-32 */
+	uint32_t current_step;         /* optimizer steps taken before this one */
+	float*    d_params_fp32;
+	void*     d_params_f16;
+	const void* d_gradients_f16;
+	float*    d_first_moments;
+	float*    d_second_moments;
+	uint32_t* d_param_steps;
+	void*     d_params_ema_f16;
+} insta_optimizer;
+INSTA_API int insta_optimizer_step(insta_ctx* ctx, const insta_optimizer* opt, insta_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience (the end-to-end path a caller without device buffers uses): H2D of the records, stage 1,
  * stage 2, D2H of the mutated records and of the fp16 encodings, chunked and double-buffered on internal streams.
  * h_coords / h_out_soa_f16 should be pinned (cudaHostAlloc / insta_host_alloc) for full PCIe speed.

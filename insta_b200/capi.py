@@ -47,6 +47,26 @@ class Camera(C.Structure):
                 ("sample_index", C.c_uint32), ("snap_to_pixel_centers", C.c_uint32)]
 
 
+class TrainImage(C.Structure):
+    _fields_ = [("d_pixels", C.c_void_p), ("d_seg_mask", C.c_void_p), ("d_depth", C.c_void_p), ("d_rays", C.c_void_p), ("resolution", C.c_uint32 * 2),
+                ("focal_length", C.c_float * 2), ("principal_point", C.c_float * 2), ("xform", C.c_float * 12), ("image_data_type", C.c_uint32), ("reserved_", C.c_uint32)]
+
+
+class TrainStep(C.Structure):
+    _fields_ = [("n_rays", C.c_uint32), ("n_rays_total", C.c_uint32), ("max_samples", C.c_uint32), ("target_batch_size", C.c_uint32), ("stride_floats", C.c_uint32),
+                ("snap_to_pixel_centers", C.c_uint32), ("random_bg_color", C.c_uint32), ("penalize_density_alpha", C.c_uint32), ("rng_seed", C.c_uint64),
+                ("rng_advances", C.c_uint64), ("cone_angle_constant", C.c_float), ("loss_scale", C.c_float), ("background_color", C.c_float * 3),
+                ("depth_weight", C.c_float), ("seg_weight", C.c_float), ("near_distance", C.c_float), ("beta_loss", C.c_float),
+                ("d_density_grid_bitfield", C.c_void_p), ("d_extra_dims", C.c_void_p), ("d_coords", C.c_void_p), ("d_counters", C.c_void_p),
+                ("d_ray_indices", C.c_void_p), ("d_rays", C.c_void_p), ("d_numsteps", C.c_void_p)]
+
+
+class Optimizer(C.Structure):
+    _fields_ = [("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float), ("l2_reg", C.c_float), ("ema_decay", C.c_float),
+                ("loss_scale", C.c_float), ("current_step", C.c_uint32), ("d_params_fp32", C.c_void_p), ("d_params_f16", C.c_void_p), ("d_gradients_f16", C.c_void_p),
+                ("d_first_moments", C.c_void_p), ("d_second_moments", C.c_void_p), ("d_param_steps", C.c_void_p), ("d_params_ema_f16", C.c_void_p)]
+
+
 class RenderStats(C.Structure):
     _fields_ = [("iterations", C.c_uint32), ("reserved_", C.c_uint32), ("samples", C.c_uint64)]
 
@@ -80,7 +100,8 @@ EXPORTS = [
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
-    "insta_network_n_params", "insta_network_inference",
+    "insta_network_n_params", "insta_network_inference", "insta_training_set_images", "insta_generate_training_samples", "insta_compute_loss",
+    "insta_optimizer_step",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
 
@@ -270,6 +291,58 @@ class Context:
         n, stride = pos.shape
         self._check(self.lib.insta_hash_slots(self.h, _dev(pos), C.c_uint32(stride), C.c_uint32(n), _dev(slots), _stream(stream)))
         return slots
+
+    # ---- training ----
+    def training_set_images(self, images):
+        """images: list of dicts with torch tensors pixels (+ optional seg, depth, rays), res, focal, pp, xform [3,4], type."""
+        arr = (TrainImage * len(images))()
+        self._keep_images = images
+        for k, im in enumerate(images):
+            t = arr[k]
+            t.d_pixels = im["pixels"].data_ptr()
+            t.d_seg_mask = im["seg"].data_ptr() if im.get("seg") is not None else None
+            t.d_depth = im["depth"].data_ptr() if im.get("depth") is not None else None
+            t.d_rays = im["rays"].data_ptr() if im.get("rays") is not None else None
+            t.resolution[0], t.resolution[1] = im["res"]
+            t.focal_length[0], t.focal_length[1] = im["focal"]
+            t.principal_point[0], t.principal_point[1] = im.get("pp", (0.5, 0.5))
+            m = np.asarray(im["xform"], np.float32)
+            for col in range(4):
+                for row in range(3):
+                    t.xform[col * 3 + row] = float(m[row, col])
+            t.image_data_type = im.get("type", 3)
+        self._check(self.lib.insta_training_set_images(self.h, arr, C.c_uint32(len(images))))
+
+    def make_train_step(self, n_rays, n_rays_total, coords, counters, ray_indices, rays, numsteps, bitfield, extra_dims=None, target_batch_size=1 << 18,
+                        rng_seed=1337, rng_advances=0, cone_angle=0.0, loss_scale=128.0, snap=True, random_bg=True, penalize_density=False,
+                        background=(0.0, 0.0, 0.0), depth_weight=1.25, seg_weight=40.0, near_distance=0.2, beta_loss=0.0):
+        t = TrainStep()
+        t.n_rays, t.n_rays_total, t.max_samples, t.target_batch_size, t.stride_floats = n_rays, n_rays_total, coords.shape[0], target_batch_size, coords.shape[1]
+        t.snap_to_pixel_centers, t.random_bg_color, t.penalize_density_alpha = int(snap), int(random_bg), int(penalize_density)
+        t.rng_seed, t.rng_advances, t.cone_angle_constant, t.loss_scale = rng_seed, rng_advances, cone_angle, loss_scale
+        for k in range(3):
+            t.background_color[k] = background[k]
+        t.depth_weight, t.seg_weight, t.near_distance, t.beta_loss = depth_weight, seg_weight, near_distance, beta_loss
+        t.d_density_grid_bitfield = bitfield.data_ptr()
+        t.d_extra_dims = extra_dims.data_ptr() if extra_dims is not None else None
+        t.d_coords, t.d_counters, t.d_ray_indices, t.d_rays, t.d_numsteps = coords.data_ptr(), counters.data_ptr(), ray_indices.data_ptr(), rays.data_ptr(), numsteps.data_ptr()
+        t._keep = (coords, counters, ray_indices, rays, numsteps, bitfield, extra_dims)
+        return t
+
+    def generate_training_samples(self, step, stream=None):
+        self._check(self.lib.insta_generate_training_samples(self.h, C.byref(step), _stream(stream)))
+
+    def compute_loss(self, step, net_out, out_width, coords_compacted, dloss, loss, mean_density, stream=None):
+        self._check(self.lib.insta_compute_loss(self.h, C.byref(step), _dev(net_out), C.c_uint32(out_width), _dev(coords_compacted), _dev(dloss), _dev(loss),
+                                                _dev(mean_density), _stream(stream)))
+
+    def optimizer_step(self, current_step, params32, params16, grads16, m1, m2, steps, ema16, lr=0.00175, beta1=0.9, beta2=0.99, eps=1e-15, l2_reg=1e-6,
+                       ema_decay=0.95, loss_scale=128.0, stream=None):
+        o = Optimizer()
+        o.learning_rate, o.beta1, o.beta2, o.epsilon, o.l2_reg, o.ema_decay, o.loss_scale, o.current_step = lr, beta1, beta2, eps, l2_reg, ema_decay, loss_scale, current_step
+        o.d_params_fp32, o.d_params_f16, o.d_gradients_f16 = params32.data_ptr(), params16.data_ptr(), grads16.data_ptr()
+        o.d_first_moments, o.d_second_moments, o.d_param_steps, o.d_params_ema_f16 = m1.data_ptr(), m2.data_ptr(), steps.data_ptr(), ema16.data_ptr()
+        self._check(self.lib.insta_optimizer_step(self.h, C.byref(o), _stream(stream)))
 
     # ---- network ----
     @property

@@ -211,6 +211,7 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (ctx->d_canon_xf) cudaFree(ctx->d_canon_xf);
 	if (ctx->d_counter) cudaFree(ctx->d_counter);
 	tracer_destroy(ctx);
+	if (ctx->d_train_images) cudaFree(ctx->d_train_images);
 	for (int k = 0; k < 2; ++k) {
 		if (ctx->d_stage_rec[k]) cudaFree(ctx->d_stage_rec[k]);
 		if (ctx->d_stage_enc[k]) cudaFree(ctx->d_stage_enc[k]);
@@ -436,6 +437,43 @@ int insta_hash_encode_bwd(insta_ctx* ctx, const float* d_pos, uint32_t pos_strid
 int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, uint32_t* d_slots, insta_stream stream) {
 	if (!ctx || ((!d_pos || !d_slots) && n) || pos_stride_floats < 3) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_slots: bad arguments");
 	return launch_hash_slots(ctx, d_pos, pos_stride_floats, n, d_slots, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int insta_training_set_images(insta_ctx* ctx, const insta_train_image* h_images, uint32_t n_images) {
+	if (!ctx || (!h_images && n_images)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_training_set_images: bad arguments");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	return training_set_images(ctx, h_images, n_images);
+}
+
+static int check_step(const insta_ctx* ctx, const insta_train_step* t, const char* who) {
+	if (!ctx || !t) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": bad arguments");
+	if (ctx->n_train_images == 0) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": no training images (insta_training_set_images)");
+	if (!t->d_coords || !t->d_counters || !t->d_ray_indices || !t->d_rays || !t->d_numsteps || !t->d_density_grid_bitfield)
+		INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": a buffer of insta_train_step is null");
+	if (t->stride_floats < 11 + ctx->p.exp_params + ctx->p.geo_params) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": stride smaller than NerfCoordinate + extra dims");
+	return INSTA_OK;
+}
+
+int insta_generate_training_samples(insta_ctx* ctx, const insta_train_step* step, insta_stream stream) {
+	int rc = check_step(ctx, step, "insta_generate_training_samples");
+	if (rc) return rc;
+	return train_generate(ctx, step, (cudaStream_t)stream);
+}
+
+int insta_compute_loss(insta_ctx* ctx, const insta_train_step* step, const void* d_net_out_f16, uint32_t out_width, float* d_coords_compacted, void* d_dloss_f16,
+                       float* d_loss, const float* d_mean_density, insta_stream stream) {
+	int rc = check_step(ctx, step, "insta_compute_loss");
+	if (rc) return rc;
+	if (!d_net_out_f16 || !d_coords_compacted || !d_dloss_f16 || !d_mean_density || out_width < 4 || out_width % 4) INSTA_FAIL(INSTA_ERR_INVALID, "insta_compute_loss: bad arguments");
+	return train_loss(ctx, step, d_net_out_f16, out_width, d_coords_compacted, d_dloss_f16, d_loss, d_mean_density, (cudaStream_t)stream);
+}
+
+int insta_optimizer_step(insta_ctx* ctx, const insta_optimizer* o, insta_stream stream) {
+	if (!ctx || !o || !o->d_params_fp32 || !o->d_params_f16 || !o->d_gradients_f16 || !o->d_first_moments || !o->d_second_moments || !o->d_param_steps || !o->d_params_ema_f16)
+		INSTA_FAIL(INSTA_ERR_INVALID, "insta_optimizer_step: bad arguments");
+	if (!(o->loss_scale > 0.f)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_optimizer_step: loss_scale must be positive");
+	return optimizer_step(ctx, o, network_n_params(ctx), 25600u, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -148,6 +148,8 @@ struct insta_ctx {
 	std::atomic<uint64_t> launches{0};
 	std::mutex mu;
 	void* tracer = nullptr;           // insta::Tracer (nerf.cu)
+	void* d_train_images = nullptr;   // insta::ImageDev[n_train_images] (train.cu)
+	uint32_t n_train_images = 0;
 	insta_render_opts render_opts{};  // last options given to insta_tracer_init_rays
 };
 
@@ -165,6 +167,12 @@ int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
 // mlp.cu
 uint32_t network_n_params(const insta_ctx* ctx);
 int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s);
+// train.cu
+int training_set_images(insta_ctx* ctx, const insta_train_image* h, uint32_t n);
+int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s);
+int train_loss(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out, uint32_t out_width, float* d_coords_compacted, void* d_dloss, float* d_loss,
+               const float* d_mean_density, cudaStream_t s);
+int optimizer_step(insta_ctx* ctx, const insta_optimizer* o, uint32_t n_params, uint32_t n_matrix, cudaStream_t s);
 // nerf.cu
 void tracer_destroy(insta_ctx* ctx);
 int tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth, float* d_dbg_origin_t,

@@ -179,3 +179,35 @@ def make_network_params(n_params, seed=5, grid_scale=1.0):
     n_grid = n_params - N_MLP_PARAMS
     parts.append(((rng.random(n_grid, dtype=np.float32) * 2 - 1) * np.float32(grid_scale)).astype(np.float16))
     return np.concatenate(parts)
+
+
+def make_training_images(n_images, res, focal, seed=3, with_rays=True, mask_fraction=0.05):
+    """Synthetic training set: random smooth RGBA float images with alpha = 1 inside a disc (the projected
+    head), a few masked-away pixels (negative red), a segmentation mask (region ids 0 / 120 / 200 in the red byte), a depth map,
+    random cameras looking at the unit-cube centre and, optionally, the explicit per-pixel rays of that camera (origin, unnormalised
+    direction) computed in fp32 numpy.  Returns a list of dicts of numpy arrays (capi.Context.training_set_images takes torch tensors)."""
+    rng = np.random.default_rng(seed)
+    W, H = res
+    out = []
+    yy, xx = np.meshgrid((np.arange(H) + 0.5) / H, (np.arange(W) + 0.5) / W, indexing="ij")
+    for k in range(n_images):
+        cam = random_camera(5000 + seed * 100 + k)
+        f = rng.random(3) * 6 + 1
+        rgb = np.stack([0.5 + 0.5 * np.sin(f[c] * xx + 3 * c + k) * np.cos(f[(c + 1) % 3] * yy) for c in range(3)], axis=-1)
+        disc = ((xx - 0.5) ** 2 + (yy - 0.5) ** 2) < 0.16
+        alpha = disc.astype(np.float32)
+        pix = np.concatenate([rgb * alpha[..., None], alpha[..., None]], axis=-1).astype(np.float32)
+        masked = rng.random((H, W)) < mask_fraction
+        pix[masked] = -1.0
+        seg = np.zeros((H, W, 4), np.uint8)
+        seg[..., 0] = np.where(disc, np.where(xx < 0.5, 120, 200), 0)
+        depth = (0.8 + 0.2 * np.sin(5 * xx) * np.cos(4 * yy)).astype(np.float32)
+        im = {"pixels": pix, "seg": seg, "depth": depth, "res": (W, H), "focal": (float(focal), float(focal)), "pp": (0.5, 0.5), "xform": cam, "type": 3}
+        if with_rays:
+            lx = ((xx.astype(np.float32) - np.float32(0.5)) * np.float32(W) / np.float32(focal)).astype(np.float32)
+            ly = ((yy.astype(np.float32) - np.float32(0.5)) * np.float32(H) / np.float32(focal)).astype(np.float32)
+            d = (cam[:, 0][None, None] * lx[..., None] + cam[:, 1][None, None] * ly[..., None] + cam[:, 2][None, None]).astype(np.float32)
+            o = np.broadcast_to(cam[:, 3].astype(np.float32), d.shape)
+            im["rays"] = np.concatenate([o, d], axis=-1).astype(np.float32).copy()
+        out.append(im)
+    return out

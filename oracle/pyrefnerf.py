@@ -52,3 +52,52 @@ class RefNerf:
 
     def shade(self, frame_rgba, frame_depth, linear_colors=False):
         return self.lib.refnerf_shade(C.c_void_p(frame_rgba.data_ptr()), C.c_void_p(frame_depth.data_ptr()), C.c_int(int(linear_colors)), self._s())
+
+
+    # ---- training kernels ----
+    def train_set_images(self, images):
+        n = len(images)
+        self._keep_images = images
+        ptrs = (C.c_void_p * (4 * n))()
+        res = (C.c_uint32 * (2 * n))()
+        focal = (C.c_float * (2 * n))()
+        pp = (C.c_float * (2 * n))()
+        xf = (C.c_float * (12 * n))()
+        typ = (C.c_uint32 * n)()
+        for k, im in enumerate(images):
+            for j, key in enumerate(("pixels", "seg", "depth", "rays")):
+                ptrs[4 * k + j] = im[key].data_ptr() if im.get(key) is not None else None
+            res[2 * k], res[2 * k + 1] = im["res"]
+            focal[2 * k], focal[2 * k + 1] = im["focal"]
+            pp[2 * k], pp[2 * k + 1] = im.get("pp", (0.5, 0.5))
+            m = np.asarray(im["xform"], np.float32)
+            for col in range(4):
+                for row in range(3):
+                    xf[12 * k + col * 3 + row] = float(m[row, col])
+            typ[k] = im.get("type", 3)
+        rc = self.lib.refnerf_train_set_images(C.c_uint32(n), ptrs, res, focal, pp, xf, typ)
+        assert rc == 0, rc
+
+    def train_generate(self, n_rays, n_rays_total, coords, counters, ray_indices, rays, numsteps, bitfield, aabb, extra_dims, rng_seed=1337, rng_advances=0,
+                       cone=0.0, snap=True):
+        a = (C.c_float * 6)(*[float(x) for x in aabb])
+        n_extra = coords.shape[1] - 11
+        rc = self.lib.refnerf_train_generate(C.c_uint32(n_rays), C.c_uint32(n_rays_total), C.c_uint32(coords.shape[0]), C.c_uint64(rng_seed), C.c_uint64(rng_advances), a,
+                                             C.c_void_p(bitfield.data_ptr()), C.c_float(cone), C.c_int(int(snap)), C.c_void_p(extra_dims.data_ptr()), C.c_uint32(n_extra),
+                                             C.c_void_p(coords.data_ptr()), C.c_void_p(counters.data_ptr()), C.c_void_p(ray_indices.data_ptr()), C.c_void_p(rays.data_ptr()),
+                                             C.c_void_p(numsteps.data_ptr()), self._s())
+        assert rc == 0, rc
+
+    def train_loss(self, n_rays, n_rays_total, target_batch, coords, counters, ray_indices, rays, numsteps, net_out, out_width, coords_compacted, dloss, loss,
+                   mean_density, aabb, rng_seed=1337, rng_advances=0, loss_scale=128.0, bg=(0, 0, 0), random_bg=True, snap=True, depth_lambda=1.25, seg_lambda=40.0,
+                   near_distance=0.2, penalize_density=False, beta=0.0):
+        a = (C.c_float * 6)(*[float(x) for x in aabb])
+        b = (C.c_float * 3)(*bg)
+        n_extra = coords.shape[1] - 11
+        rc = self.lib.refnerf_train_loss(C.c_uint32(n_rays), C.c_uint32(n_rays_total), C.c_uint32(target_batch), C.c_uint64(rng_seed), C.c_uint64(rng_advances), a,
+                                         C.c_float(loss_scale), C.c_uint32(out_width), b, C.c_int(int(random_bg)), C.c_void_p(net_out.data_ptr()), C.c_void_p(counters.data_ptr()),
+                                         C.c_void_p(ray_indices.data_ptr()), C.c_void_p(rays.data_ptr()), C.c_void_p(numsteps.data_ptr()), C.c_void_p(coords.data_ptr()),
+                                         C.c_void_p(coords_compacted.data_ptr()), C.c_uint32(n_extra), C.c_void_p(dloss.data_ptr()), C.c_void_p(loss.data_ptr()), C.c_int(int(snap)),
+                                         C.c_void_p(mean_density.data_ptr()), C.c_float(depth_lambda), C.c_float(seg_lambda), C.c_float(near_distance),
+                                         C.c_int(int(penalize_density)), C.c_float(beta), self._s())
+        assert rc == 0, rc

@@ -20,6 +20,8 @@
 #include <tiny-cuda-nn/common_device.h>
 #include <tiny-cuda-nn/gpu_matrix.h>
 
+#include <vector>
+
 using namespace Eigen;
 using namespace tcnn;
 
@@ -152,6 +154,80 @@ int refnerf_shade(float* d_frame_rgba, float* d_frame_depth, int linear_colors, 
 		linear_kernel(shade_kernel_nerf, 0, stream, n_hit, g.rgba[2], g.depth[2], g.payload[2], ERenderMode::Shade, (bool)linear_colors, (Array4f*)d_frame_rgba,
 		              d_frame_depth);
 	return (int)n_hit;
+}
+
+
+// ---- training kernels -------------------------------------------------------------------------------------------
+static TrainingImageMetadata* g_meta = nullptr;
+static TrainingXForm* g_xforms = nullptr;
+static uint32_t g_n_images = 0;
+static float* g_exposure = nullptr;
+
+// per image: device pointers (pixels, seg, depth, rays: 4 per image), resolution (2), focal (2), principal point (2), xform (12), type
+int refnerf_train_set_images(uint32_t n, const void* const* ptrs4, const uint32_t* res2, const float* focal2, const float* pp2, const float* xform12, const uint32_t* type) {
+	std::vector<TrainingImageMetadata> meta(n);
+	std::vector<TrainingXForm> xf(n);
+	for (uint32_t k = 0; k < n; ++k) {
+		meta[k].pixels = ptrs4[4 * k + 0];
+		meta[k].seg_mask = ptrs4[4 * k + 1];
+		meta[k].depth = (const float*)ptrs4[4 * k + 2];
+		meta[k].rays = (const Ray*)ptrs4[4 * k + 3];
+		meta[k].image_data_type = (EImageDataType)type[k];
+		meta[k].resolution = Vector2i((int)res2[2 * k], (int)res2[2 * k + 1]);
+		meta[k].focal_length = Vector2f(focal2[2 * k], focal2[2 * k + 1]);
+		meta[k].principal_point = Vector2f(pp2[2 * k], pp2[2 * k + 1]);
+		for (int c = 0; c < 4; ++c)
+			for (int r = 0; r < 3; ++r) xf[k].start(r, c) = xform12[12 * k + c * 3 + r];
+		xf[k].end = xf[k].start;
+	}
+	cudaFree(g_meta); cudaFree(g_xforms); cudaFree(g_exposure);
+	cudaMalloc(&g_meta, sizeof(TrainingImageMetadata) * n);
+	cudaMalloc(&g_xforms, sizeof(TrainingXForm) * n);
+	cudaMalloc(&g_exposure, sizeof(float) * 3 * n);
+	cudaMemcpy(g_meta, meta.data(), sizeof(TrainingImageMetadata) * n, cudaMemcpyHostToDevice);
+	cudaMemcpy(g_xforms, xf.data(), sizeof(TrainingXForm) * n, cudaMemcpyHostToDevice);
+	cudaMemset(g_exposure, 0, sizeof(float) * 3 * n);
+	g_n_images = n;
+	return (int)cudaGetLastError();
+}
+
+// generate_training_samples_nerf as train_nerf_step launches it (testbed_nerf.cu:3252-3284); counters = {rays, samples, compacted}
+int refnerf_train_generate(uint32_t n_rays, uint32_t n_rays_total, uint32_t max_samples, uint64_t rng_seed, uint64_t rng_advances, const float* aabb6,
+                           const uint8_t* d_bitfield, float cone_angle, int snap, const float* d_extra_dims, uint32_t n_extra, float* d_coords, uint32_t* d_counters,
+                           uint32_t* d_ray_indices, float* d_rays, uint32_t* d_numsteps, cudaStream_t stream) {
+	default_rng_t rng{rng_seed};
+	for (uint64_t k = 0; k < rng_advances; ++k) rng.advance();
+	cudaMemsetAsync(d_counters, 0, 3 * sizeof(uint32_t), stream);
+	BoundingSphere bs;
+	linear_kernel(generate_training_samples_nerf, 0, stream, n_rays, bb6(aabb6), bb6(aabb6), bs, max_samples, n_rays_total, rng, d_counters, d_counters + 1,
+	              d_ray_indices, (Ray*)d_rays, d_numsteps, PitchedPtr<NerfCoordinate>((NerfCoordinate*)d_coords, 1, 0, n_extra * sizeof(float)), g_n_images, g_meta,
+	              g_xforms, d_bitfield, false, (float*)nullptr, (bool)snap, false, cone_angle, (const float*)nullptr, Vector2i::Zero(), (const float*)nullptr,
+	              (const float*)nullptr, (const float*)nullptr, Vector2i::Zero(), d_extra_dims, n_extra);
+	return (int)cudaGetLastError();
+}
+
+// compute_loss_kernel_train_nerf as train_nerf_step launches it (testbed_nerf.cu:3298-3351) + the roll-over kernels (3353-3358)
+int refnerf_train_loss(uint32_t n_rays, uint32_t n_rays_total, uint32_t target_batch, uint64_t rng_seed, uint64_t rng_advances, const float* aabb6, float loss_scale,
+                       uint32_t padded_output_width, const float* bg3, int random_bg, const void* d_net_out, uint32_t* d_counters, const uint32_t* d_ray_indices,
+                       const float* d_rays, uint32_t* d_numsteps, const float* d_coords, float* d_coords_compacted, uint32_t n_extra, void* d_dloss, float* d_loss,
+                       int snap, const float* d_mean_density, float depth_lambda, float seg_lambda, float near_distance, int penalize_density, float beta,
+                       cudaStream_t stream) {
+	default_rng_t rng{rng_seed};
+	for (uint64_t k = 0; k < rng_advances; ++k) rng.advance();
+	const uint32_t extra_stride = n_extra * sizeof(float);
+	linear_kernel(compute_loss_kernel_train_nerf, 0, stream, n_rays, bb6(aabb6), n_rays_total, rng, target_batch, d_counters, loss_scale, (int)padded_output_width,
+	              (const float*)nullptr, (float*)nullptr, Vector2i::Zero(), ELossType::L2, Array3f(bg3[0], bg3[1], bg3[2]), EColorSpace::SRGB, (bool)random_bg, false,
+	              g_n_images, g_meta, (const network_precision_t*)d_net_out, d_counters + 2, d_ray_indices, (const Ray*)d_rays, d_numsteps,
+	              PitchedPtr<const NerfCoordinate>((NerfCoordinate*)d_coords, 1, 0, extra_stride), PitchedPtr<NerfCoordinate>((NerfCoordinate*)d_coords_compacted, 1, 0, extra_stride),
+	              (network_precision_t*)d_dloss, ELossType::Huber, ELossType::L1, d_loss, false, (float*)nullptr, ENerfActivation::Logistic, ENerfActivation::Exponential,
+	              (bool)snap, (float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, Vector2i::Zero(), Vector2i::Zero(), (const float*)nullptr,
+	              Vector2i::Zero(), (float*)nullptr, (float*)nullptr, d_mean_density, (const Eigen::Array3f*)g_exposure, (Eigen::Array3f*)nullptr, depth_lambda, seg_lambda,
+	              near_distance, (bool)penalize_density, beta);
+	const uint32_t floats_per_coord = sizeof(NerfCoordinate) / sizeof(float) + n_extra;
+	fill_rollover_and_rescale<network_precision_t><<<n_blocks_linear(target_batch * padded_output_width), n_threads_linear, 0, stream>>>(target_batch, padded_output_width,
+	                                                                                                                          d_counters + 2, (network_precision_t*)d_dloss);
+	fill_rollover<float><<<n_blocks_linear(target_batch * floats_per_coord), n_threads_linear, 0, stream>>>(target_batch, floats_per_coord, d_counters + 2, d_coords_compacted);
+	return (int)cudaGetLastError();
 }
 
 }  // extern "C"
