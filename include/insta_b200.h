@@ -146,6 +146,12 @@ INSTA_API int insta_hash_encode_bwd(insta_ctx* ctx, const float* d_pos, uint32_t
 INSTA_API int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, uint32_t* d_slots,
                                insta_stream stream);
 
+/* NerfNetwork::forward + backward on the compacted training batch (nerf_network.h:238-383; testbed_nerf.cu:3369-3370):
+ * d_dloss_f16 = dL/d(r, g, b, sigma logits), dloss_width halves per sample (already multiplied by the loss scale);
+ * d_gradients_f16 receives dL/dparams in parameter order (n_params halves, EGradientMode::Overwrite); d_out_f16 (nullable):
+ * the forward output, 4 halves per sample.  Scratch for the layer activations is owned by the context. */
+INSTA_API int insta_network_forward_backward(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16,
+                                             const void* d_dloss_f16, uint32_t dloss_width, void* d_gradients_f16, void* d_out_f16, insta_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Stage 3 -- render tracer (ngp::Testbed::NerfTracer, ngp/src/testbed_nerf.cu:2030-2244 and the kernels it launches).

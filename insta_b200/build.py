@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libinsta_b200.so")
-SOURCES = ["api.cu", "deform.cu", "hashgrid.cu", "nerf.cu", "mlp.cu", "train.cu", "mesh_host.cpp"]
-HEADERS = ["ctx.h", "grid_device.cuh", "nerf_device.cuh", os.path.join("..", "..", "include", "insta_b200.h")]
+SOURCES = ["api.cu", "deform.cu", "hashgrid.cu", "nerf.cu", "mlp.cu", "mlp_bwd.cu", "train.cu", "mesh_host.cpp"]
+HEADERS = ["ctx.h", "grid_device.cuh", "nerf_device.cuh", "umma.cuh", os.path.join("..", "..", "include", "insta_b200.h")]
 
 
 def _nvcc():

@@ -100,7 +100,7 @@ EXPORTS = [
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
-    "insta_network_n_params", "insta_network_inference", "insta_training_set_images", "insta_generate_training_samples", "insta_compute_loss",
+    "insta_network_n_params", "insta_network_inference", "insta_network_forward_backward", "insta_training_set_images", "insta_generate_training_samples", "insta_compute_loss",
     "insta_optimizer_step",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
@@ -355,6 +355,13 @@ class Context:
         self._check(self.lib.insta_network_inference(self.h, _dev(records), C.c_uint32(records.shape[1]), C.c_uint32(n), _dev(params), _dev(out),
                                                      C.c_uint32(out_stride), _stream(stream)))
         return out
+
+    def network_forward_backward(self, records, params, dloss, grads, out=None, n=None, stream=None):
+        """records float32 [n, stride]; dloss fp16 [n, width]; grads fp16 [network_n_params] (overwritten); out fp16 [n, 4] or None."""
+        n = records.shape[0] if n is None else n
+        self._check(self.lib.insta_network_forward_backward(self.h, _dev(records), C.c_uint32(records.shape[1]), C.c_uint32(n), _dev(params), _dev(dloss),
+                                                            C.c_uint32(dloss.shape[1]), _dev(grads), _dev(out), _stream(stream)))
+        return grads
 
     # ---- stage 3: render tracer (NerfTracer) ----
     def tracer_init_rays(self, cam, frame_rgba, frame_depth, bitfield=None, render_aabb=None, cone_angle=0.0, min_transmittance=0.01, linear_colors=False,

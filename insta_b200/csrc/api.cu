@@ -211,6 +211,7 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (ctx->d_canon_xf) cudaFree(ctx->d_canon_xf);
 	if (ctx->d_counter) cudaFree(ctx->d_counter);
 	tracer_destroy(ctx);
+	network_bwd_destroy(ctx);
 	if (ctx->d_train_images) cudaFree(ctx->d_train_images);
 	for (int k = 0; k < 2; ++k) {
 		if (ctx->d_stage_rec[k]) cudaFree(ctx->d_stage_rec[k]);
@@ -437,6 +438,17 @@ int insta_hash_encode_bwd(insta_ctx* ctx, const float* d_pos, uint32_t pos_strid
 int insta_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t pos_stride_floats, uint32_t n, uint32_t* d_slots, insta_stream stream) {
 	if (!ctx || ((!d_pos || !d_slots) && n) || pos_stride_floats < 3) INSTA_FAIL(INSTA_ERR_INVALID, "insta_hash_slots: bad arguments");
 	return launch_hash_slots(ctx, d_pos, pos_stride_floats, n, d_slots, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int insta_network_forward_backward(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16, const void* d_dloss_f16,
+                                   uint32_t dloss_width, void* d_gradients_f16, void* d_out_f16, insta_stream stream) {
+	if (!ctx || !d_gradients_f16 || ((!d_records || !d_params_f16 || !d_dloss_f16) && n)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_forward_backward: bad arguments");
+	if (stride_floats < 11 + ctx->p.exp_params + ctx->p.geo_params) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_forward_backward: stride smaller than NerfCoordinate + extra dims");
+	if (reinterpret_cast<uintptr_t>(d_params_f16) % 16u || reinterpret_cast<uintptr_t>(d_gradients_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_forward_backward: parameters / gradients must be 16-byte aligned");
+	if (dloss_width < 4 || dloss_width % 4) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_forward_backward: dloss_width must be a multiple of 4");
+	if (ctx->p.n_levels != 16 || ctx->p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_forward_backward: the density MLP expects 16 levels x 8 features");
+	return launch_network_fwd_bwd(ctx, d_records, stride_floats, n, d_params_f16, d_dloss_f16, dloss_width, d_gradients_f16, d_out_f16, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -148,6 +148,7 @@ struct insta_ctx {
 	std::atomic<uint64_t> launches{0};
 	std::mutex mu;
 	void* tracer = nullptr;           // insta::Tracer (nerf.cu)
+	void* bwd_scratch = nullptr;      // insta::BwdScratch (mlp_bwd.cu)
 	void* d_train_images = nullptr;   // insta::ImageDev[n_train_images] (train.cu)
 	uint32_t n_train_images = 0;
 	insta_render_opts render_opts{};  // last options given to insta_tracer_init_rays
@@ -162,11 +163,16 @@ int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, 
 int init_grid_levels(insta_ctx* ctx);
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s);
 int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s);
+int launch_hash_bwd_pitched(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, uint32_t pitch, void* grad, int zero_first, cudaStream_t s);
 int launch_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, uint32_t* slots, cudaStream_t s);
 int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
 // mlp.cu
 uint32_t network_n_params(const insta_ctx* ctx);
 int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s);
+// mlp_bwd.cu
+void network_bwd_destroy(insta_ctx* ctx);
+int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,
+                           void* d_grads, void* d_out, cudaStream_t s);
 // train.cu
 int training_set_images(insta_ctx* ctx, const insta_train_image* h, uint32_t n);
 int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s);

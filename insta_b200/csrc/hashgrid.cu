@@ -147,6 +147,7 @@ __device__ __forceinline__ void bwd_sample(const uint4* grad_base, const Corner&
 template <bool HASHED>
 __device__ __forceinline__ void bwd_level(const GridLevels& L, uint32_t level, uint32_t n, uint32_t i0, bool one, bool two, const float* __restrict__ sp,
                                           const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
+	// n = row pitch of dLdy (samples per feature row)
 	if (!one) return;
 	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
 	const float scale = L.scale[level];
@@ -178,7 +179,7 @@ __device__ __forceinline__ void bwd_level(const GridLevels& L, uint32_t level, u
 	if (two && any1) bwd_sample<HASHED>(grad, pos_fract3(sp[3], sp[4], sp[5], scale), g1, size, mul1, mul2);
 }
 
-__global__ void __launch_bounds__(kBwdThreads) hash_bwd_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
+__global__ void __launch_bounds__(kBwdThreads) hash_bwd_kernel(const __grid_constant__ GridLevels L, uint32_t n, uint32_t pitch, const float* __restrict__ pos,
                                                                uint32_t stride, const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
 	__shared__ float s_pos[kTile * 3];
 	const uint32_t tile_first = blockIdx.x * kTile;
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(kBwdThreads) hash_bwd_kernel(const __grid_cons
 	const uint32_t i0 = tile_first + 2u * lane;
 	const bool one = i0 < n, two = i0 + 1 < n;
 	for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
-		if (L.hashed[level]) bwd_level<true>(L, level, n, i0, one, two, s_pos + 6 * lane, dLdy, grad);
-		else bwd_level<false>(L, level, n, i0, one, two, s_pos + 6 * lane, dLdy, grad);
+		if (L.hashed[level]) bwd_level<true>(L, level, pitch, i0, one, two, s_pos + 6 * lane, dLdy, grad);
+		else bwd_level<false>(L, level, pitch, i0, one, two, s_pos + 6 * lane, dLdy, grad);
 	}
 }
 
@@ -256,10 +257,15 @@ int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_
 }
 
 int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s) {
+	return launch_hash_bwd_pitched(ctx, d_pos, stride, n, dLdy, n, grad, zero_first, s);
+}
+
+// dLdy rows are `pitch` samples apart (pitch >= n)
+int launch_hash_bwd_pitched(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, uint32_t pitch, void* grad, int zero_first, cudaStream_t s) {
 	if (zero_first) INSTA_CUDA(cudaMemsetAsync(grad, 0, (size_t)ctx->levels.offset[ctx->levels.n_levels] * 16, s));
 	if (n == 0) return INSTA_OK;
 	const dim3 grid((n + kTile - 1) / kTile);
-	hash_bwd_kernel<<<grid, kBwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const __half*)dLdy, (uint4*)grad);
+	hash_bwd_kernel<<<grid, kBwdThreads, 0, s>>>(ctx->levels, n, pitch, d_pos, stride, (const __half*)dLdy, (uint4*)grad);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;

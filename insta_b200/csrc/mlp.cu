@@ -29,10 +29,12 @@
 
 #include "ctx.h"
 #include "grid_device.cuh"
+#include "umma.cuh"
 
 namespace insta {
 namespace {
 using namespace griddev;
+using namespace umma;
 
 constexpr int kTileM = 128;
 constexpr int kMlpWarps = 4, kEncWarps = 8;
@@ -67,42 +69,7 @@ constexpr uint32_t kSmV4 = kSmV3 + kWidth * kWidth * 2;
 constexpr uint32_t kSmBar = kSmV4 + kOutPad * kWidth * 2;       // 5 mbarriers + tmem base
 constexpr uint32_t kSmTotal = kSmBar + 64;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "WAIT_%=:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	    "@p bra DONE_%=;\n"
-	    "bra WAIT_%=;\n"
-	    "DONE_%=:\n"
-	    "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void mlp_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMlpThreads) : "memory"); }
-
-// K-major, no swizzle: start address, LBO (K direction), SBO (M/N direction), version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-	return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-// kind::f16: D = F32, A = B = F16, both K-major, dense
-__device__ __forceinline__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N) { return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "setp.ne.b32 p, %4, 0;\n"
-	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-	    "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 
 // D[128 x N] (TMEM) = A[128 x K] * B[N x K]^T, operands in the canonical layout described in the header
 template <int N, int K>
@@ -115,23 +82,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem, uint32_t a_saddr, uint
 		umma_f16(tmem, ad, bd, idesc, j > 0 ? 1u : 0u);
 	}
 	umma_commit(mma_bar);
-}
-
-// 32 lanes x 32 bit, 16 consecutive columns per thread
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-	uint32_t r[16];
-	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-	               "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-	             : "r"(taddr));
-	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-	for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
-}
-
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-	const __half2 h = __floats2half2_rn(a, b);
-	return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // TMEM accumulators of this thread's row -> ReLU -> fp16 -> operand tile of the next layer (N_COLS / 8 chunks of 16 bytes)

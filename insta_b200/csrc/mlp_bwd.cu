@@ -1,0 +1,590 @@
+// The NeRF network of the INSTA hot path on sm_100a, training direction: forward + backward of hash grid, density MLP, SH and
+// colour MLP on the compacted batch (2^18 samples).  Replaces ngp::NerfNetwork::forward_impl / backward_impl (ngp nerf_network.h:
+// 238-383) and what they launch: kernel_grid, kernel_mlp_fused (forward, activations kept), kernel_mlp_fused_backward
+// (tcnn src/fully_fused_mlp.cu:151-313), the seven split-k CUTLASS weight-gradient GEMMs (755-855), add_density_gradient /
+// extract_rgb glue, and kernel_grid_backward (tcnn encodings/grid.h:312-435, via hashgrid.cu).
+//
+// Two tcgen05 kernels:
+//   net_fwd_bwd_kernel  persistent, same encoder / MLP warp split as the inference kernel (mlp.cu).  Per 128-sample tile: the
+//                       forward chain (7 GEMMs), then the data-gradient chain (7 GEMMs against TRANSPOSED weights staged once
+//                       per CTA).  ReLU masks stay in registers (64 bits per hidden layer and sample); every layer's input X_l
+//                       and output gradient dY_l is written once to a global fp16 scratch (row-major) for the weight gradients;
+//                       dL/d(grid features) leaves as the SoA matrix kernel hash_bwd_kernel scatters.
+//   net_wgrad_kernel    dW_l = dY_l^T X_l for all seven layers in one pass over the samples: both operands are used in their
+//                       MN-major (transposed) UMMA form, which is exactly the row-major scratch copied in 16-byte chunks; all
+//                       seven fp32 accumulators (496 columns) live in tensor memory for the whole kernel; one fp32 atomicAdd
+//                       pass per CTA at the end.  M is padded to 128 by letting the descriptor run into the next layers' tiles
+//                       (rows >= n_out are never read back).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "ctx.h"
+#include "grid_device.cuh"
+#include "umma.cuh"
+
+namespace insta {
+namespace {
+using namespace griddev;
+using namespace umma;
+
+constexpr int kTileM = 128;
+constexpr int kMlpWarps = 4, kEncWarps = 8;
+constexpr int kMlpThreads = kMlpWarps * 32, kNetThreads = (kMlpWarps + kEncWarps) * 32;
+constexpr int kWidth = 64, kInDensity = 144, kInRgb = 32, kOutPad = 16;
+constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kWidth * kInDensity, kOffW3 = kOffW2 + kWidth * kWidth;
+constexpr uint32_t kOffV1 = kOffW3 + kOutPad * kWidth, kOffV2 = kOffV1 + kWidth * kInRgb, kOffV3 = kOffV2 + kWidth * kWidth;
+constexpr uint32_t kOffV4 = kOffV3 + kWidth * kWidth, kOffGrid = kOffV4 + kOutPad * kWidth;
+
+// per-layer shapes, layer order = parameter order
+__constant__ const uint32_t c_nout[7] = {64, 64, 16, 64, 64, 64, 16};
+__constant__ const uint32_t c_kin[7] = {144, 64, 64, 32, 64, 64, 64};
+__constant__ const uint32_t c_woff[7] = {kOffW1, kOffW2, kOffW3, kOffV1, kOffV2, kOffV3, kOffV4};
+// column offsets (halves) of X_l / dY_l inside one scratch row
+constexpr uint32_t kXCols = 496, kDyCols = 352;
+__constant__ const uint32_t c_xoff[7] = {0, 144, 208, 272, 304, 368, 432};
+__constant__ const uint32_t c_dyoff[7] = {0, 64, 128, 144, 208, 272, 336};
+
+constexpr uint32_t kChunkA = kTileM * 16;
+constexpr uint32_t kBytesA0 = (kInDensity / 8) * kChunkA, kBytesH = (kWidth / 8) * kChunkA, kBytesA3 = (kInRgb / 8) * kChunkA;
+constexpr uint32_t kWBytes = kOffGrid * 2;  // 51,200
+constexpr uint32_t kSmA0 = 0, kSmH = kSmA0 + 2 * kBytesA0, kSmA3 = kSmH + 2 * kBytesH, kSmW = kSmA3 + kBytesA3, kSmWt = kSmW + kWBytes;
+constexpr uint32_t kSmBar = kSmWt + kWBytes, kSmTotal = kSmBar + 64;
+constexpr uint32_t kTmemCols = 256;
+
+__device__ __forceinline__ void mlp_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMlpThreads) : "memory"); }
+
+template <int N, int K>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t mma_bar) {
+	constexpr uint32_t idesc = umma_idesc(kTileM, N);
+#pragma unroll
+	for (int j = 0; j < K / 16; ++j) {
+		const uint64_t ad = umma_desc(a_saddr + j * 2 * kChunkA, kChunkA, 128);
+		const uint64_t bd = umma_desc(b_saddr + j * 2 * (N * 16), N * 16, 128);
+		umma_f16(tmem, ad, bd, idesc, j > 0 ? 1u : 0u);
+	}
+	umma_commit(mma_bar);
+}
+
+// weights [N][K] row-major -> K-major operand tile (B of the forward GEMMs)
+__device__ __forceinline__ void stage_w(unsigned char* dst, const __half* __restrict__ w, int N, int K) {
+	for (int t = threadIdx.x; t < N * (K / 8); t += blockDim.x) {
+		const int n = t / (K / 8), kc = t - n * (K / 8);
+		*reinterpret_cast<uint4*>(dst + kc * (N * 16) + (n >> 3) * 128 + (n & 7) * 16) = __ldg(reinterpret_cast<const uint4*>(w + (size_t)n * K + kc * 8));
+	}
+}
+// the same weights transposed: operand B of dX = dY W is Bt[n = in][k = out] = W[out][in], K-major in `out`
+__device__ __forceinline__ void stage_wt(unsigned char* dst, const __half* __restrict__ w, int N_out, int K_in) {
+	for (int t = threadIdx.x; t < K_in * (N_out / 8); t += blockDim.x) {
+		const int i = t / (N_out / 8), oc = t - i * (N_out / 8);
+		__half v[8];
+#pragma unroll
+		for (int e = 0; e < 8; ++e) v[e] = w[(size_t)(oc * 8 + e) * K_in + i];
+		*reinterpret_cast<uint4*>(dst + oc * (K_in * 16) + (i >> 3) * 128 + (i & 7) * 16) = *reinterpret_cast<const uint4*>(v);
+	}
+}
+
+// forward epilogue: TMEM row -> (ReLU, mask bits) -> fp16 -> next operand tile + global scratch row
+template <int N_COLS, bool RELU>
+__device__ __forceinline__ void epi_fwd(uint32_t taddr, unsigned char* tile, uint32_t tile_chunk0, uint32_t row, uint32_t* mask, __half* grow, float* keep0) {
+	unsigned char* dst = tile + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+	for (int c0 = 0; c0 < N_COLS; c0 += 16) {
+		float v[16];
+		tmem_ld16(taddr + c0, v);
+		if (RELU) {
+			uint32_t bits = 0;
+#pragma unroll
+			for (int k = 0; k < 16; ++k) {
+				bits |= (v[k] > 0.0f ? 1u : 0u) << k;
+				v[k] = fmaxf(v[k], 0.0f);
+			}
+			mask[c0 / 32] |= bits << (c0 % 32);
+		}
+		const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+		const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+		*reinterpret_cast<uint4*>(dst + (tile_chunk0 + c0 / 8) * kChunkA) = lo;
+		*reinterpret_cast<uint4*>(dst + (tile_chunk0 + c0 / 8 + 1) * kChunkA) = hi;
+		if (grow) {
+			*reinterpret_cast<uint4*>(grow + c0) = lo;
+			*reinterpret_cast<uint4*>(grow + c0 + 8) = hi;
+		}
+		if (keep0 && c0 == 0) *keep0 = v[0];
+	}
+}
+
+// backward epilogue: TMEM row -> (mask) -> fp16 -> operand tile of the next data-gradient GEMM + global scratch row.
+// add0 is added to column 0 before rounding (the density gradient joining the colour MLP's input gradient).
+template <int N_COLS, bool MASK>
+__device__ __forceinline__ void epi_bwd(uint32_t taddr, unsigned char* tile, uint32_t row, const uint32_t* mask, __half* grow, float add0) {
+	unsigned char* dst = tile + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+	for (int c0 = 0; c0 < N_COLS; c0 += 16) {
+		float v[16];
+		tmem_ld16(taddr + c0, v);
+		if (MASK) {
+			const uint32_t bits = mask[c0 / 32] >> (c0 % 32);
+#pragma unroll
+			for (int k = 0; k < 16; ++k) v[k] = ((bits >> k) & 1u) ? v[k] : 0.0f;
+		}
+		if (c0 == 0) v[0] += add0;
+		const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+		const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+		*reinterpret_cast<uint4*>(dst + (c0 / 8) * kChunkA) = lo;
+		*reinterpret_cast<uint4*>(dst + (c0 / 8 + 1) * kChunkA) = hi;
+		*reinterpret_cast<uint4*>(grow + c0) = lo;
+		*reinterpret_cast<uint4*>(grow + c0 + 8) = hi;
+	}
+}
+
+__device__ __forceinline__ void sh4(float x, float y, float z, uint4& lo, uint4& hi) {
+	const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+	float o[16];
+	o[0] = 0.28209479177387814f;
+	o[1] = -0.48860251190291987f * y;
+	o[2] = 0.48860251190291987f * z;
+	o[3] = -0.48860251190291987f * x;
+	o[4] = 1.0925484305920792f * xy;
+	o[5] = -1.0925484305920792f * yz;
+	o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+	o[7] = -1.0925484305920792f * xz;
+	o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+	o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+	o[10] = 2.8906114426405538f * xy * z;
+	o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+	o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+	o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+	o[14] = 1.4453057213202769f * z * (x2 - y2);
+	o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+	lo = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+	hi = make_uint4(pack2(o[8], o[9]), pack2(o[10], o[11]), pack2(o[12], o[13]), pack2(o[14], o[15]));
+}
+
+struct BwdArgs {
+	const float* records;
+	uint32_t stride, n, n_extra, n_pad;  // n_pad: rows of the scratch matrices (multiple of 128)
+	const __half* params;
+	const __half* dloss;    // dloss_width halves per sample: d(r, g, b, sigma)
+	uint32_t dloss_width;
+	__half* out;            // nullable: forward output, 4 halves per sample
+	__half* xs;             // [n_pad][kXCols]
+	__half* dys;            // [n_pad][kDyCols]
+	__half* dfeat;          // [128][n_pad] SoA: dL/d(grid features)
+	GridLevels L;
+};
+
+__global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __grid_constant__ BwdArgs a) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const uint32_t sbase = smem_u32(smem);
+	const uint32_t bar_full0 = sbase + kSmBar, bar_empty0 = sbase + kSmBar + 16, bar_mma = sbase + kSmBar + 32;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 40);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t n_tiles = (a.n + kTileM - 1) / kTileM;
+
+	for (int l = 0; l < 7; ++l) {
+		stage_w(smem + kSmW + c_woff[l] * 2, a.params + c_woff[l], (int)c_nout[l], (int)c_kin[l]);
+		stage_wt(smem + kSmWt + c_woff[l] * 2, a.params + c_woff[l], (int)c_nout[l], (int)c_kin[l]);
+	}
+	if (threadIdx.x == 0) {
+		mbar_init(bar_full0, kEncWarps);
+		mbar_init(bar_full0 + 8, kEncWarps);
+		mbar_init(bar_empty0, 1);
+		mbar_init(bar_empty0 + 8, 1);
+		mbar_init(bar_mma, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 0) {
+		__syncwarp();
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	fence_proxy_async();
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp >= kMlpWarps) {
+		// =================================== encoders (as in mlp.cu, plus the global copy of X0) ===================================
+		const uint32_t e = threadIdx.x - kMlpThreads;
+		const uint32_t row = e & (kTileM - 1), half_id = e >> 7;
+		const uint4* table = reinterpret_cast<const uint4*>(a.params + kOffGrid);
+		uint32_t it = 0;
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+			const uint32_t b = it & 1u;
+			mbar_wait(bar_empty0 + 8 * b, ((it >> 1) & 1u) ^ 1u);
+			unsigned char* A0 = smem + kSmA0 + b * kBytesA0 + (row >> 3) * 128 + (row & 7) * 16;
+			const uint32_t i = tile * kTileM + row;
+			__half* x0 = a.xs + (size_t)i * kXCols;  // i < n_pad always
+			if (i < a.n) {
+				const float* rec = a.records + (size_t)i * a.stride;
+				const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
+#pragma unroll 2
+				for (uint32_t l = 0; l < 8; ++l) {
+					const uint32_t level = half_id * 8 + l;
+					__half2 acc[4] = {__half2(), __half2(), __half2(), __half2()};
+					if (level < a.L.n_levels) {
+						const Corner c = pos_fract3(px, py, pz, a.L.scale[level]);
+						if (a.L.hashed[level]) encode_one<true>(table + a.L.offset[level], c, a.L.size[level], 0, 0, acc);
+						else encode_one<false>(table + a.L.offset[level], c, a.L.size[level], a.L.mul1[level], a.L.mul2[level], acc);
+					}
+					const uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&acc[0]), *reinterpret_cast<uint32_t*>(&acc[1]), *reinterpret_cast<uint32_t*>(&acc[2]),
+					                           *reinterpret_cast<uint32_t*>(&acc[3]));
+					*reinterpret_cast<uint4*>(A0 + level * kChunkA) = v;
+					*reinterpret_cast<uint4*>(x0 + level * 8) = v;
+				}
+				float ex[8];
+#pragma unroll
+				for (uint32_t k = 0; k < 8; ++k) {
+					const uint32_t d = half_id * 8 + k;
+					ex[k] = d < a.n_extra ? __ldg(rec + a.stride - a.n_extra + d) : 0.0f;
+				}
+				const uint4 v = make_uint4(pack2(ex[0], ex[1]), pack2(ex[2], ex[3]), pack2(ex[4], ex[5]), pack2(ex[6], ex[7]));
+				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = v;
+				*reinterpret_cast<uint4*>(x0 + (16 + half_id) * 8) = v;
+			} else {
+				const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+				for (uint32_t l = 0; l < 8; ++l) {
+					*reinterpret_cast<uint4*>(A0 + (half_id * 8 + l) * kChunkA) = z;
+					*reinterpret_cast<uint4*>(x0 + (half_id * 8 + l) * 8) = z;
+				}
+				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = z;
+				*reinterpret_cast<uint4*>(x0 + (16 + half_id) * 8) = z;
+			}
+			fence_proxy_async();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_full0 + 8 * b);
+		}
+	} else {
+		// =================================== MLP warps: forward chain, then data-gradient chain ===================================
+		const uint32_t row = threadIdx.x;
+		const uint32_t taddr = tmem_base + ((warp * 32u) << 16);
+		unsigned char* H0 = smem + kSmH;
+		unsigned char* H1 = smem + kSmH + kBytesH;
+		unsigned char* A3 = smem + kSmA3;
+		const uint32_t sH0 = sbase + kSmH, sH1 = sH0 + kBytesH, sA3 = sbase + kSmA3, sW = sbase + kSmW, sWt = sbase + kSmWt;
+		uint32_t mma_phase = 0, it = 0;
+		const bool issuer = threadIdx.x == 0;
+#define MMA_WAIT()                        \
+	mbar_wait(bar_mma, mma_phase);        \
+	mma_phase ^= 1u;                      \
+	tc_fence_after()
+#define TILE_READY()     \
+	fence_proxy_async(); \
+	tc_fence_before();   \
+	mlp_bar_sync();      \
+	tc_fence_after()
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+			const uint32_t b = it & 1u;
+			const uint32_t i = tile * kTileM + row;
+			const bool valid = i < a.n;
+			__half* xrow = a.xs + (size_t)i * kXCols;
+			__half* dyrow = a.dys + (size_t)i * kDyCols;
+			float dx = 0.5f, dy = 0.5f, dz = 0.5f;
+			float g_rgb[3] = {0.f, 0.f, 0.f}, g_sigma = 0.f;
+			if (valid) {
+				const float* rec = a.records + (size_t)i * a.stride;
+				dx = __ldg(rec + 8); dy = __ldg(rec + 9); dz = __ldg(rec + 10);
+				const uint2 raw = *reinterpret_cast<const uint2*>(a.dloss + (size_t)i * a.dloss_width);
+				const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+				g_rgb[0] = lo.x; g_rgb[1] = lo.y; g_rgb[2] = hi.x; g_sigma = hi.y;
+			}
+			uint32_t m1[2] = {0, 0}, m2[2] = {0, 0}, m4[2] = {0, 0}, m5[2] = {0, 0}, m6[2] = {0, 0};
+			// ---------------- forward ----------------
+			mbar_wait(bar_full0 + 8 * b, (it >> 1) & 1u);
+			tc_fence_after();
+			if (issuer) issue_gemm<kWidth, kInDensity>(tmem_base, sbase + kSmA0 + b * kBytesA0, sW + kOffW1 * 2, bar_mma);
+			{
+				uint4 lo, hi;
+				sh4(dx * 2.f - 1.f, dy * 2.f - 1.f, dz * 2.f - 1.f, lo, hi);
+				unsigned char* dst = A3 + (row >> 3) * 128 + (row & 7) * 16;
+				*reinterpret_cast<uint4*>(dst + 2 * kChunkA) = lo;
+				*reinterpret_cast<uint4*>(dst + 3 * kChunkA) = hi;
+				*reinterpret_cast<uint4*>(xrow + 272 + 16) = lo;
+				*reinterpret_cast<uint4*>(xrow + 272 + 24) = hi;
+			}
+			MMA_WAIT();
+			if (issuer) mbar_arrive(bar_empty0 + 8 * b);
+			epi_fwd<kWidth, true>(taddr, H0, 0, row, m1, xrow + 144, nullptr);
+			TILE_READY();
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sW + kOffW2 * 2, bar_mma);
+			MMA_WAIT();
+			epi_fwd<kWidth, true>(taddr, H1, 0, row, m2, xrow + 208, nullptr);
+			TILE_READY();
+			if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH1, sW + kOffW3 * 2, bar_mma);
+			MMA_WAIT();
+			float sigma = 0.f;
+			epi_fwd<kOutPad, false>(taddr, A3, 0, row, nullptr, xrow + 272, &sigma);
+			TILE_READY();
+			if (issuer) issue_gemm<kWidth, kInRgb>(tmem_base, sA3, sW + kOffV1 * 2, bar_mma);
+			MMA_WAIT();
+			epi_fwd<kWidth, true>(taddr, H0, 0, row, m4, xrow + 304, nullptr);
+			TILE_READY();
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sW + kOffV2 * 2, bar_mma);
+			MMA_WAIT();
+			epi_fwd<kWidth, true>(taddr, H1, 0, row, m5, xrow + 368, nullptr);
+			TILE_READY();
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH1, sW + kOffV3 * 2, bar_mma);
+			MMA_WAIT();
+			epi_fwd<kWidth, true>(taddr, H0, 0, row, m6, xrow + 432, nullptr);
+			TILE_READY();
+			if (a.out) {  // forward output, when the caller wants it
+				if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH0, sW + kOffV4 * 2, bar_mma);
+				MMA_WAIT();
+				float o[16];
+				tmem_ld16(taddr, o);
+				tc_fence_before();
+				if (valid) {
+					const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], __half2float(__float2half_rn(sigma)));
+					*reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
+				}
+				mlp_bar_sync();
+				tc_fence_after();
+			}
+			// ---------------- backward: data gradients ----------------
+			{
+				// dOut (colour output layer): d(r, g, b) in columns 0-2, the rest 0
+				const uint4 lo = make_uint4(pack2(g_rgb[0], g_rgb[1]), pack2(g_rgb[2], 0.f), 0u, 0u), z = make_uint4(0, 0, 0, 0);
+				unsigned char* dst = H1 + (row >> 3) * 128 + (row & 7) * 16;
+				*reinterpret_cast<uint4*>(dst) = lo;
+				*reinterpret_cast<uint4*>(dst + kChunkA) = z;
+				*reinterpret_cast<uint4*>(dyrow + 336) = lo;
+				*reinterpret_cast<uint4*>(dyrow + 344) = z;
+			}
+			TILE_READY();
+			// dG3 = dOut V4  (K = 16)
+			if (issuer) issue_gemm<kWidth, kOutPad>(tmem_base, sH1, sWt + kOffV4 * 2, bar_mma);
+			MMA_WAIT();
+			epi_bwd<kWidth, true>(taddr, H0, row, m6, dyrow + 272, 0.f);
+			TILE_READY();
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sWt + kOffV3 * 2, bar_mma);
+			MMA_WAIT();
+			epi_bwd<kWidth, true>(taddr, H1, row, m5, dyrow + 208, 0.f);
+			TILE_READY();
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH1, sWt + kOffV2 * 2, bar_mma);
+			MMA_WAIT();
+			epi_bwd<kWidth, true>(taddr, H0, row, m4, dyrow + 144, 0.f);
+			TILE_READY();
+			// d(colour MLP input) = dG1 V1: columns 0-15 are the density network's outputs (+ d sigma on column 0), 16-31 the SH
+			if (issuer) issue_gemm<kInRgb, kWidth>(tmem_base, sH0, sWt + kOffV1 * 2, bar_mma);
+			MMA_WAIT();
+			epi_bwd<kOutPad, false>(taddr, H1, row, nullptr, dyrow + 128, g_sigma);
+			TILE_READY();
+			// dH2 = dD W3 (K = 16)
+			if (issuer) issue_gemm<kWidth, kOutPad>(tmem_base, sH1, sWt + kOffW3 * 2, bar_mma);
+			MMA_WAIT();
+			epi_bwd<kWidth, true>(taddr, H0, row, m2, dyrow + 64, 0.f);
+			TILE_READY();
+			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sWt + kOffW2 * 2, bar_mma);
+			MMA_WAIT();
+			epi_bwd<kWidth, true>(taddr, H1, row, m1, dyrow + 0, 0.f);
+			TILE_READY();
+			// dX0 = dH1 W1: 144 columns; the first 128 are the grid features
+			if (issuer) issue_gemm<kInDensity, kWidth>(tmem_base, sH1, sWt + kOffW1 * 2, bar_mma);
+			MMA_WAIT();
+#pragma unroll 1
+			for (int c0 = 0; c0 < 128; c0 += 16) {
+				float v[16];
+				tmem_ld16(taddr + c0, v);
+#pragma unroll
+				for (int k = 0; k < 16; ++k) a.dfeat[(size_t)(c0 + k) * a.n_pad + i] = __float2half_rn(v[k]);
+			}
+			tc_fence_before();
+			mlp_bar_sync();
+			tc_fence_after();
+		}
+#undef MMA_WAIT
+#undef TILE_READY
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
+// ======================================================================================================================
+// Weight gradients.
+constexpr int kWgThreads = 256;
+constexpr uint32_t kWgK = 32;                          // samples per stage
+constexpr uint32_t kWgSbo = (kWgK / 8) * 128 + 16;     // 528: stride between 8-feature groups (+16 B: bank spread of the copy)
+constexpr uint32_t kWgXGroups = kXCols / 8, kWgDyGroups = kDyCols / 8;
+constexpr uint32_t kWgXBytes = kWgXGroups * kWgSbo, kWgDyBytes = (kWgDyGroups + 16) * kWgSbo;  // + 16 groups the M = 128 descriptor may touch
+constexpr uint32_t kWgStage = kWgXBytes + kWgDyBytes;
+constexpr uint32_t kWgBar = 2 * kWgStage, kWgSmTotal = kWgBar + 64;
+constexpr uint32_t kWgTmemCols = 512;
+__constant__ const uint32_t c_wgcol[7] = {0, 144, 208, 272, 304, 368, 432};  // accumulator column of layer l (= c_xoff)
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory"); }
+
+struct WgArgs {
+	const __half* xs;
+	const __half* dys;
+	uint32_t n_pad;
+	float* dw32;  // 25,600 floats, accumulated with atomics
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) net_wgrad_kernel(const WgArgs a) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const uint32_t sbase = smem_u32(smem);
+	const uint32_t bar_free0 = sbase + kWgBar, bar_done = sbase + kWgBar + 16;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWgBar + 24);
+	const uint32_t warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) {
+		mbar_init(bar_free0, 1);
+		mbar_init(bar_free0 + 8, 1);
+		mbar_init(bar_done, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	// the padding groups behind the dY tiles are read by the M = 128 descriptors: keep them finite
+	for (uint32_t t = threadIdx.x; t < 2 * kWgStage / 16; t += blockDim.x) reinterpret_cast<uint4*>(smem)[t] = make_uint4(0, 0, 0, 0);
+	if (warp == 0) {
+		__syncwarp();
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kWgTmemCols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	fence_proxy_async();
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	const uint32_t n_blocks = a.n_pad / kWgK;
+	uint32_t it = 0;
+	for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+		const uint32_t s = it & 1u;
+		mbar_wait(bar_free0 + 8 * s, ((it >> 1) & 1u) ^ 1u);  // the MMAs that read this stage two iterations ago are done
+		const uint32_t sx = sbase + s * kWgStage, sdy = sx + kWgXBytes;
+		const size_t row0 = (size_t)blk * kWgK;
+		// chunk (sample k, feature group g): 16 bytes of the row-major scratch -> MN-major unit
+		for (uint32_t t = threadIdx.x; t < kWgK * kWgXGroups; t += blockDim.x) {
+			const uint32_t k = t / kWgXGroups, g = t - k * kWgXGroups;
+			cp_async16(sx + g * kWgSbo + (k >> 3) * 128 + (k & 7) * 16, a.xs + (row0 + k) * kXCols + g * 8);
+		}
+		for (uint32_t t = threadIdx.x; t < kWgK * kWgDyGroups; t += blockDim.x) {
+			const uint32_t k = t / kWgDyGroups, g = t - k * kWgDyGroups;
+			cp_async16(sdy + g * kWgSbo + (k >> 3) * 128 + (k & 7) * 16, a.dys + (row0 + k) * kDyCols + g * 8);
+		}
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		fence_proxy_async();
+		tc_fence_before();
+		__syncthreads();
+		tc_fence_after();
+		if (threadIdx.x == 0) {
+#pragma unroll
+			for (int l = 0; l < 7; ++l) {
+				const uint32_t idesc = umma_idesc(128, c_kin[l], 1, 1);
+#pragma unroll
+				for (uint32_t j = 0; j < kWgK / 16; ++j) {
+					const uint64_t ad = umma_desc(sdy + (c_dyoff[l] / 8) * kWgSbo + j * 256, 128, kWgSbo);
+					const uint64_t bd = umma_desc(sx + (c_xoff[l] / 8) * kWgSbo + j * 256, 128, kWgSbo);
+					umma_f16(tmem_base + c_wgcol[l], ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+				}
+			}
+			umma_commit(bar_free0 + 8 * s);
+		}
+	}
+	// all MMAs done -> epilogue
+	if (threadIdx.x == 0) umma_commit(bar_done);
+	mbar_wait(bar_done, 0);
+	tc_fence_after();
+	if (it > 0 && warp < 2) {
+		const uint32_t o = threadIdx.x;  // output row = TMEM lane, 0..63
+		const uint32_t taddr = tmem_base + ((warp * 32u) << 16);
+#pragma unroll 1
+		for (int l = 0; l < 7; ++l) {
+			const uint32_t kin = c_kin[l], nout = c_nout[l];
+			for (uint32_t c0 = 0; c0 < kin; c0 += 16) {
+				float v[16];
+				tmem_ld16(taddr + c_wgcol[l] + c0, v);
+				if (o < nout) {
+					float* dst = a.dw32 + c_woff[l] + (size_t)o * kin + c0;
+#pragma unroll
+					for (int k = 0; k < 16; ++k) atomicAdd(dst + k, v[k]);
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kWgTmemCols) : "memory");
+}
+
+__global__ void wgrad_finish_kernel(uint32_t n, float* __restrict__ dw32, __half* __restrict__ grads) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	grads[i] = __float2half_rn(dw32[i]);
+	dw32[i] = 0.f;
+}
+
+}  // namespace
+
+struct BwdScratch {
+	uint32_t n_pad = 0;
+	__half* xs = nullptr;
+	__half* dys = nullptr;
+	__half* dfeat = nullptr;
+	float* dw32 = nullptr;
+};
+
+void network_bwd_destroy(insta_ctx* ctx) {
+	BwdScratch* s = (BwdScratch*)ctx->bwd_scratch;
+	if (!s) return;
+	cudaFree(s->xs); cudaFree(s->dys); cudaFree(s->dfeat); cudaFree(s->dw32);
+	delete s;
+	ctx->bwd_scratch = nullptr;
+}
+
+// NerfNetwork::forward + backward on the compacted batch: fills the fp16 gradient buffer (MLP weights, then grid) in parameter order.
+int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,
+                           void* d_grads, void* d_out, cudaStream_t s) {
+	if (n == 0) return INSTA_OK;
+	if (!ctx->bwd_scratch) ctx->bwd_scratch = new BwdScratch();
+	BwdScratch* sc = (BwdScratch*)ctx->bwd_scratch;
+	const uint32_t n_pad = (n + kTileM - 1) / kTileM * kTileM;
+	if (n_pad > sc->n_pad) {
+		INSTA_CUDA(cudaDeviceSynchronize());
+		cudaFree(sc->xs); cudaFree(sc->dys); cudaFree(sc->dfeat);
+		sc->xs = sc->dys = sc->dfeat = nullptr;
+		sc->n_pad = 0;
+		INSTA_CUDA(cudaMalloc(&sc->xs, (size_t)n_pad * kXCols * 2));
+		INSTA_CUDA(cudaMalloc(&sc->dys, (size_t)n_pad * kDyCols * 2));
+		INSTA_CUDA(cudaMalloc(&sc->dfeat, (size_t)n_pad * 128 * 2));
+		sc->n_pad = n_pad;
+	}
+	if (!sc->dw32) {
+		INSTA_CUDA(cudaMalloc(&sc->dw32, kOffGrid * sizeof(float)));
+		INSTA_CUDA(cudaMemsetAsync(sc->dw32, 0, kOffGrid * sizeof(float), s));
+	}
+	BwdArgs a{};
+	a.records = d_records;
+	a.stride = stride;
+	a.n = n;
+	a.n_extra = ctx->p.exp_params + ctx->p.geo_params;
+	a.n_pad = n_pad;
+	a.params = (const __half*)d_params;
+	a.dloss = (const __half*)d_dloss;
+	a.dloss_width = dloss_width;
+	a.out = (__half*)d_out;
+	a.xs = sc->xs;
+	a.dys = sc->dys;
+	a.dfeat = sc->dfeat;
+	a.L = ctx->levels;
+	// rows [n, n_pad) of the dY scratch are read by the weight-gradient kernel: they must be zero
+	if (n_pad > n) INSTA_CUDA(cudaMemsetAsync(sc->dys + (size_t)n * kDyCols, 0, (size_t)(n_pad - n) * kDyCols * 2, s));
+	INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+	const uint32_t n_tiles = n_pad / kTileM;
+	net_fwd_bwd_kernel<<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), kNetThreads, kSmTotal, s>>>(a);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	WgArgs w{sc->xs, sc->dys, n_pad, sc->dw32};
+	INSTA_CUDA(cudaFuncSetAttribute(net_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmTotal));
+	net_wgrad_kernel<<<std::min<uint32_t>(n_pad / kWgK, (uint32_t)ctx->sm_count), kWgThreads, kWgSmTotal, s>>>(w);
+	ctx->launches++;
+	wgrad_finish_kernel<<<(kOffGrid + 255) / 256, 256, 0, s>>>(kOffGrid, sc->dw32, (__half*)d_grads);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	// grid gradients: kernel_grid_backward on the SoA dL/d(features)
+	return launch_hash_bwd_pitched(ctx, d_records, stride, n, sc->dfeat, n_pad, (__half*)d_grads + kOffGrid, 1, s);
+}
+
+}  // namespace insta

@@ -1,0 +1,70 @@
+// tcgen05 / TMEM / mbarrier helpers shared by the network kernels (mlp.cu, mlp_bwd.cu).  Operand tiles live in shared memory in
+// the canonical no-swizzle UMMA layouts (cute/arch/mma_sm100_desc.hpp, cute/atom/mma_traits_sm100.hpp of CUTLASS describe them):
+//   K-major : 16-byte unit = 8 consecutive K elements of one row;   8 rows x 16 B = one 128-byte core matrix;
+//             SBO = byte stride between 8-row groups, LBO = byte stride between 8-element K chunks
+//   MN-major: 16-byte unit = 8 consecutive M/N elements at one k;    8 k x 16 B = one 128-byte core matrix;
+//             SBO = byte stride between 8-element M/N groups, LBO = byte stride between groups of 8 k
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace insta {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no swizzle: start address, LBO (K direction), SBO (M/N direction), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+	return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16: D = F32, A = B = F16, dense; a_mn / b_mn = 1 selects the MN-major (transposed) form of that operand
+__device__ __forceinline__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
+	return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+	    "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 bit, 16 consecutive columns per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+	uint32_t r[16];
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+	               "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+	             : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+	const __half2 h = __floats2half2_rn(a, b);
+	return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+}  // namespace umma
+}  // namespace insta
