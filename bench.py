@@ -300,9 +300,17 @@ def run_ours(args):
         e2e_total = float(t.item())
     e2e_value = world * N_SAMPLES * len(e2e_t) / e2e_total
 
-    net = rnd = None
+    net = rnd = trn = None
     if not args.no_render:
         net = network_leg(ctx, rec_np, args) if rank == 0 else None
+        del bufs, pristine, h_rec0, h_rec, h_out  # the legs below bring their own buffers
+        torch.cuda.empty_cache()
+        try:
+            trn = train_leg(ctx, verts, fv, args, rank, world)
+        except Exception as e:
+            if world > 1:
+                raise
+            trn = {"error": repr(e)}
         rnd = render_leg(ctx, verts, fv, args, rank, world)
         if world > 1:
             # frames are sharded over ranks: aggregate frames/s = sum over ranks, ms/frame reported = max over ranks
@@ -343,6 +351,7 @@ def run_ours(args):
         if not args.no_render:
             line["network"] = net
             line["render"] = rnd
+            line["train_step"] = trn
         if world == 1 and args.ref_cuda:
             try:
                 line["ref_cuda"] = ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args)
@@ -388,6 +397,105 @@ def render_leg(ctx, verts, fv, args, rank, world):
     return {"ms_per_frame": float(np.mean(ms)), "ms_per_frame_min": float(np.min(ms)), "resolution": list(res), "frames_timed": len(ms),
             "samples_per_frame": float(np.mean(samples)), "march_iterations_per_frame": float(np.mean(iters)),
             "hit_fraction": float((fr[:, 3] > 0.2).float().mean()), "note": "deform + fused encode/MLP (tcgen05) + composite per iteration; one stream sync per iteration"}
+
+
+def train_leg(ctx, verts, fv, args, rank, world):
+    """BASELINE.json configs[3]: one full training step (sample generation, deformation, inference, loss + compaction, forward + backward,
+    gradient allreduce over NCCL at N > 1, Adam + EMA) through insta_train_nerf, target batch 2^18 samples, rays_per_batch adapting up to
+    2^18 as in the reference; plus the occupancy-grid refresh (insta_update_density_grid on 2 x 2^19 points, random frame per point).
+    Synthetic 512^2 byte images, one per local frame (<= --train-images), cameras as in the render leg."""
+    import torch
+    import torch.distributed as dist
+
+    from insta_b200 import synth
+
+    n_img = min(ctx.n_frames, args.train_images)
+    if n_img == 0:
+        return None
+    res = (512, 512)
+    ims = synth.make_training_images(n_img, res, 1200.0, seed=11 + rank, with_rays=False, mask_fraction=0.0)
+    dev = []
+    for im in ims:
+        d = dict(im)
+        pix = np.clip(im["pixels"], 0.0, 1.0)
+        d["pixels"] = torch.from_numpy((pix * 255.0 + 0.5).astype(np.uint8)).cuda()
+        d["type"] = 1
+        d["seg"] = torch.from_numpy(im["seg"]).cuda()
+        d["depth"] = torch.from_numpy(im["depth"]).cuda()
+        dev.append(d)
+    ctx.training_set_images(dev)
+    bf0 = torch.from_numpy(synth.occupancy_bitfield([fv[k] for k in range(min(len(fv), 8))], radius=0.03)).cuda()
+    extra = torch.randn((n_img, 16), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    n = ctx.network_n_params
+    p16 = torch.from_numpy(synth.make_network_params(n, seed=1337, grid_scale=1e-4)).cuda()
+    p32, grads = p16.float(), torch.zeros(n, dtype=torch.float16, device="cuda")
+    m1, m2, steps, ema = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.int32, device="cuda"), p16.clone()
+    opt = ctx.make_optimizer(0, p32, p16, grads, m1, m2, steps, ema)
+    mean_density = torch.tensor([0.01], device="cuda")
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    # frames beyond n_img exist in the context, but the generator only draws images [0, n_img): frame i <-> image i
+    ctx.trainer_create(target_batch_size=1 << 18, rays_per_batch=1 << 12, depth_weight=1.25, seg_weight=40.0)
+    launches0 = ctx.launch_count
+    hist = []
+    for k in range(args.train_warmup):
+        hist.append(ctx.train_nerf(opt, bf0, extra, mean_density))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ts = []
+    l0 = ctx.launch_count
+    for k in range(args.train_steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = ctx.train_nerf(opt, bf0, extra, mean_density, get_loss_scalar=(k == args.train_steps - 1))
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+        hist.append(st)
+    launches = ctx.launch_count - l0
+    ms = float(np.mean(ts))
+    # occupancy-grid refresh (training_prep_nerf after step 256: 2^19 uniform + 2^19 non-uniform points)
+    grid = torch.zeros(128 ** 3, device="cuda")
+    bits = torch.zeros(128 ** 3, dtype=torch.uint8, device="cuda")
+    mean = torch.zeros(1, device="cuda")
+    g = ctx.make_density_grid(grid, bits, mean, rng_seed=7, has_rays=True)
+    g.training_step = 0
+    ctx.update_density_grid(g, p16, 128 ** 3, 0)
+    tg_full, tg = [], []
+    for k in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.training_step = 1 + k
+        e0.record()
+        ctx.update_density_grid(g, p16, 128 ** 3, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        tg_full.append(e0.elapsed_time(e1))
+    for k in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.training_step = 300 + k
+        e0.record()
+        ctx.update_density_grid(g, p16, 128 ** 3 // 4, 128 ** 3 // 4)
+        e1.record()
+        torch.cuda.synchronize()
+        tg.append(e0.elapsed_time(e1))
+    ctx.trainer_destroy()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        ctx.comm_destroy()
+    last = hist[-1]
+    return {"ms_per_step": ms, "ms_per_step_min": float(np.min(ts)), "steps_timed": len(ts), "warmup_steps": args.train_warmup, "target_batch_size": 1 << 18,
+            "rays_per_step": last["n_rays"], "samples_generated": last["measured_batch_size_before_compaction"], "samples_compacted": last["measured_batch_size"],
+            "aggregate_rays_per_s": world * last["n_rays"] / (ms * 1e-3), "loss": last["loss"], "images_per_gpu": n_img, "launches_per_step": launches / max(1, len(ts)),
+            "grad_allreduce": ("NCCL fp16 sum of %d halves per step" % n) if world > 1 else "none (1 GPU)",
+            "grid_update_ms": {"first_256_steps (2^21 uniform points)": float(np.mean(tg_full[1:])), "later (2^19 + 2^19 points)": float(np.mean(tg[1:]))},
+            "note": "insta_train_nerf: generate + deform + fused inference + loss/compaction + fused forward/backward (tcgen05) + Adam/EMA; one stream sync per step"}
 
 
 def network_leg(ctx, rec_np, args):
@@ -467,6 +575,9 @@ def main():
     ap.add_argument("--no-render", action="store_true", help="skip the network / 512^2 render legs")
     ap.add_argument("--render-res", type=int, default=512)
     ap.add_argument("--render-frames", type=int, default=8)
+    ap.add_argument("--train-images", type=int, default=128, help="synthetic 512^2 training images (= frames) per GPU in the train-step leg")
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--train-warmup", type=int, default=30)
     ap.add_argument("--ref-cuda", action="store_true", default=True)
     ap.add_argument("--no-ref-cuda", dest="ref_cuda", action="store_false")
     args = ap.parse_args()

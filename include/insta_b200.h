@@ -226,6 +226,11 @@ INSTA_API uint32_t insta_network_n_params(const insta_ctx* ctx); /* 25,600 + gri
 INSTA_API int insta_network_inference(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_out_f16,
                                       uint32_t out_stride_elems, insta_stream stream);
 
+/* NerfNetwork::density (nerf_network.h:385-414): hash grid + density MLP on bare positions (d_xyz[i * stride_floats + {0,1,2}]), expression
+ * inputs all 1 (extract_expressions_random, nerf_network.h:108-128); one fp16 density logit per sample. */
+INSTA_API int insta_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_logits_f16,
+                                    insta_stream stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Stage 3 -- training step pieces (ngp::Testbed::train_nerf_step, ngp/src/testbed_nerf.cu:3170-3426).
  * ------------------------------------------------------------------------------------------------------------ */
@@ -296,6 +301,90 @@ typedef struct insta_optimizer {
 	void*     d_params_ema_f16;
 } insta_optimizer;
 INSTA_API int insta_optimizer_step(insta_ctx* ctx, const insta_optimizer* opt, insta_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * One full training step -- ngp::Testbed::train_nerf (ngp/src/testbed_nerf.cu:2916-2992): Counters::prepare_for_training_steps,
+ * train_nerf_step (3170-3426: sample generation, rta::Core::surface_closest_point, inference, loss + compaction, forward + backward),
+ * the data-parallel gradient exchange (none in the single-GPU reference), tcnn::Trainer::optimizer_step (Adam + EMA) and
+ * Counters::update_after_training (2889-2914: adapts rays_per_batch so that the compacted batch approaches target_batch_size).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct insta_trainer_config {
+	uint32_t struct_size;            /* = sizeof(insta_trainer_config) */
+	uint32_t target_batch_size;      /* 2^18 (ngp testbed.h:857) */
+	uint32_t rays_per_batch;         /* initial Counters::rays_per_batch, 2^12 (ngp testbed.h:640) */
+	uint32_t snap_to_pixel_centers;  /* training.snap_to_pixel_centers */
+	uint32_t random_bg_color;        /* training.random_bg_color */
+	uint32_t penalize_density_alpha; /* "penalize_density_alpha" (core.cu:191) */
+	uint64_t rng_seed;               /* Testbed::m_rng seed (ngp/src/testbed.cu:2185: 1337) */
+	float    cone_angle_constant;
+	float    loss_scale;             /* LOSS_SCALE = 128 (ngp testbed.h:256) */
+	float    background_color[3];
+	float    depth_weight, seg_weight, near_distance, beta_loss; /* core.cu:189-208 */
+} insta_trainer_config;
+typedef struct insta_train_stats {
+	uint32_t training_step;          /* steps finished */
+	uint32_t n_rays;                 /* rays of THIS step */
+	uint32_t n_rays_accepted;        /* rays that hit occupied cells */
+	uint32_t rays_per_batch;         /* rays of the NEXT step */
+	uint32_t n_rays_total;
+	uint32_t measured_batch_size;    /* samples after compaction */
+	uint32_t measured_batch_size_before_compaction;
+	float    loss;                   /* loss scalar of update_after_training when requested, else 0 */
+} insta_train_stats;
+INSTA_API void insta_trainer_config_default(insta_trainer_config* cfg);
+/* allocates the step's workspace once (the reference takes it from the tcnn arena every step, testbed_nerf.cu:3175-3202): ~0.55 GB at 2^18 */
+INSTA_API int insta_trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg);
+INSTA_API int insta_trainer_destroy(insta_ctx* ctx);
+INSTA_API int insta_trainer_state(const insta_ctx* ctx, insta_train_stats* h_stats);
+/* one step.  opt: the trainer's buffers + hyper-parameters (opt->current_step = optimizer steps taken so far; opt->loss_scale is ignored in
+ * favour of the trainer's).  d_density_grid_bitfield / d_extra_dims ([n_images][exp_params]) / d_mean_density as in insta_train_step and
+ * insta_compute_loss.  Needs insta_training_set_images and frames (frame i deforms the samples of image i).  Synchronises the stream once
+ * at the end to read the counters back, like update_after_training. */
+INSTA_API int insta_train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_density_grid_bitfield, const float* d_extra_dims,
+                               const float* d_mean_density, int get_loss_scalar, insta_train_stats* h_stats, insta_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Occupancy-grid maintenance -- ngp::Testbed::training_prep_nerf / update_density_grid_nerf / update_density_grid_mean_and_bitfield
+ * (ngp/src/testbed_nerf.cu:3428-3444, 2774-2878) including the INSTA hook on the sampled points (rta::Core::surface_closest_point on
+ * bare xyz -> kernel `warp_random_samples`, src/core.cu:528-579; called at testbed_nerf.cu:2850) and NerfNetwork::density
+ * (ngp nerf_network.h:385-414).  The grid buffers are the caller's (Testbed::Nerf::density_grid / density_grid_bitfield /
+ * density_grid_mean, ngp testbed.h:642-646); the sample scratch is the context's.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct insta_density_grid {
+	float*   d_density_grid;          /* 128^3 * n_cascades floats, Morton order */
+	void*    d_density_grid_bitfield; /* 8 levels x 128^3 bits = 2 MiB (grid_mip_offset(NERF_CASCADES) / 8, testbed_nerf.cu:78-80) */
+	float*   d_density_grid_mean;     /* 1 float */
+	uint32_t n_cascades;              /* Testbed::Nerf::max_cascade + 1; 1 for aabb_scale 1 */
+	uint32_t ema_step;                /* density_grid_ema_step; advanced by every update */
+	uint64_t rng_seed;                /* density_grid_rng = default_rng_t{m_rng.next_uint()} (ngp/src/testbed.cu:2198) */
+	uint64_t rng_advances;            /* advanced by every update */
+	float    decay;                   /* training.density_grid_decay, 0.95 (ngp testbed.h:617) */
+	uint32_t training_step;           /* Testbed::m_training_step: 0 resets the grid, < 256 samples every cell */
+	uint32_t has_rays;                /* dataset.has_rays: skip the camera-frustum culling of step 0 */
+	uint32_t images_changed;          /* n_images_for_training != n_images_for_training_prev; cleared by the update */
+} insta_density_grid;
+/* update_density_grid_nerf with explicit sample counts; g->ema_step / rng_advances are advanced. d_params_f16: the TRAINING parameters
+ * (density(..., use_inference_params = false)). */
+INSTA_API int insta_update_density_grid(insta_ctx* ctx, insta_density_grid* g, const void* d_params_f16, uint32_t n_uniform_samples,
+                                        uint32_t n_nonuniform_samples, insta_stream stream);
+/* training_prep_nerf with Testbed::train's schedule (ngp/src/testbed.cu:2480-2481): does nothing unless
+ * training_step % clamp(training_step / 16, 1, 16) == 0; 128^3 * n_cascades uniform samples before step 256, a quarter uniform + a
+ * quarter non-uniform after.  *did_update (nullable) reports whether the grid was refreshed. */
+INSTA_API int insta_training_prep_nerf(insta_ctx* ctx, insta_density_grid* g, const void* d_params_f16, int* did_update, insta_stream stream);
+/* update_density_grid_mean_and_bitfield alone (e.g. after loading a snapshot's density grid) */
+INSTA_API int insta_update_density_grid_mean_and_bitfield(insta_ctx* ctx, const insta_density_grid* g, insta_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Data-parallel training across the GPUs of one box: one context (process) per GPU, each with its own shard of frames / images and its
+ * own ray batches; the only exchange step is the sum of the fp16 gradient buffer between backward and the optimizer step (SURVEY.md 8e;
+ * 25,741,888 halves = 51.5 MB), NCCL over NVLink on the caller's stream.  NCCL is resolved at run time (dlopen of libnccl.so.2); without
+ * a communicator every call below is a no-op for world size 1.
+ * ------------------------------------------------------------------------------------------------------------ */
+INSTA_API int insta_comm_unique_id(void* h_id128);  /* ncclGetUniqueId on rank 0; distribute the 128 bytes to the other ranks */
+INSTA_API int insta_comm_init_rank(insta_ctx* ctx, int world_size, int rank, const void* h_id128);
+INSTA_API int insta_comm_destroy(insta_ctx* ctx);
+/* in-place sum over the ranks; insta_train_nerf calls it itself, pre-scaling each rank's loss by 1 / world_size */
+INSTA_API int insta_grad_allreduce(insta_ctx* ctx, void* d_gradients_f16, uint64_t n_halves, insta_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host-buffer convenience (the end-to-end path a caller without device buffers uses): H2D of the records, stage 1,

@@ -67,6 +67,27 @@ class Optimizer(C.Structure):
                 ("d_first_moments", C.c_void_p), ("d_second_moments", C.c_void_p), ("d_param_steps", C.c_void_p), ("d_params_ema_f16", C.c_void_p)]
 
 
+class TrainerConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("target_batch_size", C.c_uint32), ("rays_per_batch", C.c_uint32), ("snap_to_pixel_centers", C.c_uint32),
+                ("random_bg_color", C.c_uint32), ("penalize_density_alpha", C.c_uint32), ("rng_seed", C.c_uint64), ("cone_angle_constant", C.c_float),
+                ("loss_scale", C.c_float), ("background_color", C.c_float * 3), ("depth_weight", C.c_float), ("seg_weight", C.c_float),
+                ("near_distance", C.c_float), ("beta_loss", C.c_float)]
+
+
+class TrainStats(C.Structure):
+    _fields_ = [("training_step", C.c_uint32), ("n_rays", C.c_uint32), ("n_rays_accepted", C.c_uint32), ("rays_per_batch", C.c_uint32), ("n_rays_total", C.c_uint32),
+                ("measured_batch_size", C.c_uint32), ("measured_batch_size_before_compaction", C.c_uint32), ("loss", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class DensityGrid(C.Structure):
+    _fields_ = [("d_density_grid", C.c_void_p), ("d_density_grid_bitfield", C.c_void_p), ("d_density_grid_mean", C.c_void_p), ("n_cascades", C.c_uint32),
+                ("ema_step", C.c_uint32), ("rng_seed", C.c_uint64), ("rng_advances", C.c_uint64), ("decay", C.c_float), ("training_step", C.c_uint32),
+                ("has_rays", C.c_uint32), ("images_changed", C.c_uint32)]
+
+
 class RenderStats(C.Structure):
     _fields_ = [("iterations", C.c_uint32), ("reserved_", C.c_uint32), ("samples", C.c_uint64)]
 
@@ -100,8 +121,11 @@ EXPORTS = [
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
-    "insta_network_n_params", "insta_network_inference", "insta_network_forward_backward", "insta_training_set_images", "insta_generate_training_samples", "insta_compute_loss",
+    "insta_network_n_params", "insta_network_inference", "insta_network_density", "insta_network_forward_backward", "insta_training_set_images", "insta_generate_training_samples", "insta_compute_loss",
     "insta_optimizer_step",
+    "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
+    "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
+    "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
 
@@ -127,6 +151,7 @@ def load_library(build_if_missing=True):
     lib.insta_network_n_params.restype = C.c_uint32
     lib.insta_ctx_destroy.restype = None
     lib.insta_params_default.restype = None
+    lib.insta_trainer_config_default.restype = None
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the .so lost a symbol
     _lib = lib
@@ -344,6 +369,81 @@ class Context:
         o.d_first_moments, o.d_second_moments, o.d_param_steps, o.d_params_ema_f16 = m1.data_ptr(), m2.data_ptr(), steps.data_ptr(), ema16.data_ptr()
         self._check(self.lib.insta_optimizer_step(self.h, C.byref(o), _stream(stream)))
 
+    def make_optimizer(self, current_step, params32, params16, grads16, m1, m2, steps, ema16, lr=0.00175, beta1=0.9, beta2=0.99, eps=1e-15, l2_reg=1e-6,
+                       ema_decay=0.95, loss_scale=128.0):
+        o = Optimizer()
+        o.learning_rate, o.beta1, o.beta2, o.epsilon, o.l2_reg, o.ema_decay, o.loss_scale, o.current_step = lr, beta1, beta2, eps, l2_reg, ema_decay, loss_scale, current_step
+        o.d_params_fp32, o.d_params_f16, o.d_gradients_f16 = params32.data_ptr(), params16.data_ptr(), grads16.data_ptr()
+        o.d_first_moments, o.d_second_moments, o.d_param_steps, o.d_params_ema_f16 = m1.data_ptr(), m2.data_ptr(), steps.data_ptr(), ema16.data_ptr()
+        o._keep = (params32, params16, grads16, m1, m2, steps, ema16)
+        return o
+
+    def trainer_create(self, **overrides):
+        """Testbed::train_nerf state + workspace; keyword overrides are insta_trainer_config fields."""
+        c = TrainerConfig()
+        self.lib.insta_trainer_config_default(C.byref(c))
+        for k, v in overrides.items():
+            if k == "background_color":
+                for i in range(3):
+                    c.background_color[i] = v[i]
+            else:
+                if not hasattr(c, k):
+                    raise AttributeError(k)
+                setattr(c, k, v)
+        self._check(self.lib.insta_trainer_create(self.h, C.byref(c)))
+        return c
+
+    def trainer_destroy(self):
+        self._check(self.lib.insta_trainer_destroy(self.h))
+
+    def trainer_state(self):
+        st = TrainStats()
+        self._check(self.lib.insta_trainer_state(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def train_nerf(self, opt, bitfield, extra_dims, mean_density, get_loss_scalar=False, stream=None):
+        """One full training step (insta_train_nerf); opt from make_optimizer (its current_step is advanced here)."""
+        st = TrainStats()
+        self._check(self.lib.insta_train_nerf(self.h, C.byref(opt), _dev(bitfield), _dev(extra_dims), _dev(mean_density), C.c_int(int(get_loss_scalar)),
+                                              C.byref(st), _stream(stream)))
+        opt.current_step += 1
+        return st.as_dict()
+
+    # ---- occupancy grid ----
+    def make_density_grid(self, grid, bitfield, mean, n_cascades=1, rng_seed=0, decay=0.95, has_rays=False):
+        """grid float32 [128^3 * n_cascades], bitfield uint8 [2 MiB], mean float32 [1] (torch tensors, kept alive by the struct)."""
+        g = DensityGrid()
+        g.d_density_grid, g.d_density_grid_bitfield, g.d_density_grid_mean = grid.data_ptr(), bitfield.data_ptr(), mean.data_ptr()
+        g.n_cascades, g.ema_step, g.rng_seed, g.rng_advances, g.decay, g.training_step, g.has_rays, g.images_changed = n_cascades, 0, rng_seed, 0, decay, 0, int(has_rays), 0
+        g._keep = (grid, bitfield, mean)
+        return g
+
+    def update_density_grid(self, g, params, n_uniform, n_nonuniform, stream=None):
+        self._check(self.lib.insta_update_density_grid(self.h, C.byref(g), _dev(params), C.c_uint32(n_uniform), C.c_uint32(n_nonuniform), _stream(stream)))
+
+    def training_prep_nerf(self, g, params, stream=None):
+        did = C.c_int(0)
+        self._check(self.lib.insta_training_prep_nerf(self.h, C.byref(g), _dev(params), C.byref(did), _stream(stream)))
+        return bool(did.value)
+
+    def update_density_grid_mean_and_bitfield(self, g, stream=None):
+        self._check(self.lib.insta_update_density_grid_mean_and_bitfield(self.h, C.byref(g), _stream(stream)))
+
+    # ---- data-parallel gradient exchange ----
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._check(self.lib.insta_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init_rank(self, world_size, rank, unique_id):
+        self._check(self.lib.insta_comm_init_rank(self.h, C.c_int(world_size), C.c_int(rank), C.c_char_p(unique_id) if unique_id is not None else None))
+
+    def comm_destroy(self):
+        self._check(self.lib.insta_comm_destroy(self.h))
+
+    def grad_allreduce(self, grads16, stream=None):
+        self._check(self.lib.insta_grad_allreduce(self.h, _dev(grads16), C.c_uint64(grads16.numel()), _stream(stream)))
+
     # ---- network ----
     @property
     def network_n_params(self):
@@ -355,6 +455,11 @@ class Context:
         self._check(self.lib.insta_network_inference(self.h, _dev(records), C.c_uint32(records.shape[1]), C.c_uint32(n), _dev(params), _dev(out),
                                                      C.c_uint32(out_stride), _stream(stream)))
         return out
+
+    def network_density(self, xyz, params, logits, stream=None):
+        """xyz float32 [n, stride>=3]; logits fp16 [n]."""
+        self._check(self.lib.insta_network_density(self.h, _dev(xyz), C.c_uint32(xyz.shape[1]), C.c_uint32(xyz.shape[0]), _dev(params), _dev(logits), _stream(stream)))
+        return logits
 
     def network_forward_backward(self, records, params, dloss, grads, out=None, n=None, stream=None):
         """records float32 [n, stride]; dloss fp16 [n, width]; grads fp16 [network_n_params] (overwritten); out fp16 [n, 4] or None."""

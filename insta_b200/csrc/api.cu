@@ -212,6 +212,9 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (ctx->d_counter) cudaFree(ctx->d_counter);
 	tracer_destroy(ctx);
 	network_bwd_destroy(ctx);
+	trainer_destroy(ctx);
+	comm_destroy(ctx);
+	occupancy_destroy(ctx);
 	if (ctx->d_train_images) cudaFree(ctx->d_train_images);
 	for (int k = 0; k < 2; ++k) {
 		if (ctx->d_stage_rec[k]) cudaFree(ctx->d_stage_rec[k]);
@@ -489,6 +492,116 @@ int insta_optimizer_step(insta_ctx* ctx, const insta_optimizer* o, insta_stream 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+void insta_trainer_config_default(insta_trainer_config* c) {
+	if (!c) return;
+	std::memset(c, 0, sizeof(*c));
+	c->struct_size = sizeof(*c);
+	c->target_batch_size = 1u << 18;
+	c->rays_per_batch = 1u << 12;
+	c->snap_to_pixel_centers = 1;
+	c->random_bg_color = 1;
+	c->penalize_density_alpha = 0;
+	c->rng_seed = 1337;
+	c->cone_angle_constant = 0.f;
+	c->loss_scale = 128.f;
+	c->depth_weight = 0.f;
+	c->seg_weight = 0.f;
+	c->near_distance = 0.2f;
+	c->beta_loss = 0.f;
+}
+
+int insta_trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
+	if (!ctx || !cfg || cfg->struct_size != sizeof(insta_trainer_config)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_trainer_create: bad arguments / struct_size");
+	if (cfg->target_batch_size == 0 || cfg->target_batch_size % 128 || cfg->target_batch_size > (1u << 20)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_trainer_create: target_batch_size must be a multiple of 128, at most 2^20");
+	if (!(cfg->loss_scale > 0.f)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_trainer_create: loss_scale must be positive");
+	if (ctx->p.n_levels != 16 || ctx->p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "insta_trainer_create: the density MLP expects 16 levels x 8 features");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	return trainer_create(ctx, cfg);
+}
+
+int insta_trainer_destroy(insta_ctx* ctx) {
+	if (!ctx) INSTA_FAIL(INSTA_ERR_INVALID, "insta_trainer_destroy: null context");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	INSTA_CUDA(cudaDeviceSynchronize());
+	trainer_destroy(ctx);
+	return INSTA_OK;
+}
+
+int insta_trainer_state(const insta_ctx* ctx, insta_train_stats* h_stats) {
+	if (!ctx || !h_stats) INSTA_FAIL(INSTA_ERR_INVALID, "insta_trainer_state: bad arguments");
+	return trainer_state(ctx, h_stats);
+}
+
+int insta_train_nerf(insta_ctx* ctx, const insta_optimizer* o, const void* d_bitfield, const float* d_extra_dims, const float* d_mean_density, int get_loss_scalar,
+                     insta_train_stats* h_stats, insta_stream stream) {
+	if (!ctx || !o || !o->d_params_fp32 || !o->d_params_f16 || !o->d_gradients_f16 || !o->d_first_moments || !o->d_second_moments || !o->d_param_steps || !o->d_params_ema_f16)
+		INSTA_FAIL(INSTA_ERR_INVALID, "insta_train_nerf: bad arguments");
+	if (!d_bitfield || !d_mean_density) INSTA_FAIL(INSTA_ERR_INVALID, "insta_train_nerf: density grid bitfield / mean are required");
+	if (ctx->n_train_images == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_train_nerf: no training images (insta_training_set_images)");
+	if (ctx->frames.empty()) INSTA_FAIL(INSTA_ERR_INVALID, "insta_train_nerf: no frames loaded");
+	if (reinterpret_cast<uintptr_t>(o->d_params_f16) % 16u || reinterpret_cast<uintptr_t>(o->d_gradients_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_train_nerf: parameters / gradients must be 16-byte aligned");
+	return train_nerf(ctx, o, d_bitfield, d_extra_dims, d_mean_density, get_loss_scalar, h_stats, (cudaStream_t)stream);
+}
+
+static int check_grid(const insta_ctx* ctx, const insta_density_grid* g, const char* who) {
+	if (!ctx || !g || !g->d_density_grid || !g->d_density_grid_bitfield || !g->d_density_grid_mean) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": bad arguments");
+	if (g->n_cascades < 1 || g->n_cascades > 8) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": n_cascades must be 1..8");
+	if (reinterpret_cast<uintptr_t>(g->d_density_grid) % 16u || reinterpret_cast<uintptr_t>(g->d_density_grid_bitfield) % 8u) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": grid buffers must be 16-byte aligned");
+	return INSTA_OK;
+}
+
+int insta_update_density_grid(insta_ctx* ctx, insta_density_grid* g, const void* d_params_f16, uint32_t n_uniform, uint32_t n_nonuniform, insta_stream stream) {
+	int rc = check_grid(ctx, g, "insta_update_density_grid");
+	if (rc) return rc;
+	if (!d_params_f16 || reinterpret_cast<uintptr_t>(d_params_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_update_density_grid: parameters must be non-null and 16-byte aligned");
+	if (ctx->p.n_levels != 16 || ctx->p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "insta_update_density_grid: the density MLP expects 16 levels x 8 features");
+	if ((uint64_t)n_uniform + n_nonuniform > (1ull << 27)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_update_density_grid: too many samples");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	return density_grid_update(ctx, g, d_params_f16, n_uniform, n_nonuniform, (cudaStream_t)stream);
+}
+
+int insta_training_prep_nerf(insta_ctx* ctx, insta_density_grid* g, const void* d_params_f16, int* did_update, insta_stream stream) {
+	if (did_update) *did_update = 0;
+	int rc = check_grid(ctx, g, "insta_training_prep_nerf");
+	if (rc) return rc;
+	const uint32_t n_prep_to_skip = std::min(std::max(g->training_step / 16u, 1u), 16u);
+	if (g->training_step % n_prep_to_skip != 0) return INSTA_OK;
+	const uint32_t cells = 128u * 128u * 128u * g->n_cascades;
+	if (g->training_step < 256) rc = insta_update_density_grid(ctx, g, d_params_f16, cells, 0, stream);
+	else rc = insta_update_density_grid(ctx, g, d_params_f16, cells / 4, cells / 4, stream);
+	if (rc == INSTA_OK && did_update) *did_update = 1;
+	return rc;
+}
+
+int insta_update_density_grid_mean_and_bitfield(insta_ctx* ctx, const insta_density_grid* g, insta_stream stream) {
+	int rc = check_grid(ctx, g, "insta_update_density_grid_mean_and_bitfield");
+	if (rc) return rc;
+	return density_grid_mean_and_bitfield(ctx, g, (cudaStream_t)stream);
+}
+
+int insta_comm_unique_id(void* h_id128) {
+	if (!h_id128) INSTA_FAIL(INSTA_ERR_INVALID, "insta_comm_unique_id: null buffer");
+	return comm_unique_id(h_id128);
+}
+
+int insta_comm_init_rank(insta_ctx* ctx, int world_size, int rank, const void* h_id128) {
+	if (!ctx || world_size < 1 || rank < 0 || rank >= world_size || (world_size > 1 && !h_id128)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_comm_init_rank: bad arguments");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	return comm_init(ctx, world_size, rank, h_id128);
+}
+
+int insta_comm_destroy(insta_ctx* ctx) {
+	if (!ctx) INSTA_FAIL(INSTA_ERR_INVALID, "insta_comm_destroy: null context");
+	comm_destroy(ctx);
+	return INSTA_OK;
+}
+
+int insta_grad_allreduce(insta_ctx* ctx, void* d_gradients_f16, uint64_t n_halves, insta_stream stream) {
+	if (!ctx || (!d_gradients_f16 && n_halves)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_grad_allreduce: bad arguments");
+	return grad_allreduce(ctx, d_gradients_f16, n_halves, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 uint32_t insta_network_n_params(const insta_ctx* ctx) { return ctx ? network_n_params(ctx) : 0; }
 
 int insta_network_inference(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_out_f16,
@@ -499,6 +612,14 @@ int insta_network_inference(insta_ctx* ctx, const float* d_records, uint32_t str
 	if (ctx->p.n_levels != 16 || ctx->p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: the density MLP expects 16 levels x 8 features");
 	if (out_stride_elems != 0 && out_stride_elems < n) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: out_stride_elems < n");
 	return launch_network_fwd(ctx, d_records, stride_floats, n, d_params_f16, d_out_f16, out_stride_elems, (cudaStream_t)stream);
+}
+
+int insta_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_logits_f16, insta_stream stream) {
+	if (!ctx || ((!d_xyz || !d_params_f16 || !d_logits_f16) && n)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_density: bad arguments");
+	if (stride_floats < 3) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_density: stride smaller than a position");
+	if (reinterpret_cast<uintptr_t>(d_params_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_density: parameters must be 16-byte aligned");
+	if (ctx->p.n_levels != 16 || ctx->p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_density: the density MLP expects 16 levels x 8 features");
+	return launch_network_density(ctx, d_xyz, stride_floats, n, d_params_f16, d_logits_f16, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -102,6 +102,19 @@ struct GridLevels {
 	float scale[kMaxLevels];
 };
 
+// One training image on the device (ngp::TrainingImageMetadata + TrainingXForm, ngp nerf_loader.h:48-64)
+struct ImageDev {
+	const void* pixels;
+	const void* seg;
+	const float* depth;
+	const float* rays;  // 6 floats per pixel (origin, unnormalised direction) or null
+	uint32_t res[2];
+	float focal[2], pp[2];
+	float xform[12];
+	uint32_t type;  // EImageDataType: 1 = Byte, 2 = Half, 3 = Float (ngp common.h)
+	uint32_t pad;
+};
+
 }  // namespace insta
 
 struct insta_ctx {
@@ -151,6 +164,9 @@ struct insta_ctx {
 	void* bwd_scratch = nullptr;      // insta::BwdScratch (mlp_bwd.cu)
 	void* d_train_images = nullptr;   // insta::ImageDev[n_train_images] (train.cu)
 	uint32_t n_train_images = 0;
+	void* trainer = nullptr;          // insta::Trainer (trainer.cu)
+	void* comm = nullptr;             // insta::Comm (trainer.cu)
+	void* occ_scratch = nullptr;      // insta::OccScratch (occupancy.cu)
 	insta_render_opts render_opts{};  // last options given to insta_tracer_init_rays
 };
 
@@ -158,7 +174,7 @@ namespace insta {
 // deform.cu
 int launch_build_xf(insta_ctx* ctx, const float* d_verts, TriXf* d_xf, const float* d_canon_area, float* d_area_out, cudaStream_t s);
 int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, int32_t frame_id, const int32_t* d_frame_ids,
-                  bool random_frames, int32_t* d_tri_ids, cudaStream_t s);
+                  bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr);
 // hashgrid.cu
 int init_grid_levels(insta_ctx* ctx);
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s);
@@ -168,17 +184,36 @@ int launch_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint3
 int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
 // mlp.cu
 uint32_t network_n_params(const insta_ctx* ctx);
-int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s);
+int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s,
+                       const uint32_t* d_n = nullptr);
 // mlp_bwd.cu
 void network_bwd_destroy(insta_ctx* ctx);
 int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,
                            void* d_grads, void* d_out, cudaStream_t s);
 // train.cu
+void pcg_seed(uint64_t seed, uint64_t advance_steps, uint64_t& state, uint64_t& inc);  // pcg32{seed} advanced `advance_steps` x advance()
 int training_set_images(insta_ctx* ctx, const insta_train_image* h, uint32_t n);
 int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s);
 int train_loss(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out, uint32_t out_width, float* d_coords_compacted, void* d_dloss, float* d_loss,
                const float* d_mean_density, cudaStream_t s);
 int optimizer_step(insta_ctx* ctx, const insta_optimizer* o, uint32_t n_params, uint32_t n_matrix, cudaStream_t s);
+int launch_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride, uint32_t n, const void* d_params, void* d_logits_f16, cudaStream_t s);
+// occupancy.cu
+void occupancy_destroy(insta_ctx* ctx);
+int density_grid_update(insta_ctx* ctx, insta_density_grid* g, const void* d_params_f16, uint32_t n_uniform, uint32_t n_nonuniform, cudaStream_t s);
+int density_grid_mean_and_bitfield(insta_ctx* ctx, const insta_density_grid* g, cudaStream_t s);
+// trainer.cu
+void trainer_rng_advance(insta_ctx* ctx);
+void trainer_destroy(insta_ctx* ctx);
+void comm_destroy(insta_ctx* ctx);
+int comm_unique_id(void* h_id128);
+int comm_init(insta_ctx* ctx, int world, int rank, const void* h_id128);
+int comm_world(const insta_ctx* ctx);
+int grad_allreduce(insta_ctx* ctx, void* d_grads_f16, uint64_t n, cudaStream_t s);
+int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg);
+int trainer_state(const insta_ctx* ctx, insta_train_stats* out);
+int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfield, const float* d_extra_dims, const float* d_mean_density, int get_loss_scalar,
+               insta_train_stats* h_stats, cudaStream_t s);
 // nerf.cu
 void tracer_destroy(insta_ctx* ctx);
 int tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, float* d_frame_rgba, float* d_frame_depth, float* d_dbg_origin_t,

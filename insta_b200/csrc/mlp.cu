@@ -144,6 +144,8 @@ struct NetArgs {
 	const __half* params;   // MLP weights then the grid table
 	__half* out;
 	uint32_t out_stride;    // 0: 4 halves per sample; else out[i + c * out_stride]
+	const uint32_t* n_ptr;  // nullable: device-side count, only min(n, *n_ptr) samples are evaluated
+	uint32_t density_only;  // NerfNetwork::density: records are bare positions, expression inputs = 1, out = one density logit per sample
 	GridLevels L;
 };
 
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 	const uint32_t bar_full0 = sbase + kSmBar, bar_empty0 = sbase + kSmBar + 16, bar_mma = sbase + kSmBar + 32;
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 40);
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-	const uint32_t n_tiles = (a.n + kTileM - 1) / kTileM;
+	const uint32_t n_samples = a.n_ptr ? min(a.n, __ldg(a.n_ptr)) : a.n;
+	const uint32_t n_tiles = (n_samples + kTileM - 1) / kTileM;
 
 	// ---- one-time setup: weights, barriers, tensor memory ----
 	stage_weights(smem + kSmW1, a.params + kOffW1, kWidth, kInDensity);
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 			mbar_wait(bar_empty0 + 8 * b, ((it >> 1) & 1u) ^ 1u);
 			unsigned char* A0 = smem + kSmA0 + b * kBytesA0 + (row >> 3) * 128 + (row & 7) * 16;
 			const uint32_t i = tile * kTileM + row;
-			if (i < a.n) {
+			if (i < n_samples) {
 				const float* rec = a.records + (size_t)i * a.stride;
 				const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
 #pragma unroll 2
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 #pragma unroll
 				for (uint32_t k = 0; k < 8; ++k) {
 					const uint32_t d = half_id * 8 + k;
-					ex[k] = d < a.n_extra ? __ldg(rec + a.stride - a.n_extra + d) : 0.0f;
+					ex[k] = d < a.n_extra ? (a.density_only ? 1.0f : __ldg(rec + a.stride - a.n_extra + d)) : 0.0f;
 				}
 				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = make_uint4(pack2(ex[0], ex[1]), pack2(ex[2], ex[3]), pack2(ex[4], ex[5]), pack2(ex[6], ex[7]));
 			} else {
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 			const uint32_t i = tile * kTileM + row;
 			// SH of the view direction while the first GEMM is in flight
 			float dx = 0.5f, dy = 0.5f, dz = 0.5f;
-			if (i < a.n) {
+			if (i < n_samples && !a.density_only) {
 				const float* rec = a.records + (size_t)i * a.stride;
 				dx = __ldg(rec + 8); dy = __ldg(rec + 9); dz = __ldg(rec + 10);
 			}
@@ -299,9 +302,11 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 			float o[16];
 			tmem_ld16(taddr, o);
 			tc_fence_before();
-			if (i < a.n) {
+			if (i < n_samples) {
 				const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], sigma);
-				if (a.out_stride == 0) {
+				if (a.density_only) {
+					a.out[i] = __high2half(bs);
+				} else if (a.out_stride == 0) {
 					*reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
 				} else {
 					a.out[i] = __low2half(rg);
@@ -324,7 +329,8 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 
 uint32_t network_n_params(const insta_ctx* ctx) { return kOffGrid + ctx->levels.offset[ctx->levels.n_levels] * 8u; }
 
-int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s) {
+int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s,
+                       const uint32_t* d_n) {
 	if (n == 0) return INSTA_OK;
 	NetArgs a{};
 	a.records = d_records;
@@ -334,12 +340,38 @@ int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, 
 	a.params = (const __half*)d_params;
 	a.out = (__half*)d_out;
 	a.out_stride = out_stride;
+	a.n_ptr = d_n;
 	a.L = ctx->levels;
 	if (a.n_extra > 16) INSTA_FAIL(INSTA_ERR_INVALID, "network: more than 16 extra dims are not supported by the density MLP input (144 = 128 + 16)");
 	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
 	const uint32_t n_tiles = (n + kTileM - 1) / kTileM;
 	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
 	nerf_network_fwd_kernel<<<grid, kNetThreads, kSmTotal, s>>>(a);
+	ctx->launches++;
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+// NerfNetwork::density (ngp nerf_network.h:385-414): hash grid + expression rows (all 1, extract_expressions_random) + density MLP; the first
+// output of the density MLP is the density logit.  Runs the same fused kernel (the colour MLP's result is dropped; the kernel is bound by the
+// grid gathers, not by the GEMMs).
+int launch_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride, uint32_t n, const void* d_params, void* d_logits, cudaStream_t s) {
+	if (n == 0) return INSTA_OK;
+	NetArgs a{};
+	a.records = d_xyz;
+	a.stride = stride;
+	a.n = n;
+	a.n_extra = ctx->p.exp_params + ctx->p.geo_params;
+	a.params = (const __half*)d_params;
+	a.out = (__half*)d_logits;
+	a.out_stride = 0;
+	a.n_ptr = nullptr;
+	a.density_only = 1;
+	a.L = ctx->levels;
+	if (a.n_extra > 16) INSTA_FAIL(INSTA_ERR_INVALID, "network: more than 16 extra dims are not supported by the density MLP input (144 = 128 + 16)");
+	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+	const uint32_t n_tiles = (n + kTileM - 1) / kTileM;
+	nerf_network_fwd_kernel<<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), kNetThreads, kSmTotal, s>>>(a);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;

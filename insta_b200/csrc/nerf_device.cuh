@@ -10,6 +10,32 @@
 namespace insta {
 namespace nerfdev {
 
+// pcg32 (tcnn pcg32.h): the generator every reference kernel draws from
+struct Pcg32 {
+	uint64_t state, inc;
+	__device__ __forceinline__ uint32_t next_uint() {
+		const uint64_t old = state;
+		state = old * 0x5851f42d4c957f2dULL + inc;
+		const uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+		const uint32_t rot = (uint32_t)(old >> 59u);
+		return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+	}
+	__device__ __forceinline__ float next_float() { return __uint_as_float((next_uint() >> 9) | 0x3f800000u) - 1.0f; }
+	__device__ __forceinline__ void advance(uint64_t delta) {
+		uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+		while (delta > 0) {
+			if (delta & 1) {
+				acc_mult *= cur_mult;
+				acc_plus = acc_plus * cur_mult + cur_plus;
+			}
+			cur_plus = (cur_mult + 1) * cur_plus;
+			cur_mult *= cur_mult;
+			delta >>= 1;
+		}
+		state = acc_mult * state + acc_plus;
+	}
+};
+
 constexpr uint32_t kGrid = 128;        // NERF_GRIDSIZE (ngp nerf.h:24-26)
 constexpr uint32_t kNerfSteps = 1024;  // NERF_STEPS
 constexpr uint32_t kCascades = 8;      // NERF_CASCADES

@@ -27,43 +27,6 @@ namespace insta {
 namespace {
 using namespace nerfdev;
 
-struct Pcg32 {
-	uint64_t state, inc;
-	__device__ __forceinline__ uint32_t next_uint() {
-		const uint64_t old = state;
-		state = old * 0x5851f42d4c957f2dULL + inc;
-		const uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u);
-		const uint32_t rot = (uint32_t)(old >> 59u);
-		return (xs >> rot) | (xs << ((~rot + 1u) & 31));
-	}
-	__device__ __forceinline__ float next_float() { return __uint_as_float((next_uint() >> 9) | 0x3f800000u) - 1.0f; }
-	__device__ __forceinline__ void advance(uint64_t delta) {
-		uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
-		while (delta > 0) {
-			if (delta & 1) {
-				acc_mult *= cur_mult;
-				acc_plus = acc_plus * cur_mult + cur_plus;
-			}
-			cur_plus = (cur_mult + 1) * cur_plus;
-			cur_mult *= cur_mult;
-			delta >>= 1;
-		}
-		state = acc_mult * state + acc_plus;
-	}
-};
-
-struct ImageDev {
-	const void* pixels;
-	const void* seg;
-	const float* depth;
-	const float* rays;  // 6 floats per pixel (origin, unnormalised direction) or null
-	uint32_t res[2];
-	float focal[2], pp[2];
-	float xform[12];
-	uint32_t type;  // EImageDataType: 1 = Byte, 2 = Half, 3 = Float (ngp common.h)
-	uint32_t pad;
-};
-
 __device__ __forceinline__ float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : powf((s + 0.055f) / 1.055f, 2.4f); }
 __device__ __forceinline__ float linear_to_srgb(float l) { return l < 0.0031308f ? 12.92f * l : 1.055f * powf(l, 0.41666f) - 0.055f; }
 
@@ -455,7 +418,7 @@ int training_set_images(insta_ctx* ctx, const insta_train_image* h, uint32_t n) 
 	return INSTA_OK;
 }
 
-static void pcg_seed(uint64_t seed, uint64_t advance_steps, uint64_t& state, uint64_t& inc) {
+void pcg_seed(uint64_t seed, uint64_t advance_steps, uint64_t& state, uint64_t& inc) {
 	// pcg32(seed): state = 0; inc = 3; next; state += seed; next   (tcnn pcg32.h:57-63), then `advance_steps` x advance()
 	const uint64_t mult = 0x5851f42d4c957f2dULL;
 	inc = 3;

@@ -1,0 +1,340 @@
+// One full training step behind the C ABI: ngp::Testbed::train_nerf / train_nerf_step (ngp/src/testbed_nerf.cu:2916-2992, 3170-3426)
+// + tcnn::Trainer::optimizer_step (tcnn trainer.h:113-131), with rta::Core::surface_closest_point hooked in between sample generation and
+// the network (testbed_nerf.cu:3290).  The gradient exchange of a data-parallel run sits between backward and the optimizer
+// step and is the only collective of the path: ncclAllReduce(sum, fp16) over the gradient buffer on the caller's stream.
+//
+// B200-first differences to the reference's step (results for the records the loss reads are unchanged):
+//   * the reference deforms and evaluates `max_inference` records (last step's sample count rounded up, 16 x batch on the first step) and
+//     needs a host round trip to learn the real count.  Here the deformation and inference kernels read the generator's sample counter on
+//     the device (`n_ptr`), so exactly the generated samples are processed, with no host synchronisation before the loss.
+//   * the workspace the reference carves out of the tcnn arena every step (testbed_nerf.cu:3175-3202) is allocated once per trainer.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "ctx.h"
+
+namespace insta {
+
+// ---- NCCL through dlopen: libinsta_b200.so must load on a machine without NCCL (single-GPU callers) -------------------------------------
+namespace {
+struct NcclId { char internal[128]; };  // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
+typedef void* NcclComm;
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetUniqueId)(NcclId*) = nullptr;
+	int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+	int (*CommDestroy)(NcclComm) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclHalf = 6, kNcclFloat = 7, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+NcclApi* nccl_api(std::string& err) {
+	static NcclApi api;
+	static bool tried = false;
+	static std::string load_err;
+	if (!tried) {
+		tried = true;
+		// a process that already imported torch has its bundled libnccl.so.2 loaded: the soname lookup returns that copy
+		for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+			api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if (api.lib) break;
+		}
+		if (!api.lib) {
+			load_err = std::string("NCCL not found: ") + dlerror();
+		} else {
+			api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+			api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+			api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+			api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+			api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+			if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) {
+				load_err = "NCCL library lacks a required symbol";
+				api.lib = nullptr;
+			}
+		}
+	}
+	if (!api.lib) {
+		err = load_err;
+		return nullptr;
+	}
+	return &api;
+}
+}  // namespace
+
+struct Comm {
+	NcclComm comm = nullptr;
+	int rank = 0, world = 1;
+};
+
+struct Trainer {
+	insta_trainer_config cfg{};
+	// workspace of train_nerf_step (testbed_nerf.cu:3175-3202)
+	uint32_t* ray_indices = nullptr;
+	float* rays = nullptr;
+	uint32_t* numsteps = nullptr;
+	float* coords = nullptr;
+	void* mlp_out = nullptr;
+	void* dloss = nullptr;
+	float* coords_compacted = nullptr;
+	uint32_t* counters = nullptr;   // [0] rays accepted, [1] samples generated, [2] samples after compaction
+	float* loss = nullptr;          // per ray
+	float* loss_sum = nullptr;      // one float
+	uint32_t* h_counters = nullptr; // pinned: 3 counters + loss sum
+	// Testbed::Nerf::Training::Counters (testbed.h:638-650)
+	uint32_t rays_per_batch = 1u << 12;
+	uint32_t n_rays_total = 0;
+	uint32_t measured_batch_size = 0, measured_batch_size_before_compaction = 0;
+	uint64_t rng_advances = 0;
+	uint32_t training_step = 0;
+};
+
+namespace {
+constexpr uint32_t kMaxRays = 1u << 18;   // testbed_nerf.cu:2910
+constexpr uint32_t kGranularity = 128;    // tcnn::batch_size_granularity
+constexpr uint32_t kOutWidth = 4;         // halves per sample of this library's network output (r, g, b, sigma logits)
+
+__global__ void __launch_bounds__(256) loss_sum_kernel(const float* __restrict__ loss, uint32_t n, float* __restrict__ out) {
+	float acc = 0.f;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += loss[i];
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	__shared__ float part[8];
+	if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x < 8) {
+		acc = part[threadIdx.x];
+		for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffu, acc, o);
+		if (threadIdx.x == 0) atomicAdd(out, acc);
+	}
+}
+
+void free_trainer(Trainer* t) {
+	if (!t) return;
+	cudaFree(t->ray_indices); cudaFree(t->rays); cudaFree(t->numsteps); cudaFree(t->coords); cudaFree(t->mlp_out); cudaFree(t->dloss);
+	cudaFree(t->coords_compacted); cudaFree(t->counters); cudaFree(t->loss); cudaFree(t->loss_sum);
+	if (t->h_counters) cudaFreeHost(t->h_counters);
+	delete t;
+}
+}  // namespace
+
+void trainer_destroy(insta_ctx* ctx) {
+	free_trainer((Trainer*)ctx->trainer);
+	ctx->trainer = nullptr;
+}
+
+void comm_destroy(insta_ctx* ctx) {
+	Comm* c = (Comm*)ctx->comm;
+	if (!c) return;
+	std::string err;
+	if (c->comm)
+		if (NcclApi* api = nccl_api(err)) api->CommDestroy(c->comm);
+	delete c;
+	ctx->comm = nullptr;
+}
+
+int comm_unique_id(void* h_id128) {
+	std::string err;
+	NcclApi* api = nccl_api(err);
+	if (!api) INSTA_FAIL(INSTA_ERR_INVALID, "insta_comm_unique_id: " + err);
+	NcclId id;
+	const int rc = api->GetUniqueId(&id);
+	if (rc != 0) INSTA_FAIL(INSTA_ERR_CUDA, std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+	std::memcpy(h_id128, &id, sizeof(id));
+	return INSTA_OK;
+}
+
+int comm_init(insta_ctx* ctx, int world, int rank, const void* h_id128) {
+	comm_destroy(ctx);
+	Comm* c = new Comm();
+	c->rank = rank;
+	c->world = world;
+	if (world > 1) {
+		std::string err;
+		NcclApi* api = nccl_api(err);
+		if (!api) {
+			delete c;
+			INSTA_FAIL(INSTA_ERR_INVALID, "insta_comm_init_rank: " + err);
+		}
+		NcclId id;
+		std::memcpy(&id, h_id128, sizeof(id));
+		const int rc = api->CommInitRank(&c->comm, world, id, rank);
+		if (rc != 0) {
+			delete c;
+			INSTA_FAIL(INSTA_ERR_CUDA, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+		}
+	}
+	ctx->comm = c;
+	return INSTA_OK;
+}
+
+int comm_world(const insta_ctx* ctx) { return ctx->comm ? ((Comm*)ctx->comm)->world : 1; }
+
+int grad_allreduce(insta_ctx* ctx, void* d_grads_f16, uint64_t n, cudaStream_t s) {
+	Comm* c = (Comm*)ctx->comm;
+	if (!c || c->world <= 1) return INSTA_OK;  // a single rank owns the whole batch
+	std::string err;
+	NcclApi* api = nccl_api(err);
+	if (!api) INSTA_FAIL(INSTA_ERR_INVALID, "insta_grad_allreduce: " + err);
+	const int rc = api->AllReduce(d_grads_f16, d_grads_f16, (size_t)n, kNcclHalf, kNcclSum, c->comm, s);
+	if (rc != 0) INSTA_FAIL(INSTA_ERR_CUDA, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+	return INSTA_OK;
+}
+
+int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
+	INSTA_CUDA(cudaDeviceSynchronize());
+	trainer_destroy(ctx);
+	Trainer* t = new Trainer();
+	t->cfg = *cfg;
+	const uint32_t target = cfg->target_batch_size;
+	const uint32_t max_samples = target * 16;  // "somewhat of a worst case" (testbed_nerf.cu:3172)
+	const uint32_t stride = 11 + ctx->p.exp_params + ctx->p.geo_params;
+	t->rays_per_batch = std::min(std::max(cfg->rays_per_batch, 1u), kMaxRays);
+	auto fail = [&](cudaError_t e) {
+		set_error(std::string("insta_trainer_create: ") + cudaGetErrorString(e));
+		free_trainer(t);
+		return INSTA_ERR_CUDA;
+	};
+	cudaError_t e;
+	if ((e = cudaMalloc(&t->ray_indices, sizeof(uint32_t) * kMaxRays)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->rays, sizeof(float) * 6 * kMaxRays)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->numsteps, sizeof(uint32_t) * 2 * kMaxRays)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->coords, sizeof(float) * (size_t)max_samples * stride)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->mlp_out, 2 * (size_t)max_samples * kOutWidth)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->dloss, 2 * (size_t)target * kOutWidth)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->coords_compacted, sizeof(float) * (size_t)target * stride)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->counters, sizeof(uint32_t) * 4)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->loss, sizeof(float) * kMaxRays)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->loss_sum, sizeof(float))) != cudaSuccess) return fail(e);
+	if ((e = cudaHostAlloc(&t->h_counters, sizeof(uint32_t) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail(e);
+	// the reference's arena memory is not cleared either, but stale records must at least be finite for the first step's kernels
+	if ((e = cudaMemset(t->coords, 0, sizeof(float) * (size_t)max_samples * stride)) != cudaSuccess) return fail(e);
+	ctx->trainer = t;
+	return INSTA_OK;
+}
+
+void trainer_rng_advance(insta_ctx* ctx) {
+	if (Trainer* t = (Trainer*)ctx->trainer) t->rng_advances += 1;
+}
+
+int trainer_state(const insta_ctx* ctx, insta_train_stats* out) {
+	const Trainer* t = (const Trainer*)ctx->trainer;
+	if (!t) INSTA_FAIL(INSTA_ERR_INVALID, "no trainer (insta_trainer_create)");
+	std::memset(out, 0, sizeof(*out));
+	out->training_step = t->training_step;
+	out->rays_per_batch = t->rays_per_batch;
+	out->n_rays_total = t->n_rays_total;
+	out->measured_batch_size = t->measured_batch_size;
+	out->measured_batch_size_before_compaction = t->measured_batch_size_before_compaction;
+	return INSTA_OK;
+}
+
+int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfield, const float* d_extra_dims, const float* d_mean_density, int get_loss_scalar,
+               insta_train_stats* h_stats, cudaStream_t s) {
+	Trainer* t = (Trainer*)ctx->trainer;
+	if (!t) INSTA_FAIL(INSTA_ERR_INVALID, "insta_train_nerf: no trainer (insta_trainer_create)");
+	const insta_trainer_config& c = t->cfg;
+	const uint32_t target = c.target_batch_size;
+	const uint32_t n_rays = t->rays_per_batch;
+	const uint32_t world = (uint32_t)comm_world(ctx);
+	const uint32_t stride = 11 + ctx->p.exp_params + ctx->p.geo_params;
+
+	// Counters::prepare_for_training_steps (testbed_nerf.cu:2880-2887) -- the generator clears the counters itself
+	INSTA_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(float) * n_rays, s));
+
+	insta_train_step st{};
+	st.n_rays = n_rays;
+	st.n_rays_total = t->n_rays_total;
+	// max_inference (testbed_nerf.cu:3217-3222): the generator's capacity is last step's sample count rounded up, the full workspace on step 0
+	st.max_samples = t->measured_batch_size_before_compaction == 0
+	                     ? target * 16
+	                     : (std::min(t->measured_batch_size_before_compaction, target * 16) + kGranularity - 1) / kGranularity * kGranularity;
+	st.target_batch_size = target;
+	st.stride_floats = stride;
+	st.snap_to_pixel_centers = c.snap_to_pixel_centers;
+	st.random_bg_color = c.random_bg_color;
+	st.penalize_density_alpha = c.penalize_density_alpha;
+	st.rng_seed = c.rng_seed;
+	st.rng_advances = t->rng_advances;
+	st.cone_angle_constant = c.cone_angle_constant;
+	// every rank contributes the mean over ITS rays; the summed gradient must be the mean over all ranks (pre-scale by 1/R
+	// so that the fp16 sum cannot overflow where a single rank's gradient would not)
+	st.loss_scale = c.loss_scale / (float)world;
+	for (int k = 0; k < 3; ++k) st.background_color[k] = c.background_color[k];
+	st.depth_weight = c.depth_weight;
+	st.seg_weight = c.seg_weight;
+	st.near_distance = c.near_distance;
+	st.beta_loss = c.beta_loss;
+	st.d_density_grid_bitfield = d_bitfield;
+	st.d_extra_dims = d_extra_dims;
+	st.d_coords = t->coords;
+	st.d_counters = t->counters;
+	st.d_ray_indices = t->ray_indices;
+	st.d_rays = t->rays;
+	st.d_numsteps = t->numsteps;
+	t->n_rays_total += n_rays;  // testbed_nerf.cu:3235
+
+	int rc = train_generate(ctx, &st, s);
+	if (rc) return rc;
+	// rta::Core::surface_closest_point on the generated records (testbed_nerf.cu:3290), then the network on the same records (3292)
+	{
+		std::lock_guard<std::mutex> lock(ctx->mu);
+		rc = sync_frame_table(ctx, s);
+	}
+	if (rc) return rc;
+	rc = launch_deform(ctx, t->coords, st.max_samples, stride, -1, nullptr, false, nullptr, s, t->counters + 1);
+	if (rc) return rc;
+	rc = launch_network_fwd(ctx, t->coords, stride, st.max_samples, opt->d_params_f16, t->mlp_out, 0, s, t->counters + 1);
+	if (rc) return rc;
+	rc = train_loss(ctx, &st, t->mlp_out, kOutWidth, t->coords_compacted, t->dloss, t->loss, d_mean_density, s);
+	if (rc) return rc;
+	// forward + backward on the compacted, rolled-over batch (testbed_nerf.cu:3366-3371)
+	rc = launch_network_fwd_bwd(ctx, t->coords_compacted, stride, target, opt->d_params_f16, t->dloss, kOutWidth, (void*)opt->d_gradients_f16, nullptr, s);
+	if (rc) return rc;
+	t->rng_advances += 1;  // m_rng.advance() (testbed_nerf.cu:3419)
+	// data-parallel exchange step
+	rc = grad_allreduce(ctx, (void*)opt->d_gradients_f16, network_n_params(ctx), s);
+	if (rc) return rc;
+	// Trainer::optimizer_step(stream, LOSS_SCALE) (testbed_nerf.cu:2974)
+	insta_optimizer o = *opt;
+	o.loss_scale = c.loss_scale;
+	rc = optimizer_step(ctx, &o, network_n_params(ctx), 25600u, s);
+	if (rc) return rc;
+	t->training_step += 1;
+
+	// Counters::update_after_training (testbed_nerf.cu:2889-2914): one read-back per step, as in the reference
+	if (get_loss_scalar) {
+		INSTA_CUDA(cudaMemsetAsync(t->loss_sum, 0, sizeof(float), s));
+		loss_sum_kernel<<<std::min<uint32_t>((n_rays + 255) / 256, 148u), 256, 0, s>>>(t->loss, n_rays, t->loss_sum);
+		ctx->launches++;
+		INSTA_CUDA(cudaMemcpyAsync(t->h_counters + 3, t->loss_sum, sizeof(float), cudaMemcpyDeviceToHost, s));
+	}
+	INSTA_CUDA(cudaMemcpyAsync(t->h_counters, t->counters, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, s));
+	INSTA_CUDA(cudaStreamSynchronize(s));
+	const uint32_t generated = t->h_counters[1], compacted = t->h_counters[2];
+	float loss_scalar = 0.f;
+	t->measured_batch_size = t->measured_batch_size_before_compaction = 0;
+	if (generated != 0 && compacted != 0) {
+		t->measured_batch_size_before_compaction = generated;
+		t->measured_batch_size = compacted;
+		if (get_loss_scalar) {
+			float sum;
+			std::memcpy(&sum, t->h_counters + 3, sizeof(float));
+			loss_scalar = sum * (float)compacted / (float)target;
+		}
+		uint32_t r = (uint32_t)((float)t->rays_per_batch * (float)target / (float)compacted);
+		r = (r + kGranularity - 1) / kGranularity * kGranularity;
+		t->rays_per_batch = std::min(r, kMaxRays);
+	}
+	if (h_stats) {
+		trainer_state(ctx, h_stats);
+		h_stats->n_rays = n_rays;
+		h_stats->n_rays_accepted = t->h_counters[0];
+		h_stats->loss = loss_scalar;
+	}
+	return INSTA_OK;
+}
+
+}  // namespace insta

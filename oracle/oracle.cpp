@@ -549,6 +549,13 @@ void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const 
 // out8 = {expands, inner entries dropped at pop, leaf visits, triangle tests, leaf visits whose box distance exceeded
 //         `best` at pop (would be skippable), stack high-water mark, queries, 0}
 void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, double* out8) {
+	orc_closest_stats_bounded(pts, n, nodes, tris, nullptr, out8);
+}
+
+// Same traversal started from an initial upper bound per query (init_best[q] >= the true minimum, e.g. the distance to a
+// candidate triangle).  Pruned subtrees cannot hold the winner and the relative visit order of the rest is unchanged, so the
+// winner (last visited among the tied minima, bvh.cuh:82-85) is the reference's.  Diagnostic for the cost model in DESIGN.md.
+void orc_closest_stats_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, double* out8) {
 	double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	for (int q = 0; q < n; ++q) {
 		V3 p = v3(pts + 3 * q);
@@ -556,7 +563,7 @@ void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc
 		float sd[64];
 		int sp = 0;
 		stack[sp] = 0; sd[sp] = 0.f; ++sp;
-		float best = std::numeric_limits<float>::max();
+		float best = init_best ? init_best[q] : std::numeric_limits<float>::max();
 		while (sp > 0) {
 			--sp;
 			int idx = stack[sp];

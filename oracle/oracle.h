@@ -53,6 +53,7 @@ void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const 
                           int n_threads);
 /* diagnostic: traversal statistics (see oracle.cpp) */
 void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, double* out8);
+void orc_closest_stats_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, double* out8);
 float orc_triangle_distance_sq(const orc_tri* t, const float* p);
 float orc_bbox_distance_sq(const float* mn, const float* mx, const float* p);
 void orc_tri2projection(const orc_tri* t, float* out16_colmajor);

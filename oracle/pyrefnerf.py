@@ -101,3 +101,23 @@ class RefNerf:
                                          C.c_void_p(mean_density.data_ptr()), C.c_float(depth_lambda), C.c_float(seg_lambda), C.c_float(near_distance),
                                          C.c_int(int(penalize_density)), C.c_float(beta), self._s())
         assert rc == 0, rc
+
+    # ---- occupancy-grid maintenance kernels ----
+    def grid_mark_untrained(self, grid, clear_visible):
+        rc = self.lib.refnerf_grid_mark_untrained(C.c_uint32(grid.numel()), C.c_void_p(grid.data_ptr()), C.c_int(int(clear_visible)), self._s())
+        assert rc == 0, rc
+
+    def grid_generate(self, n, rng_seed, rng_advances, step, aabb, grid, positions, indices, n_cascades, thresh):
+        a = (C.c_float * 6)(*[float(x) for x in aabb])
+        rc = self.lib.refnerf_grid_generate(C.c_uint32(n), C.c_uint64(rng_seed), C.c_uint64(rng_advances), C.c_uint32(step), a, C.c_void_p(grid.data_ptr()),
+                                            C.c_void_p(positions.data_ptr()), C.c_void_p(indices.data_ptr()), C.c_uint32(n_cascades), C.c_float(thresh), self._s())
+        assert rc == 0, rc
+
+    def grid_splat_ema(self, indices, logits, decay, ema_step, grid, grid_tmp):
+        rc = self.lib.refnerf_grid_splat_ema(C.c_uint32(indices.numel()), C.c_void_p(indices.data_ptr()), C.c_void_p(logits.data_ptr()), C.c_uint32(grid.numel()),
+                                             C.c_float(decay), C.c_uint32(ema_step), C.c_void_p(grid.data_ptr()), C.c_void_p(grid_tmp.data_ptr()), self._s())
+        assert rc == 0, rc
+
+    def grid_mean_and_bitfield(self, grid, bitfield, mean, n_cascades):
+        rc = self.lib.refnerf_grid_mean_and_bitfield(C.c_void_p(grid.data_ptr()), C.c_void_p(bitfield.data_ptr()), C.c_void_p(mean.data_ptr()), C.c_uint32(n_cascades), self._s())
+        assert rc == 0, rc

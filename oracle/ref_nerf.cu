@@ -19,6 +19,7 @@
 #include <tiny-cuda-nn/common.h>
 #include <tiny-cuda-nn/common_device.h>
 #include <tiny-cuda-nn/gpu_matrix.h>
+#include <tiny-cuda-nn/reduce_sum.h>
 
 #include <vector>
 
@@ -227,6 +228,40 @@ int refnerf_train_loss(uint32_t n_rays, uint32_t n_rays_total, uint32_t target_b
 	fill_rollover_and_rescale<network_precision_t><<<n_blocks_linear(target_batch * padded_output_width), n_threads_linear, 0, stream>>>(target_batch, padded_output_width,
 	                                                                                                                          d_counters + 2, (network_precision_t*)d_dloss);
 	fill_rollover<float><<<n_blocks_linear(target_batch * floats_per_coord), n_threads_linear, 0, stream>>>(target_batch, floats_per_coord, d_counters + 2, d_coords_compacted);
+	return (int)cudaGetLastError();
+}
+
+// ---- occupancy-grid maintenance: the kernels of update_density_grid_nerf / update_density_grid_mean_and_bitfield (testbed_nerf.cu:2774-2878) ----
+int refnerf_grid_mark_untrained(uint32_t n_elements, float* d_grid, int clear_visible, cudaStream_t stream) {
+	linear_kernel(mark_untrained_density_grid, 0, stream, n_elements, d_grid, g_n_images, g_meta, g_xforms, (bool)clear_visible);
+	return (int)cudaGetLastError();
+}
+
+int refnerf_grid_generate(uint32_t n, uint64_t rng_seed, uint64_t rng_advances, uint32_t step, const float* aabb6, const float* d_grid, float* d_positions,
+                          uint32_t* d_indices, uint32_t n_cascades, float thresh, cudaStream_t stream) {
+	default_rng_t rng{rng_seed};
+	for (uint64_t k = 0; k < rng_advances; ++k) rng.advance();
+	static_assert(sizeof(NerfPosition) == 12, "NerfPosition is a bare position in this build");
+	linear_kernel(generate_grid_samples_nerf_nonuniform, 0, stream, n, rng, step, bb6(aabb6), d_grid, (NerfPosition*)d_positions, d_indices, n_cascades, thresh);
+	return (int)cudaGetLastError();
+}
+
+int refnerf_grid_splat_ema(uint32_t n_samples, const uint32_t* d_indices, const void* d_logits_f16, uint32_t n_elements, float decay, uint32_t ema_step, float* d_grid,
+                           float* d_grid_tmp, cudaStream_t stream) {
+	cudaMemsetAsync(d_grid_tmp, 0, sizeof(float) * n_elements, stream);
+	linear_kernel(splat_grid_samples_nerf_max_nearest_neighbor, 0, stream, n_samples, d_indices, (const network_precision_t*)d_logits_f16, d_grid_tmp,
+	              ENerfActivation::Logistic, ENerfActivation::Exponential);
+	linear_kernel(ema_grid_samples_nerf, 0, stream, n_elements, decay, ema_step, d_grid, d_grid_tmp);
+	return (int)cudaGetLastError();
+}
+
+int refnerf_grid_mean_and_bitfield(float* d_grid, uint8_t* d_bitfield, float* d_mean, uint32_t n_cascades, cudaStream_t stream) {
+	const uint32_t n_elements = NERF_GRIDSIZE() * NERF_GRIDSIZE() * NERF_GRIDSIZE();
+	cudaMemsetAsync(d_mean, 0, sizeof(float), stream);
+	reduce_sum(d_grid, [n_elements] __device__(float val) { return fmaxf(val, 0.f) / (n_elements); }, d_mean, n_elements, stream);
+	linear_kernel(grid_to_bitfield, 0, stream, n_elements / 8 * NERF_CASCADES(), n_elements / 8 * n_cascades, d_grid, d_bitfield, d_mean);
+	for (uint32_t level = 1; level < NERF_CASCADES(); ++level)
+		linear_kernel(bitfield_max_pool, 0, stream, n_elements / 64, d_bitfield + grid_mip_offset(level - 1) / 8, d_bitfield + grid_mip_offset(level) / 8);
 	return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,171 @@
+"""insta_train_nerf (one full training step: Testbed::train_nerf, ngp/src/testbed_nerf.cu:2916-2992) against the same step composed by hand
+from the individually parity-tested C-ABI entry points, and its multi-step behaviour (rays_per_batch adaptation, loss decreasing)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_IMAGES, RES, FOCAL = 6, (96, 80), 260.0
+STRIDE = 27
+TARGET = 1 << 14
+
+
+@pytest.fixture(scope="module")
+def train_ctx(scene):
+    from insta_b200 import capi
+
+    capi.load_library(build_if_missing=False)
+    ctx = capi.Context(device=0)
+    ctx.set_canonical(scene.verts, scene.faces, scene.masks)
+    verts = [scene.synth.frame(f) for f in range(N_IMAGES)]  # frame i belongs to image i
+    for v in verts:
+        ctx.add_frame(v)
+    ctx._frame_verts = verts
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def dataset(train_ctx):
+    import torch
+
+    from insta_b200 import synth
+
+    ims = synth.make_training_images(N_IMAGES, RES, FOCAL, seed=3)
+    dev = []
+    for im in ims:
+        d = dict(im)
+        for k in ("pixels", "seg", "depth", "rays"):
+            d[k] = torch.from_numpy(np.ascontiguousarray(im[k])).cuda()
+        dev.append(d)
+    bf = torch.from_numpy(synth.occupancy_bitfield(train_ctx._frame_verts, radius=0.03)).cuda()
+    extra = torch.randn((N_IMAGES, 16), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    train_ctx.training_set_images(dev)
+    return dev, bf, extra
+
+
+class State:
+    """the trainer's buffers (tcnn trainer.h:282-297)"""
+
+    def __init__(self, ctx, seed=11):
+        import torch
+
+        from insta_b200 import synth
+
+        n = ctx.network_n_params
+        p = synth.make_network_params(n, seed=seed, grid_scale=0.1)
+        self.p16 = torch.from_numpy(p).cuda()
+        self.p32 = self.p16.float()
+        self.grads = torch.zeros(n, dtype=torch.float16, device="cuda")
+        self.m1 = torch.zeros(n, device="cuda")
+        self.m2 = torch.zeros(n, device="cuda")
+        self.steps = torch.zeros(n, dtype=torch.int32, device="cuda")
+        self.ema = self.p16.clone()
+
+    def optimizer(self, ctx, current_step=0):
+        return ctx.make_optimizer(current_step, self.p32, self.p16, self.grads, self.m1, self.m2, self.steps, self.ema)
+
+
+def test_full_step_matches_manual_composition(train_ctx, dataset):
+    import torch
+
+    ctx = train_ctx
+    dev, bf, extra = dataset
+    n_rays = 4096
+    mean_density = torch.tensor([0.02], device="cuda")
+    cfg = dict(target_batch_size=TARGET, rays_per_batch=n_rays, depth_weight=1.25, seg_weight=40.0, rng_seed=99)
+    A, B = State(ctx), State(ctx)
+    ctx.trainer_create(**cfg)
+    st = ctx.train_nerf(A.optimizer(ctx), bf, extra, mean_density, get_loss_scalar=True)
+    # ---- the same step by hand ----
+    max_samples = TARGET * 16
+    coords = torch.zeros((max_samples, STRIDE), device="cuda")
+    counters = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ray_indices = torch.zeros(n_rays, dtype=torch.int32, device="cuda")
+    rays = torch.zeros((n_rays, 6), device="cuda")
+    numsteps = torch.zeros((n_rays, 2), dtype=torch.int32, device="cuda")
+    step = ctx.make_train_step(n_rays, 0, coords, counters, ray_indices, rays, numsteps, bf, extra, target_batch_size=TARGET, rng_seed=99, rng_advances=0)
+    ctx.generate_training_samples(step)
+    n_gen = int(counters[1])
+    ctx.surface_closest_point(coords[:n_gen])
+    out = torch.zeros((max_samples, 4), dtype=torch.float16, device="cuda")
+    ctx.network_inference(coords[:n_gen], B.p16, out[:n_gen])
+    cc = torch.zeros((TARGET, STRIDE), device="cuda")
+    dl = torch.zeros((TARGET, 4), dtype=torch.float16, device="cuda")
+    loss = torch.zeros(n_rays, device="cuda")
+    ctx.compute_loss(step, out, 4, cc, dl, loss, mean_density)
+    ctx.network_forward_backward(cc, B.p16, dl, B.grads)
+    ctx.optimizer_step(0, B.p32, B.p16, B.grads, B.m1, B.m2, B.steps, B.ema)
+    torch.cuda.synchronize()
+    assert st["n_rays"] == n_rays and st["n_rays_accepted"] == int(counters[0]) > 500
+    assert st["measured_batch_size_before_compaction"] == n_gen > 10000
+    assert st["measured_batch_size"] == int(counters[2]) > 1000
+    want_rays = min((int(np.float32(n_rays) * np.float32(TARGET) / np.float32(int(counters[2]))) + 127) // 128 * 128, 1 << 18)
+    assert st["rays_per_batch"] == want_rays
+    assert st["training_step"] == 1 and st["n_rays_total"] == n_rays
+    want_loss = float(loss.sum()) * int(counters[2]) / TARGET
+    assert abs(st["loss"] - want_loss) <= 1e-4 * abs(want_loss) and want_loss > 0
+    # gradients: the MLP part is deterministic up to the order of the fp32 partial sums, the grid part is fp16 atomics
+    ga, gb = A.grads.float(), B.grads.float()
+    assert float(gb.abs().sum()) > 0
+    assert float((ga[:25600] - gb[:25600]).abs().max()) <= 2e-3 * float(gb[:25600].abs().max()) + 1e-6
+    touched = gb[25600:] != 0
+    assert torch.equal(touched, ga[25600:] != 0) or float((touched != (ga[25600:] != 0)).float().mean()) < 1e-4
+    d = (ga[25600:] - gb[25600:]).abs()
+    assert float((d > 0.02 * gb[25600:].abs() + 1e-4).float().mean()) < 1e-3
+    assert torch.equal(A.steps != 0, B.steps != 0) or float(((A.steps != 0) != (B.steps != 0)).float().mean()) < 1e-4
+    assert float((A.p32 - B.p32).abs().max()) < 4e-3  # one Adam step moves a weight by at most ~lr = 1.75e-3
+    assert float((A.p32 - B.p32).abs().mean()) < 1e-5
+    assert not torch.equal(A.p16, State(ctx).p16)
+    ctx.trainer_destroy()
+
+
+def test_steps_adapt_rays_and_reduce_loss(train_ctx, dataset):
+    import torch
+
+    ctx = train_ctx
+    dev, bf, extra = dataset
+    mean_density = torch.tensor([0.02], device="cuda")
+    S = State(ctx)
+    ctx.trainer_create(target_batch_size=TARGET, rays_per_batch=1024, depth_weight=0.0, seg_weight=0.0, rng_seed=5)
+    opt = S.optimizer(ctx)
+    hist = []
+    for k in range(40):
+        hist.append(ctx.train_nerf(opt, bf, extra, mean_density, get_loss_scalar=True))
+    torch.cuda.synchronize()
+    assert [h["training_step"] for h in hist] == list(range(1, 41))
+    assert all(np.isfinite(h["loss"]) and h["loss"] > 0 for h in hist)
+    assert all(h["measured_batch_size"] > 0 for h in hist)
+    # rays_per_batch converges so that the compacted batch approaches the target
+    assert hist[-1]["n_rays"] > 1024
+    assert abs(hist[-1]["measured_batch_size"] - TARGET) < 0.35 * TARGET
+    # the generator's capacity ratchet (max_inference): samples before compaction never grow by more than the 128-granularity
+    for a, b in zip(hist, hist[1:]):
+        assert b["measured_batch_size_before_compaction"] <= (a["measured_batch_size_before_compaction"] + 127) // 128 * 128
+    first, last = np.mean([h["loss"] for h in hist[:5]]), np.mean([h["loss"] for h in hist[-5:]])
+    assert last < first, "loss did not decrease: %g -> %g" % (first, last)
+    assert bool(torch.isfinite(S.p32).all()) and bool(torch.isfinite(S.ema.float()).all())
+    assert opt.current_step == 40
+    assert ctx.trainer_state()["rays_per_batch"] == hist[-1]["rays_per_batch"]
+    ctx.trainer_destroy()
+
+
+def test_single_rank_communicator_is_a_no_op(train_ctx):
+    import torch
+
+    g = torch.ones(1024, dtype=torch.float16, device="cuda")
+    train_ctx.comm_init_rank(1, 0, None)
+    train_ctx.grad_allreduce(g)
+    torch.cuda.synchronize()
+    assert float(g.sum()) == 1024
+    train_ctx.comm_destroy()
+
+
+def test_train_requires_trainer_and_images(gpu_ctx):
+    import torch
+
+    from insta_b200 import capi
+
+    S = State(gpu_ctx)
+    with pytest.raises(capi.InstaError):
+        gpu_ctx.train_nerf(S.optimizer(gpu_ctx), torch.zeros(1 << 21, dtype=torch.uint8, device="cuda"), torch.zeros((2, 16), device="cuda"), torch.zeros(1, device="cuda"))
