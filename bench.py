@@ -98,12 +98,12 @@ class ClockSampler:
 
 def build_scene(n_frames, rank, world):
     """Canonical mesh + this rank's shard of the synthetic frames (rank r holds frames r, r+R, ...: SURVEY.md 8e)."""
-    from insta_b200 import synth
+    from insta_b200 import shard, synth
 
     verts, faces, regions = synth.load_canonical()
     masks = synth.mask_ids_from_regions(faces, regions)
     fs = synth.FrameSynth(verts, faces)
-    mine = list(range(rank, n_frames, world))
+    mine = shard.frames_of_rank(n_frames, rank, world)
     fv = np.stack([fs.frame(f) for f in mine]) if mine else np.zeros((0,) + verts.shape, np.float32)
     return verts, faces, masks, fv
 
