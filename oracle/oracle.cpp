@@ -575,6 +575,15 @@ void orc_closest_stats_bounded(const float* pts, int n, const orc_node* nodes, c
 				int end = -nd.right_idx - 1;
 				for (int i = -nd.left_idx - 1; i < end; ++i) {
 					acc[3] += 1;
+					{  // how many exact tests a conservative per-triangle bound (its own AABB) would have skipped
+						const orc_tri& t = tris[i];
+						float mn[3], mx[3];
+						for (int k = 0; k < 3; ++k) {
+							mn[k] = std::min(t.a[k], std::min(t.b[k], t.c[k]));
+							mx[k] = std::max(t.a[k], std::max(t.b[k], t.c[k]));
+						}
+						if (box_distance_sq(mn, mx, p) > best) acc[7] += 1;
+					}
 					float d = tri_distance_sq(tris[i], p);
 					if (d <= best) best = d;
 				}

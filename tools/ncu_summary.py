@@ -23,7 +23,8 @@ def main(path):
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         print("kernel:", d.get("Kernel Name"), "| grid", d.get("Grid Size"), "block", d.get("Block Size"))
-        for k in KEYS:
+        keys = KEYS + sorted(k for k in hdr if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio") and k not in KEYS)
+        for k in keys:
             if k in d and d[k] != "":
                 print("  %-95s %s %s" % (k, d[k], units[hdr.index(k)]))
         try:
