@@ -319,6 +319,17 @@ def run_ours(args):
             if rnd:
                 rnd["ms_per_frame_max_over_ranks"] = float(t.item())
                 rnd["aggregate_frames_per_s"] = world * 1e3 / float(t.item())
+    gather = None
+    if rank == 0 and not args.no_render:
+        # the L2-gather roofline MEASURED_PEAKS.json lacks: divergent 16-B / 128-B gathers from a table-sized L2-resident
+        # buffer and from one that spills to HBM
+        try:
+            tb = n_entries * 16
+            gather = {"l2_16B_gbs": ctx.microbench_gather(tb, 16), "l2_128B_gbs": ctx.microbench_gather(tb, 128),
+                      "hbm_16B_gbs": ctx.microbench_gather(1 << 30, 16), "buffer_bytes": tb,
+                      "how": "insta_microbench_gather: every lane loads 16 B (or 8 lanes one 128-B line) from pseudo-random offsets, 8 loads in flight per lane, best of 5"}
+        except Exception as e:
+            gather = {"error": repr(e)}
     if rank == 0:
         peak, peak_src = measured_peaks()
         # dominant kernel = the one with the larger share of the step
@@ -338,6 +349,13 @@ def run_ours(args):
                          "traffic": None, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
                          "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},
             "kernels_ms": {"deform_kernel": float(t_deform.mean()), "hash_fwd_kernel": float(t_encode.mean())},
+            "l2_gather_roofline": None if not gather or "error" in gather else dict(gather, **{
+                "hash_fwd_gathered_gbs": 2048 * N_SAMPLES / (float(t_encode.mean()) * 1e-3) / 1e9,
+                "hash_fwd_frac": 2048 * N_SAMPLES / (float(t_encode.mean()) * 1e-3) / 1e9 / gather["l2_16B_gbs"],
+                "deform_gathered_gbs": (BYTES_DEFORM - 52) * N_SAMPLES / (float(t_deform.mean()) * 1e-3) / 1e9,
+                "deform_frac": (BYTES_DEFORM - 52) * N_SAMPLES / (float(t_deform.mean()) * 1e-3) / 1e9 / gather["l2_128B_gbs"],
+                "step_frac": ((2048 * N_SAMPLES / gather["l2_16B_gbs"] + (BYTES_DEFORM - 52) * N_SAMPLES / gather["l2_128B_gbs"]) / 1e9) / (float(step_ms.mean()) * 1e-3),
+                "note": "frac = algorithmic gathered bytes / s over the measured divergent-gather bandwidth (16-B entries for the hash grid, 128-B lines for BVH quads / leaves); step_frac = time the step's gathers would take at those bandwidths / measured step time"}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_SAMPLES * STRIDE * 4,
                     "d2h_bytes_per_step": N_SAMPLES * STRIDE * 4 + N_SAMPLES * 128 * 2, "steps": len(e2e_t)},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t1 - t0,

@@ -418,6 +418,45 @@ INSTA_API int insta_host_load_canonical_obj(const char* canonical_obj, const cha
 /* TinyMesh::m_aabb (src/tiny_mesh.cu:157-162) */
 INSTA_API int insta_host_mesh_aabb(const float* h_verts, uint32_t n_verts, float* h_aabb6);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Snapshots in the reference's MessagePack layout -- ngp::Testbed::save_snapshot / load_snapshot (ngp/src/testbed.cu:2916-3016),
+ * tcnn::Trainer::serialize / deserialize (tcnn trainer.h:255-279), EmaOptimizer / AdamOptimizer::serialize (tcnn optimizers/ema.h:182-194,
+ * adam.h:271-292).  Host-only (no GPU needed): binaries are HOST pointers; copy them to / from the trainer's device buffers yourself.
+ * A file written here loads in the reference and vice versa ("nerf"/"dataset" is not written; the reference then keeps its loaded dataset).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct insta_snapshot {
+	uint64_t    n_params;              /* snapshot.n_params */
+	const void* h_params_f16;          /* snapshot.params_binary: the INFERENCE (= EMA) weights, trainer order (density MLP, colour MLP, grid) */
+	uint64_t    n_density_grid;        /* elements of snapshot.density_grid_binary: 128^3 * n_cascades, 0 = never populated */
+	const void* h_density_grid_f16;
+	uint32_t    training_step;         /* snapshot.training_step (the reference resumes at training_step + 1) */
+	float       loss;
+	float       aabb[6], render_aabb[6]; /* min xyz, max xyz */
+	float       bounding_radius;
+	uint32_t    aabb_scale;            /* snapshot.nerf.aabb_scale */
+	uint32_t    rays_per_batch, measured_batch_size, measured_batch_size_before_compaction; /* snapshot.nerf.rgb.* */
+	/* optimizer: hyper-parameters from the embedded network config; state only when has_optimizer (include_optimizer_state) */
+	float       ema_decay, beta1, beta2, epsilon, l2_reg;
+	float       opt_base_learning_rate;
+	uint32_t    has_optimizer;
+	uint32_t    opt_current_step;
+	const float*    h_first_moments;   /* n_params; when read from a file: NOT necessarily 4-byte aligned, copy with memcpy / cudaMemcpy */
+	const float*    h_second_moments;
+	const uint32_t* h_param_steps;     /* NULL in files of older tcnn versions = all zero */
+	const void*     h_weights_ema_f16;
+} insta_snapshot;
+typedef struct insta_snapshot_file insta_snapshot_file;
+/* writes "encoding" from p (NULL = defaults), the shipped network blocks, and the "snapshot" object */
+INSTA_API int insta_snapshot_save(const char* path, const insta_params* p, const insta_snapshot* s);
+/* parses the file; the pointers in *s stay valid until insta_snapshot_close(*file) */
+INSTA_API int insta_snapshot_open(const char* path, insta_snapshot_file** file, insta_snapshot* s);
+INSTA_API void insta_snapshot_close(insta_snapshot_file* file);
+
+/* Measurement aid (not on the hot path): bandwidth of fully divergent gathers of chunk_bytes (16 = one hash-table entry, 128 = one BVH quad
+ * read by 8 cooperating lanes) from an internal buffer of buffer_bytes -- L2-resident when it fits the 126 MB L2, HBM-bound otherwise.
+ * Best of `iters` launches after warm-up, GB/s of gathered bytes.  bench.py reports it as the L2-gather roofline. */
+INSTA_API int insta_microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, insta_stream stream);
+
 /* number of kernels this library has launched on behalf of ctx since creation (bench.py's gpu_launches) */
 INSTA_API uint64_t insta_launch_count(const insta_ctx* ctx);
 

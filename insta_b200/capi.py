@@ -88,6 +88,15 @@ class DensityGrid(C.Structure):
                 ("has_rays", C.c_uint32), ("images_changed", C.c_uint32)]
 
 
+class Snapshot(C.Structure):
+    _fields_ = [("n_params", C.c_uint64), ("h_params_f16", C.c_void_p), ("n_density_grid", C.c_uint64), ("h_density_grid_f16", C.c_void_p), ("training_step", C.c_uint32),
+                ("loss", C.c_float), ("aabb", C.c_float * 6), ("render_aabb", C.c_float * 6), ("bounding_radius", C.c_float), ("aabb_scale", C.c_uint32),
+                ("rays_per_batch", C.c_uint32), ("measured_batch_size", C.c_uint32), ("measured_batch_size_before_compaction", C.c_uint32), ("ema_decay", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float), ("l2_reg", C.c_float), ("opt_base_learning_rate", C.c_float),
+                ("has_optimizer", C.c_uint32), ("opt_current_step", C.c_uint32), ("h_first_moments", C.c_void_p), ("h_second_moments", C.c_void_p),
+                ("h_param_steps", C.c_void_p), ("h_weights_ema_f16", C.c_void_p)]
+
+
 class RenderStats(C.Structure):
     _fields_ = [("iterations", C.c_uint32), ("reserved_", C.c_uint32), ("samples", C.c_uint64)]
 
@@ -125,6 +134,7 @@ EXPORTS = [
     "insta_optimizer_step",
     "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
     "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
+    "insta_microbench_gather", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
     "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
@@ -152,6 +162,7 @@ def load_library(build_if_missing=True):
     lib.insta_ctx_destroy.restype = None
     lib.insta_params_default.restype = None
     lib.insta_trainer_config_default.restype = None
+    lib.insta_snapshot_close.restype = None
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the .so lost a symbol
     _lib = lib
@@ -527,6 +538,12 @@ class Context:
         self._check(self.lib.insta_deform_encode_host(self.h, C.c_void_p(h_coords.data_ptr()), C.c_uint32(n), C.c_uint32(stride), C.c_int32(frame_id),
                                                       _dev(table), C.c_void_p(h_out.data_ptr())))
 
+    def microbench_gather(self, buffer_bytes, chunk_bytes=16, iters=5):
+        """GB/s of fully divergent chunk_bytes gathers from a buffer of buffer_bytes (L2-resident when it fits)."""
+        g = C.c_float(0)
+        self._check(self.lib.insta_microbench_gather(self.h, C.c_uint64(buffer_bytes), C.c_uint32(chunk_bytes), C.c_uint32(iters), C.byref(g), _stream(None)))
+        return float(g.value)
+
     @property
     def launch_count(self):
         return self.lib.insta_launch_count(self.h)
@@ -583,3 +600,54 @@ def host_mesh_aabb(verts):
     out = np.empty(6, np.float32)
     _hcheck(load_library().insta_host_mesh_aabb(_vp(verts), C.c_uint32(len(verts)), _vp(out)))
     return out
+
+
+# ---- snapshots (host-only) ----
+def snapshot_save(path, params16, density_grid16=None, training_step=0, loss=0.0, aabb=(0, 0, 0, 1, 1, 1), render_aabb=(0, 0, 0, 1, 1, 1), bounding_radius=1.0,
+                  aabb_scale=1, rays_per_batch=1 << 12, measured_batch_size=0, measured_batch_size_before_compaction=0, optimizer=None, lib_params=None,
+                  learning_rate=1.75e-3, ema_decay=0.95, beta1=0.9, beta2=0.99, epsilon=1e-15, l2_reg=1e-6):
+    """numpy arrays in, reference-layout MessagePack out.  optimizer: dict(current_step, m1, m2, steps, ema16) or None."""
+    lib = load_library()
+    s = Snapshot()
+    keep = [np.ascontiguousarray(params16, np.float16)]
+    s.n_params, s.h_params_f16 = keep[0].size, keep[0].ctypes.data
+    if density_grid16 is not None:
+        keep.append(np.ascontiguousarray(density_grid16, np.float16))
+        s.n_density_grid, s.h_density_grid_f16 = keep[-1].size, keep[-1].ctypes.data
+    s.training_step, s.loss, s.bounding_radius, s.aabb_scale = training_step, loss, bounding_radius, aabb_scale
+    for k in range(6):
+        s.aabb[k], s.render_aabb[k] = aabb[k], render_aabb[k]
+    s.rays_per_batch, s.measured_batch_size, s.measured_batch_size_before_compaction = rays_per_batch, measured_batch_size, measured_batch_size_before_compaction
+    s.ema_decay, s.beta1, s.beta2, s.epsilon, s.l2_reg, s.opt_base_learning_rate = ema_decay, beta1, beta2, epsilon, l2_reg, learning_rate
+    if optimizer is not None:
+        m1, m2 = np.ascontiguousarray(optimizer["m1"], np.float32), np.ascontiguousarray(optimizer["m2"], np.float32)
+        st, ema = np.ascontiguousarray(optimizer["steps"], np.uint32), np.ascontiguousarray(optimizer["ema16"], np.float16)
+        keep += [m1, m2, st, ema]
+        s.has_optimizer, s.opt_current_step = 1, int(optimizer["current_step"])
+        s.h_first_moments, s.h_second_moments, s.h_param_steps, s.h_weights_ema_f16 = m1.ctypes.data, m2.ctypes.data, st.ctypes.data, ema.ctypes.data
+    _hcheck(lib.insta_snapshot_save(str(path).encode(), C.byref(lib_params) if lib_params is not None else None, C.byref(s)))
+
+
+def snapshot_load(path):
+    """dict of numpy arrays / scalars (copies; the file is closed before returning)"""
+    lib = load_library()
+    s, f = Snapshot(), C.c_void_p()
+    _hcheck(lib.insta_snapshot_open(str(path).encode(), C.byref(f), C.byref(s)))
+    try:
+        def arr(ptr, n, dt):
+            if not ptr or n == 0:
+                return None
+            return np.frombuffer(C.string_at(ptr, n * np.dtype(dt).itemsize), dtype=dt).copy()
+        out = {k: getattr(s, k) for k in ("n_params", "training_step", "loss", "bounding_radius", "aabb_scale", "rays_per_batch", "measured_batch_size",
+                                          "measured_batch_size_before_compaction", "ema_decay", "beta1", "beta2", "epsilon", "l2_reg", "opt_base_learning_rate",
+                                          "has_optimizer", "opt_current_step")}
+        out["aabb"], out["render_aabb"] = np.array(list(s.aabb), np.float32), np.array(list(s.render_aabb), np.float32)
+        out["params16"] = arr(s.h_params_f16, s.n_params, np.float16)
+        out["density_grid16"] = arr(s.h_density_grid_f16, s.n_density_grid, np.float16)
+        if s.has_optimizer:
+            out["m1"], out["m2"] = arr(s.h_first_moments, s.n_params, np.float32), arr(s.h_second_moments, s.n_params, np.float32)
+            out["steps"] = arr(s.h_param_steps, s.n_params, np.uint32)
+            out["ema16"] = arr(s.h_weights_ema_f16, s.n_params, np.float16)
+        return out
+    finally:
+        lib.insta_snapshot_close(f)

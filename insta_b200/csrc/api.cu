@@ -579,6 +579,35 @@ int insta_update_density_grid_mean_and_bitfield(insta_ctx* ctx, const insta_dens
 	return density_grid_mean_and_bitfield(ctx, g, (cudaStream_t)stream);
 }
 
+int insta_snapshot_save(const char* path, const insta_params* p, const insta_snapshot* s) {
+	if (!path || !s || !s->h_params_f16 || s->n_params == 0 || (s->n_density_grid && !s->h_density_grid_f16)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_snapshot_save: bad arguments");
+	if (s->has_optimizer && (!s->h_first_moments || !s->h_second_moments || !s->h_param_steps || !s->h_weights_ema_f16)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_snapshot_save: optimizer state incomplete");
+	if (s->n_params * 4 > 0xffffffffull) INSTA_FAIL(INSTA_ERR_INVALID, "insta_snapshot_save: parameter count exceeds a MessagePack bin32");
+	insta_params dflt;
+	if (!p) {
+		insta_params_default(&dflt);
+		p = &dflt;
+	}
+	return snapshot_save(path, p, s);
+}
+
+int insta_snapshot_open(const char* path, insta_snapshot_file** file, insta_snapshot* s) {
+	if (!path || !file || !s) INSTA_FAIL(INSTA_ERR_INVALID, "insta_snapshot_open: bad arguments");
+	*file = nullptr;
+	SnapshotFile* f = nullptr;
+	const int rc = snapshot_open(path, &f, s);
+	if (rc == INSTA_OK) *file = reinterpret_cast<insta_snapshot_file*>(f);
+	return rc;
+}
+
+void insta_snapshot_close(insta_snapshot_file* file) { snapshot_close(reinterpret_cast<SnapshotFile*>(file)); }
+
+int insta_microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, insta_stream stream) {
+	if (!ctx || !h_gbs || iters == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_microbench_gather: bad arguments");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	return microbench_gather(ctx, buffer_bytes, chunk_bytes, iters, h_gbs, (cudaStream_t)stream);
+}
+
 int insta_comm_unique_id(void* h_id128) {
 	if (!h_id128) INSTA_FAIL(INSTA_ERR_INVALID, "insta_comm_unique_id: null buffer");
 	return comm_unique_id(h_id128);

@@ -198,6 +198,13 @@ int train_loss(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out,
                const float* d_mean_density, cudaStream_t s);
 int optimizer_step(insta_ctx* ctx, const insta_optimizer* o, uint32_t n_params, uint32_t n_matrix, cudaStream_t s);
 int launch_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride, uint32_t n, const void* d_params, void* d_logits_f16, cudaStream_t s);
+// snapshot.cpp
+struct SnapshotFile;
+int snapshot_save(const char* path, const insta_params* p, const insta_snapshot* s);
+int snapshot_open(const char* path, SnapshotFile** out_file, insta_snapshot* s);
+void snapshot_close(SnapshotFile* f);
+// microbench.cu
+int microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, cudaStream_t s);
 // occupancy.cu
 void occupancy_destroy(insta_ctx* ctx);
 int density_grid_update(insta_ctx* ctx, insta_density_grid* g, const void* d_params_f16, uint32_t n_uniform, uint32_t n_nonuniform, cudaStream_t s);
