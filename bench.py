@@ -330,6 +330,9 @@ def run_ours(args):
                       "how": "insta_microbench_gather: every lane loads 16 B (or 8 lanes one 128-B line) from pseudo-random offsets, 8 loads in flight per lane, best of 5"}
         except Exception as e:
             gather = {"error": repr(e)}
+    stress = None
+    if args.stress:
+        stress = stress_leg(args, rank, world)
     if rank == 0:
         peak, peak_src = measured_peaks()
         # dominant kernel = the one with the larger share of the step
@@ -370,6 +373,8 @@ def run_ours(args):
             line["network"] = net
             line["render"] = rnd
             line["train_step"] = trn
+        if args.stress:
+            line["stress"] = stress
         if world == 1 and args.ref_cuda:
             try:
                 line["ref_cuda"] = ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args)
@@ -516,6 +521,64 @@ def train_leg(ctx, verts, fv, args, rank, world):
             "note": "insta_train_nerf: generate + deform + fused inference + loss/compaction + fused forward/backward (tcgen05) + Adam/EMA; one stream sync per step"}
 
 
+def stress_leg(args, rank, world):
+    """BASELINE.json configs[4]: 2048^2 render with max_cached_bvh = 4000 per-frame BVHs resident and a 2^22-entry hash table (632 MB fp16:
+    the gathers spill the 126 MB L2 and become HBM-bound).  Own context (different grid size)."""
+    import torch
+
+    from insta_b200 import capi, shard, synth
+
+    verts, faces, regions = synth.load_canonical()
+    masks = synth.mask_ids_from_regions(faces, regions)
+    fs = synth.FrameSynth(verts, faces)
+    mine = shard.frames_of_rank(args.stress_frames, rank, world)
+    ctx = capi.Context(device=int(os.environ.get("LOCAL_RANK", 0)), log2_hashmap_size=22, max_cached_bvh=4000)
+    ctx.set_canonical(verts, faces, masks)
+    t0 = time.perf_counter()
+    fv = np.stack([fs.frame(f) for f in mine])
+    t1 = time.perf_counter()
+    ctx.add_frames(fv)
+    t2 = time.perf_counter()
+    res = (2048, 2048)
+    bf = torch.from_numpy(synth.occupancy_bitfield([fv[k] for k in range(min(len(fv), 8))], radius=0.03)).cuda()
+    pn = synth.make_network_params(ctx.network_n_params, seed=1337)
+    pn[13312:13312 + 64] = np.float16(0.6)
+    params = torch.from_numpy(pn).cuda()
+    n = res[0] * res[1]
+    fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+    extra = torch.zeros(16, device="cuda")
+    ms, samples = [], []
+    for k in range(2 + args.stress_renders):
+        f = (k * 997) % len(mine)
+        cam = capi.make_camera(synth.random_camera(777 + k), 1200.0 * res[0] / 512.0, res)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        it, smp = ctx.render_frame(cam, f, params, fr, fd, bitfield=bf, extra_dims=extra)
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= 2:
+            ms.append(e0.elapsed_time(e1)); samples.append(smp)
+    # the hash-grid forward alone with the spilling table
+    rec = torch.from_numpy(synth.make_records(N_SAMPLES, synth.mesh_aabb(verts), np.zeros(N_SAMPLES, np.int32), seed=3)).cuda()
+    out = torch.empty((128, N_SAMPLES), dtype=torch.float16, device="cuda")
+    table = params[25600:].view(-1, 8)
+    th = []
+    for k in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.hash_encode_fwd(rec, table, out)
+        e1.record()
+        torch.cuda.synchronize()
+        th.append(e0.elapsed_time(e1))
+    hash_ms = float(np.mean(th[2:]))
+    r = {"resolution": list(res), "frames_resident_per_gpu": len(mine), "hash_table_bytes": int(table.numel() * 2), "ms_per_frame": float(np.mean(ms)),
+         "samples_per_frame": float(np.mean(samples)), "frames_timed": len(ms), "frame_synthesis_s": t1 - t0, "ingest_s (host BVH builds + upload)": t2 - t1,
+         "hash_fwd_ms_4M_samples": hash_ms, "hash_fwd_gathered_gbs": 2048 * N_SAMPLES / (hash_ms * 1e-3) / 1e9,
+         "device_memory_gb": torch.cuda.memory_allocated() / 1e9}
+    ctx.close()
+    return r
+
+
 def network_leg(ctx, rec_np, args):
     """The fused encode + MLP kernel alone on the 4M-sample batch (what the reference does with kernel_grid + 2 x kernel_mlp_fused + glue)."""
     import torch
@@ -596,6 +659,9 @@ def main():
     ap.add_argument("--train-images", type=int, default=128, help="synthetic 512^2 training images (= frames) per GPU in the train-step leg")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-warmup", type=int, default=30)
+    ap.add_argument("--stress", action="store_true", help="also run configs[4]: 2048^2 render, 4000 resident BVHs, 2^22-entry hash table")
+    ap.add_argument("--stress-frames", type=int, default=4000)
+    ap.add_argument("--stress-renders", type=int, default=4)
     ap.add_argument("--ref-cuda", action="store_true", default=True)
     ap.add_argument("--no-ref-cuda", dest="ref_cuda", action="store_false")
     args = ap.parse_args()
