@@ -137,7 +137,11 @@ __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
 	if (j == 0) return;
 	const uint32_t numsteps = j;
 	const uint32_t base = atomicAdd(a.numsteps_counter, numsteps);
-	if (base + numsteps > a.max_samples) return;
+	if (base + numsteps > a.max_samples) {
+		// dropped (testbed_nerf.cu:1248-1251).  The part of the span below the capacity stays a hole: mark it so that the emit pass skips it
+		for (uint32_t k = base; k < a.max_samples; ++k) reinterpret_cast<uint32_t*>(a.coords + (size_t)k * a.stride)[1] = 0xffffffffu;
+		return;
+	}
 	const uint32_t ray_idx = atomicAdd(a.ray_counter, 1u);
 	a.ray_indices[ray_idx] = i;
 	float* ro = a.rays + (size_t)ray_idx * 6;
@@ -145,10 +149,8 @@ __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
 	a.numsteps[ray_idx * 2 + 0] = numsteps;
 	a.numsteps[ray_idx * 2 + 1] = base;
 
-	// second march: emit
-	const float wdx = (dx + 1.0f) * 0.5f, wdy = (dy + 1.0f) * 0.5f, wdz = (dz + 1.0f) * 0.5f;
-	const float max_step = min_stepsize() * (1 << (kCascades - 1));
-	const float* extra = a.extra_dims ? a.extra_dims + (size_t)img * a.n_extra : nullptr;
+	// second march: only the ray parameter t and the ray's slot per sample (8 bytes); train_emit_kernel expands them into records with
+	// coalesced stores.  (Writing the 27 floats from here costs 27 store instructions per sample, each touching 32 different lines.)
 	float* rec = a.coords + (size_t)base * a.stride;
 	t = startt;
 	j = 0;
@@ -158,19 +160,71 @@ __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
 		const float dt = calc_dt(t, a.cone_angle);
 		const uint32_t mip = (uint32_t)mip_from_dt(dt, qx, qy, qz);
 		if (occupied_at(qx, qy, qz, a.bitfield, mip)) {
-			const float wx = (qx - a.aabb[0]) / (a.aabb[3] - a.aabb[0]), wy = (qy - a.aabb[1]) / (a.aabb[4] - a.aabb[1]), wz = (qz - a.aabb[2]) / (a.aabb[5] - a.aabb[2]);
-			rec[0] = wx; rec[1] = wy; rec[2] = wz;
-			rec[3] = (dt - min_stepsize()) / (max_step - min_stepsize());
-			rec[4] = (float)img;
-			rec[5] = wx; rec[6] = wy; rec[7] = wz;
-			rec[8] = wdx; rec[9] = wdy; rec[10] = wdz;
-			for (uint32_t e = 0; e < a.n_extra; ++e) rec[11 + e] = extra ? extra[e] : 0.0f;
+			rec[0] = t;
+			reinterpret_cast<uint32_t*>(rec)[1] = ray_idx;
 			rec += a.stride;
 			++j;
 			t += dt;
 		} else {
 			t = advance_to_next_voxel(t, a.cone_angle, qx, qy, qz, dx, dy, dz, ix, iy, iz, kGrid >> mip);
 		}
+	}
+}
+
+// Expands (t, ray slot) into the NerfCoordinate records (testbed_nerf.cu:1262-1272).  A warp owns 32 consecutive records: every lane
+// computes the fields of one sample, the 32 x stride floats leave through shared memory as full-line stores.
+constexpr uint32_t kEmitWarps = 4;
+__global__ void __launch_bounds__(kEmitWarps * 32) train_emit_kernel(const GenArgs a) {
+	extern __shared__ float emit_smem[];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	float* tile = emit_smem + (size_t)warp * 32u * a.stride;
+	const uint32_t n = min(*a.numsteps_counter, a.max_samples);
+	const uint32_t first = (blockIdx.x * kEmitWarps + warp) * 32u;
+	if (first >= n) return;
+	const uint32_t cnt = min(32u, n - first);
+	float* rec0 = a.coords + (size_t)first * a.stride;
+	bool valid = false;
+	if (lane < cnt) {
+		const float* rec = rec0 + (size_t)lane * a.stride;
+		const float t = rec[0];
+		const uint32_t ray_idx = reinterpret_cast<const uint32_t*>(rec)[1];
+		valid = ray_idx != 0xffffffffu;
+		if (valid) {
+			const float* ro = a.rays + (size_t)ray_idx * 6;
+			const float ox = ro[0], oy = ro[1], oz = ro[2];
+			float dx = ro[3], dy = ro[4], dz = ro[5];
+			{
+				const float n2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+				if (n2 > 0.f) {
+					const float nn = sqrtf(n2);
+					dx /= nn; dy /= nn; dz /= nn;
+				}
+			}
+			const uint32_t img = image_idx(a.ray_indices[ray_idx], a.n_rays, a.n_rays_total, a.n_images);
+			const float qx = fmaf(t, dx, ox), qy = fmaf(t, dy, oy), qz = fmaf(t, dz, oz);
+			const float dt = calc_dt(t, a.cone_angle);
+			const float max_step = min_stepsize() * (1 << (kCascades - 1));
+			const float wx = (qx - a.aabb[0]) / (a.aabb[3] - a.aabb[0]), wy = (qy - a.aabb[1]) / (a.aabb[4] - a.aabb[1]), wz = (qz - a.aabb[2]) / (a.aabb[5] - a.aabb[2]);
+			float* o = tile + (size_t)lane * a.stride;
+			o[0] = wx; o[1] = wy; o[2] = wz;
+			o[3] = (dt - min_stepsize()) / (max_step - min_stepsize());
+			o[4] = (float)img;
+			o[5] = wx; o[6] = wy; o[7] = wz;
+			o[8] = (dx + 1.0f) * 0.5f; o[9] = (dy + 1.0f) * 0.5f; o[10] = (dz + 1.0f) * 0.5f;
+			const float* extra = a.extra_dims ? a.extra_dims + (size_t)img * a.n_extra : nullptr;
+			for (uint32_t e = 0; e < a.n_extra; ++e) o[11 + e] = extra ? __ldg(extra + e) : 0.0f;
+			for (uint32_t e = 11 + a.n_extra; e < a.stride; ++e) o[e] = rec[e];  // floats past the extra dims are not the generator's
+		}
+	}
+	const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+	__syncwarp();
+	if (vmask == (cnt == 32u ? 0xffffffffu : ((1u << cnt) - 1u))) {
+		for (uint32_t k = lane; k < cnt * a.stride; k += 32) rec0[k] = tile[k];
+	} else {
+		// a hole of a dropped ray inside this tile (at most one per step): per-record copies of the valid ones
+		for (uint32_t r = 0; r < cnt; ++r)
+			if ((vmask >> r) & 1u)
+				for (uint32_t k = lane; k < a.stride; k += 32) rec0[(size_t)r * a.stride + k] = tile[(size_t)r * a.stride + k];
 	}
 }
 
@@ -205,10 +259,17 @@ __device__ __forceinline__ void huber5(float target, float pred, float& loss, fl
 	grad = (ad > alpha ? (d > 0 ? 1.0f : -1.0f) : (d / alpha)) / 5.0f;
 }
 
+// One WARP per ray (the reference runs one thread per ray, so a step of 10^4..10^5 rays leaves most of the chip idle and every thread
+// walks its samples through a chain of dependent, 108-byte-strided loads).  Lanes take consecutive samples of the ray: network outputs and
+// record fields are loaded and activated in parallel (coalesced), then the order-dependent recurrences -- transmittance, colour / depth
+// accumulation, the early exit at T < 1e-4 -- run as a warp-uniform loop over the 32 staged samples with exactly the reference's
+// operation order, so the compacted step count and every rounding are those of the sequential loop.  The compacted records are copied
+// cooperatively.
 __global__ void __launch_bounds__(128) train_loss_kernel(const LossArgs a) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	constexpr uint32_t FULL = 0xffffffffu;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
 	if (i >= *a.ray_counter) return;
-	uint32_t numsteps = a.numsteps[i * 2 + 0];
+	const uint32_t numsteps = a.numsteps[i * 2 + 0];
 	const uint32_t base = a.numsteps[i * 2 + 1];
 	const float* cin = a.coords + (size_t)base * a.stride;
 	const __half* nout = a.net_out + (size_t)base * a.out_width;
@@ -217,11 +278,12 @@ __global__ void __launch_bounds__(128) train_loss_kernel(const LossArgs a) {
 	const float sx = a.aabb[3] - a.aabb[0], sy = a.aabb[4] - a.aabb[1], sz = a.aabb[5] - a.aabb[2];
 	const float max_step = min_stepsize() * (1 << (kCascades - 1));
 
-	auto sample = [&](uint32_t j, float& r, float& g, float& b, float& o0, float& o1, float& o2, float& o3, float& density, float& dt, float& depth) {
+	// per-sample quantities of sample j (one lane each)
+	auto sample = [&](uint32_t j, float& r, float& g, float& b, float& o3, float& density, float& dt, float& depth) {
 		const uint2 raw = *reinterpret_cast<const uint2*>(nout + (size_t)j * a.out_width);
 		const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-		o0 = lo.x; o1 = lo.y; o2 = hi.x; o3 = hi.y;
-		r = logistic(o0); g = logistic(o1); b = logistic(o2);
+		o3 = hi.y;
+		r = logistic(lo.x); g = logistic(lo.y); b = logistic(hi.x);
 		const float* c = cin + (size_t)j * a.stride;
 		const float px = fmaf(c[5], sx, a.aabb[0]), py = fmaf(c[6], sy, a.aabb[1]), pz = fmaf(c[7], sz, a.aabb[2]);  // deformed_pos
 		dt = fmaf(c[3], max_step - min_stepsize(), min_stepsize());
@@ -235,19 +297,31 @@ __global__ void __launch_bounds__(128) train_loss_kernel(const LossArgs a) {
 	const float EPSILON = 1e-4f;
 	float rr = 0.f, rg = 0.f, rb = 0.f, depth_ray = 0.f;
 	uint32_t compacted = 0;
-	for (; compacted < numsteps; ++compacted) {
-		if (T < EPSILON) break;
-		float r, g, b, o0, o1, o2, o3, density, dt, depth;
-		sample(compacted, r, g, b, o0, o1, o2, o3, density, dt, depth);
-		const float alpha = 1.f - __expf(-density * dt);
-		const float w = alpha * T;
-		rr += w * r; rg += w * g; rb += w * b;
-		depth_ray += w * depth;
-		T *= (1.f - alpha);
+	bool stop = false;
+	for (uint32_t j0 = 0; j0 < numsteps && !stop; j0 += 32) {
+		const uint32_t cnt = min(32u, numsteps - j0);
+		float r = 0.f, g = 0.f, b = 0.f, o3, density, dt, depth = 0.f, alpha = 0.f;
+		if (lane < cnt) {
+			sample(j0 + lane, r, g, b, o3, density, dt, depth);
+			alpha = 1.f - __expf(-density * dt);
+		}
+		for (uint32_t k = 0; k < cnt; ++k) {
+			if (T < EPSILON) {
+				stop = true;
+				break;
+			}
+			const float ak = __shfl_sync(FULL, alpha, k), rk = __shfl_sync(FULL, r, k), gk = __shfl_sync(FULL, g, k), bk = __shfl_sync(FULL, b, k),
+			            dk = __shfl_sync(FULL, depth, k);
+			const float w = ak * T;
+			rr += w * rk; rg += w * gk; rb += w * bk;
+			depth_ray += w * dk;
+			T *= (1.f - ak);
+			++compacted;
+		}
 	}
 	const float T_ray = T;
 
-	// target colour: same pcg32 stream as the generator
+	// target colour: same pcg32 stream as the generator (every lane computes the same values)
 	const uint32_t ray_idx = a.ray_indices[i];
 	Pcg32 rng{a.rng_state, a.rng_inc};
 	rng.advance((uint64_t)(uint32_t)(ray_idx * 8u));
@@ -275,13 +349,14 @@ __global__ void __launch_bounds__(128) train_loss_kernel(const LossArgs a) {
 		rr += T * bgx; rg += T * bgy; rb += T * bgz;
 	}
 
-	const uint32_t cbase = atomicAdd(a.compacted_counter, compacted);
+	uint32_t cbase = 0;
+	if (lane == 0) cbase = atomicAdd(a.compacted_counter, compacted);
+	cbase = __shfl_sync(FULL, cbase, 0);
 	compacted = min(a.max_samples_compacted - min(a.max_samples_compacted, cbase), compacted);
-	a.numsteps[i * 2 + 0] = compacted;
-	a.numsteps[i * 2 + 1] = cbase;
-	if (compacted == 0) return;
-	float* cout = a.coords_out + (size_t)cbase * a.stride;
-	__half* dl = a.dloss + (size_t)cbase * a.out_width;
+	if (lane == 0) {
+		a.numsteps[i * 2 + 0] = compacted;
+		a.numsteps[i * 2 + 1] = cbase;
+	}
 
 	float seg_supervision = 1.f, depth_lambda = a.depth_lambda;
 	if (im.seg) {
@@ -291,18 +366,22 @@ __global__ void __launch_bounds__(128) train_loss_kernel(const LossArgs a) {
 		if (mask_id <= 90 || mask_id > 250) depth_lambda = 0.f;
 		if (tex.w < 0.001f) depth_lambda = 0.f;
 	}
-	const float dnorm = sqrtf(ray[3] * ray[3] + (ray[4] * ray[4] + ray[5] * ray[5]));
-	const float target_depth = dnorm * ((depth_lambda > 0.0f && im.depth) ? im.depth[(size_t)px + (size_t)py * im.res[0]] : -1.0f);
-	// L1 depth loss gradient: sign(prediction - target)
-	float depth_grad = target_depth > 0.0f ? copysignf(1.0f, depth_ray - target_depth) : 0.f;
-	depth_grad *= depth_lambda;
-
 	float lr_, lg_, lb_, gr, gg, gb;
 	huber5(tr, rr, lr_, gr);
 	huber5(tg, rg, lg_, gg);
 	huber5(tb, rb, lb_, gb);
 	gr *= seg_supervision; gg *= seg_supervision; gb *= seg_supervision;
-	if (a.loss_out) a.loss_out[i] = ((lr_ + lg_ + lb_) / 3.0f) / (float)a.n_rays;
+	// the reference returns before writing the loss of a ray whose samples no longer fit the compacted batch (1468-1470)
+	if (compacted == 0) return;
+	if (a.loss_out && lane == 0) a.loss_out[i] = ((lr_ + lg_ + lb_) / 3.0f) / (float)a.n_rays;
+	float* cout = a.coords_out + (size_t)cbase * a.stride;
+	__half* dl = a.dloss + (size_t)cbase * a.out_width;
+
+	const float dnorm = sqrtf(ray[3] * ray[3] + (ray[4] * ray[4] + ray[5] * ray[5]));
+	const float target_depth = dnorm * ((depth_lambda > 0.0f && im.depth) ? im.depth[(size_t)px + (size_t)py * im.res[0]] : -1.0f);
+	// L1 depth loss gradient: sign(prediction - target)
+	float depth_grad = target_depth > 0.0f ? copysignf(1.0f, depth_ray - target_depth) : 0.f;
+	depth_grad *= depth_lambda;
 
 	const float loss_scale = a.loss_scale / (float)a.n_rays;
 	const float l1_reg_density = *a.mean_density < 0.01f ? 1e-4f : 0.0f;  // NERF_MIN_OPTICAL_THICKNESS
@@ -310,30 +389,49 @@ __global__ void __launch_bounds__(128) train_loss_kernel(const LossArgs a) {
 	// backward sweep (1547-1602)
 	float r2 = 0.f, g2 = 0.f, b2 = 0.f, depth_ray2 = 0.f;
 	T = 1.f;
-	for (uint32_t j = 0; j < compacted; ++j) {
-		const float* c = cin + (size_t)j * a.stride;
-		float* co = cout + (size_t)j * a.stride;
-		for (uint32_t k = 0; k < a.stride; ++k) co[k] = c[k];
-		float r, g, b, o0, o1, o2, o3, density, dt, depth;
-		sample(j, r, g, b, o0, o1, o2, o3, density, dt, depth);
-		const float alpha = 1.f - __expf(-density * dt);
-		const float w = alpha * T;
-		r2 += w * r; g2 += w * g; b2 += w * b;
-		depth_ray2 += w * depth;
-		T *= (1.f - alpha);
-		const float sfx_r = rr - r2, sfx_g = rg - g2, sfx_b = rb - b2;
-		// logistic derivative s (1 - s); output_l2_reg is 0 for logistic colours
-		const float d0 = loss_scale * (w * gr * (r * (1 - r))), d1 = loss_scale * (w * gg * (g * (1 - g))), d2 = loss_scale * (w * gb * (b * (1 - b)));
-		const float density_derivative = __expf(tclamp(o3, -15.0f, 15.0f));
-		const float depth_suffix = depth_ray - depth_ray2;
-		const float depth_supervision = depth_grad * (T * depth - depth_suffix);
-		const float beta_supervision = dt / (T_ray - 1.f + 1e-3f);
-		float dmlp = density_derivative * (dt * (gr * (T * r - sfx_r) + (gg * (T * g - sfx_g) + gb * (T * b - sfx_b)) + depth_supervision) + a.beta * beta_supervision);
-		if (a.penalize_density) dmlp += (tex.w <= 0.01f) ? w : 0.f;
-		const float d3 = loss_scale * dmlp + (o3 < 0.0f ? -l1_reg_density : 0.0f) + (o3 > -10.0f && depth < a.near_distance ? 1e-4f : 0.0f);
-		const __half2 h01 = __floats2half2_rn(d0, d1), h23 = __floats2half2_rn(d2, d3);
-		*reinterpret_cast<uint2*>(dl + (size_t)j * a.out_width) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-		for (uint32_t k = 4; k < a.out_width; ++k) dl[(size_t)j * a.out_width + k] = __float2half(0.f);
+	for (uint32_t j0 = 0; j0 < compacted; j0 += 32) {
+		const uint32_t cnt = min(32u, compacted - j0);
+		// the records of the chunk, copied as one contiguous run of floats
+		{
+			const float* src = cin + (size_t)j0 * a.stride;
+			float* dst = cout + (size_t)j0 * a.stride;
+			for (uint32_t k = lane; k < cnt * a.stride; k += 32) dst[k] = src[k];
+		}
+		float r = 0.f, g = 0.f, b = 0.f, o3 = 0.f, density = 0.f, dt = 0.f, depth = 0.f, alpha = 0.f;
+		if (lane < cnt) {
+			sample(j0 + lane, r, g, b, o3, density, dt, depth);
+			alpha = 1.f - __expf(-density * dt);
+		}
+		// prefix state of THIS lane's sample, taken from the warp-uniform sequential recurrence
+		float my_w = 0.f, my_T = 0.f, my_r2 = 0.f, my_g2 = 0.f, my_b2 = 0.f, my_d2 = 0.f;
+		for (uint32_t k = 0; k < cnt; ++k) {
+			const float ak = __shfl_sync(FULL, alpha, k), rk = __shfl_sync(FULL, r, k), gk = __shfl_sync(FULL, g, k), bk = __shfl_sync(FULL, b, k),
+			            dk = __shfl_sync(FULL, depth, k);
+			const float w = ak * T;
+			r2 += w * rk; g2 += w * gk; b2 += w * bk;
+			depth_ray2 += w * dk;
+			T *= (1.f - ak);
+			if (lane == k) {
+				my_w = w; my_T = T; my_r2 = r2; my_g2 = g2; my_b2 = b2; my_d2 = depth_ray2;
+			}
+		}
+		if (lane < cnt) {
+			const float w = my_w, Tj = my_T;
+			const float sfx_r = rr - my_r2, sfx_g = rg - my_g2, sfx_b = rb - my_b2;
+			// logistic derivative s (1 - s); output_l2_reg is 0 for logistic colours
+			const float d0 = loss_scale * (w * gr * (r * (1 - r))), d1 = loss_scale * (w * gg * (g * (1 - g))), d2 = loss_scale * (w * gb * (b * (1 - b)));
+			const float density_derivative = __expf(tclamp(o3, -15.0f, 15.0f));
+			const float depth_suffix = depth_ray - my_d2;
+			const float depth_supervision = depth_grad * (Tj * depth - depth_suffix);
+			const float beta_supervision = dt / (T_ray - 1.f + 1e-3f);
+			float dmlp = density_derivative * (dt * (gr * (Tj * r - sfx_r) + (gg * (Tj * g - sfx_g) + gb * (Tj * b - sfx_b)) + depth_supervision) + a.beta * beta_supervision);
+			if (a.penalize_density) dmlp += (tex.w <= 0.01f) ? w : 0.f;
+			const float d3 = loss_scale * dmlp + (o3 < 0.0f ? -l1_reg_density : 0.0f) + (o3 > -10.0f && depth < a.near_distance ? 1e-4f : 0.0f);
+			const __half2 h01 = __floats2half2_rn(d0, d1), h23 = __floats2half2_rn(d2, d3);
+			const size_t j = j0 + lane;
+			*reinterpret_cast<uint2*>(dl + j * a.out_width) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+			for (uint32_t k = 4; k < a.out_width; ++k) dl[j * a.out_width + k] = __float2half(0.f);
+		}
 	}
 }
 
@@ -465,7 +563,11 @@ int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s) {
 	INSTA_CUDA(cudaMemsetAsync(t->d_counters, 0, 3 * sizeof(uint32_t), s));
 	if (a.n_rays == 0) return INSTA_OK;
 	train_generate_kernel<<<(a.n_rays + 127) / 128, 128, 0, s>>>(a);
-	ctx->launches++;
+	// the sample count is only known on the device: the emit grid covers the capacity, warps past the count exit at once
+	const size_t emit_smem = (size_t)kEmitWarps * 32u * a.stride * sizeof(float);
+	if (emit_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(train_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+	train_emit_kernel<<<(a.max_samples + kEmitWarps * 32 - 1) / (kEmitWarps * 32), kEmitWarps * 32, emit_smem, s>>>(a);
+	ctx->launches += 2;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
 }
@@ -503,7 +605,7 @@ int train_loss(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out,
 	a.loss_out = d_loss;
 	a.mean_density = d_mean_density;
 	if (a.n_rays == 0) return INSTA_OK;
-	train_loss_kernel<<<(a.n_rays + 127) / 128, 128, 0, s>>>(a);
+	train_loss_kernel<<<(a.n_rays + 3) / 4, 128, 0, s>>>(a);  // one warp per ray
 	ctx->launches++;
 	// pad the compacted batch to exactly target_batch_size samples
 	const uint32_t nb = t->target_batch_size;
