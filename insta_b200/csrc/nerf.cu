@@ -125,51 +125,71 @@ __global__ void __launch_bounds__(128) nerf_init_rays_kernel(const RenderArgs a,
 
 // generate_next_nerf_network_inputs: up to n_steps occupied samples per alive ray, sample (i + j n_alive) of the record
 // buffer; records of steps the ray never reaches keep holder = -1 (so the deformation skips them).
+// The 32 records a warp produces for one step are contiguous in the buffer ((i0 + j n_alive) .. + 31): they are assembled in shared
+// memory and leave as full-line stores (27 scalar stores per record, each touching 32 different lines, otherwise).
 __global__ void __launch_bounds__(128) nerf_march_kernel(const RenderArgs a, RaySet rays, const uint32_t n_alive, float* __restrict__ records, const uint32_t stride,
                                                          const uint32_t n_steps, const float frame_id, const float* __restrict__ extra_dims, const uint32_t n_extra) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n_alive) return;
-	const float4 o_t = rays.o_t[i], d_w = rays.d_w[i];
-	const float ox = o_t.x, oy = o_t.y, oz = o_t.z, dx = d_w.x, dy = d_w.y, dz = d_w.z;
-	const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
-	float t = o_t.w;
-	const float max_step = min_stepsize() * (1 << (kCascades - 1));
-	uint32_t j = 0;
-	for (; j < n_steps; ++j) {
-		float* rec = records + (size_t)(i + j * n_alive) * stride;
-		float px, py, pz, dt;
-		bool left = false;
-		while (true) {
-			px = fmaf(dx, t, ox); py = fmaf(dy, t, oy); pz = fmaf(dz, t, oz);
-			if (!aabb_contains(a.render_aabb, px, py, pz)) {
-				left = true;
-				break;
-			}
-			dt = calc_dt(t, a.cone_angle);
-			const uint32_t mip = max(a.min_mip, (uint32_t)mip_from_dt(dt, px, py, pz));
-			if (!a.bitfield || occupied_at(px, py, pz, a.bitfield, mip)) break;
-			t = advance_to_next_voxel(t, a.cone_angle, px, py, pz, dx, dy, dz, ix, iy, iz, kGrid >> mip);
-		}
-		if (left) {
-			rec[4] = -1.0f;
-			break;
-		}
-		// warp_position(pos, train_aabb) = (pos - min) / diag
-		const float wx = (px - a.train_aabb[0]) / (a.train_aabb[3] - a.train_aabb[0]);
-		const float wy = (py - a.train_aabb[1]) / (a.train_aabb[4] - a.train_aabb[1]);
-		const float wz = (pz - a.train_aabb[2]) / (a.train_aabb[5] - a.train_aabb[2]);
-		rec[0] = wx; rec[1] = wy; rec[2] = wz;
-		rec[3] = (dt - min_stepsize()) / (max_step - min_stepsize());  // warp_dt
-		rec[4] = frame_id;
-		rec[5] = wx; rec[6] = wy; rec[7] = wz;
-		rec[8] = (dx + 1.0f) * 0.5f; rec[9] = (dy + 1.0f) * 0.5f; rec[10] = (dz + 1.0f) * 0.5f;
-		for (uint32_t e = 0; e < n_extra; ++e) rec[11 + e] = extra_dims ? extra_dims[e] : 0.0f;
-		t += dt;
+	extern __shared__ float march_smem[];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	float* tile = march_smem + (size_t)warp * 32u * stride;
+	const uint32_t i0 = blockIdx.x * blockDim.x + warp * 32u;
+	if (i0 >= n_alive) return;
+	const uint32_t cnt = min(32u, n_alive - i0);
+	const uint32_t i = i0 + lane;
+	const bool mine = lane < cnt;
+	float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f, t = 0.f;
+	if (mine) {
+		const float4 o_t = rays.o_t[i], d_w = rays.d_w[i];
+		ox = o_t.x; oy = o_t.y; oz = o_t.z; dx = d_w.x; dy = d_w.y; dz = d_w.z;
+		t = o_t.w;
 	}
-	// steps after the one where the ray left the box are never composited; mark them as padding
-	for (uint32_t k = j + 1; k < n_steps; ++k) records[(size_t)(i + k * n_alive) * stride + 4] = -1.0f;
-	rays.o_t[i].w = t;
-	rays.meta[i].y = (rays.meta[i].y & 0xffff0000u) | j;  // low half: steps generated in this round (payload.n_steps)
+	const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+	const float max_step = min_stepsize() * (1 << (kCascades - 1));
+	float* my = tile + (size_t)lane * stride;
+	for (uint32_t e = 0; e < stride; ++e) my[e] = 0.0f;
+	if (mine) {
+		my[8] = (dx + 1.0f) * 0.5f; my[9] = (dy + 1.0f) * 0.5f; my[10] = (dz + 1.0f) * 0.5f;
+		for (uint32_t e = 0; e < n_extra; ++e) my[11 + e] = extra_dims ? extra_dims[e] : 0.0f;
+	}
+	uint32_t steps = 0;   // samples this ray generated in this round
+	bool left = !mine;    // steps after the one where the ray left the box are never composited: holder = -1 marks them as padding
+	for (uint32_t j = 0; j < n_steps; ++j) {
+		if (!left) {
+			float px, py, pz, dt;
+			while (true) {
+				px = fmaf(dx, t, ox); py = fmaf(dy, t, oy); pz = fmaf(dz, t, oz);
+				if (!aabb_contains(a.render_aabb, px, py, pz)) {
+					left = true;
+					break;
+				}
+				dt = calc_dt(t, a.cone_angle);
+				const uint32_t mip = max(a.min_mip, (uint32_t)mip_from_dt(dt, px, py, pz));
+				if (!a.bitfield || occupied_at(px, py, pz, a.bitfield, mip)) break;
+				t = advance_to_next_voxel(t, a.cone_angle, px, py, pz, dx, dy, dz, ix, iy, iz, kGrid >> mip);
+			}
+			if (!left) {
+				// warp_position(pos, train_aabb) = (pos - min) / diag
+				const float wx = (px - a.train_aabb[0]) / (a.train_aabb[3] - a.train_aabb[0]);
+				const float wy = (py - a.train_aabb[1]) / (a.train_aabb[4] - a.train_aabb[1]);
+				const float wz = (pz - a.train_aabb[2]) / (a.train_aabb[5] - a.train_aabb[2]);
+				my[0] = wx; my[1] = wy; my[2] = wz;
+				my[3] = (dt - min_stepsize()) / (max_step - min_stepsize());  // warp_dt
+				my[4] = frame_id;
+				my[5] = wx; my[6] = wy; my[7] = wz;
+				t += dt;
+				++steps;
+			}
+		}
+		if (left) my[4] = -1.0f;
+		__syncwarp();
+		float* dst = records + (size_t)(i0 + j * n_alive) * stride;
+		for (uint32_t k = lane; k < cnt * stride; k += 32) dst[k] = tile[k];
+		__syncwarp();
+	}
+	if (mine) {
+		rays.o_t[i].w = t;
+		rays.meta[i].y = (rays.meta[i].y & 0xffff0000u) | steps;  // low half: steps generated in this round (payload.n_steps)
+	}
 }
 
 __device__ __forceinline__ float logistic(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -361,8 +381,10 @@ int tracer_generate(insta_ctx* ctx, float* d_records, uint32_t stride, uint32_t 
 	if (n_records) *n_records = t->n_alive * n_steps;
 	if (t->n_alive == 0) return INSTA_OK;
 	if (stride < 11) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_generate_samples: stride < 11");
-	nerf_march_kernel<<<(t->n_alive + 127) / 128, 128, 0, s>>>(t->args, t->set[t->cur], t->n_alive, d_records, stride, n_steps, (float)frame_id, d_extra_dims,
-	                                                           stride - 11);
+	const size_t march_smem = (size_t)4 * 32 * stride * sizeof(float);
+	if (march_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(nerf_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem));
+	nerf_march_kernel<<<(t->n_alive + 127) / 128, 128, march_smem, s>>>(t->args, t->set[t->cur], t->n_alive, d_records, stride, n_steps, (float)frame_id,
+	                                                                    d_extra_dims, stride - 11);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
