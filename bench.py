@@ -27,6 +27,9 @@ STRIDE = 27
 BYTES_DEFORM = 1012
 BYTES_DEFORM_BLEND = 1300
 BYTES_ENCODE = 2316
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4,194,304-sample batch, from `ncu --set full` captures of this command
+# (profiles/r1_deform_wq_v5_ncu_summary.txt; the hash kernel has no capture of its tiled version yet -> null)
+NCU_TRAFFIC_BYTES = {"deform_kernel": 1016225000, "hash_fwd_kernel": None}
 METRIC = "deformed+encoded samples/s (BVH+TBN+hash)"
 UNIT = "samples/s"
 
@@ -349,7 +352,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (453 MB records + 1.07 GB encodings per step, fresh record buffer each step)",
                        "timing": "CUDA events on the launching stream around the K timed steps (per-kernel events inside apportion it), max over ranks"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
+                         "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full, profiles/r1_deform_wq_v5_ncu_summary.txt" if NCU_TRAFFIC_BYTES.get(dom) else None,
+                         "algorithmic_bytes": dom_bytes, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
                          "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},
             "kernels_ms": {"deform_kernel": float(t_deform.mean()), "hash_fwd_kernel": float(t_encode.mean())},
             "l2_gather_roofline": None if not gather or "error" in gather else dict(gather, **{
@@ -667,10 +671,28 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner at communicator creation) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import io
+    import contextlib
+
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    out = buf.getvalue().strip()
+    if out:
+        lines = out.split("\n")
+        for extra in lines[:-1]:
+            print(extra, file=sys.stderr)
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":
