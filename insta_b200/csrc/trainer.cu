@@ -211,6 +211,10 @@ int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
 	if ((e = cudaHostAlloc(&t->h_counters, sizeof(uint32_t) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail(e);
 	// the reference's arena memory is not cleared either, but stale records must at least be finite for the first step's kernels
 	if ((e = cudaMemset(t->coords, 0, sizeof(float) * (size_t)max_samples * stride)) != cudaSuccess) return fail(e);
+	// a step that accepts no ray leaves the compacted batch untouched (the reference's fill_rollover divides by zero there): zero records and
+	// zero loss gradients then give zero parameter gradients instead of whatever the allocation held
+	if ((e = cudaMemset(t->coords_compacted, 0, sizeof(float) * (size_t)target * stride)) != cudaSuccess) return fail(e);
+	if ((e = cudaMemset(t->dloss, 0, 2 * (size_t)target * kOutWidth)) != cudaSuccess) return fail(e);
 	ctx->trainer = t;
 	return INSTA_OK;
 }

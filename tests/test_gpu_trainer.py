@@ -169,3 +169,21 @@ def test_train_requires_trainer_and_images(gpu_ctx):
     S = State(gpu_ctx)
     with pytest.raises(capi.InstaError):
         gpu_ctx.train_nerf(S.optimizer(gpu_ctx), torch.zeros(1 << 21, dtype=torch.uint8, device="cuda"), torch.zeros((2, 16), device="cuda"), torch.zeros(1, device="cuda"))
+
+
+def test_step_without_occupied_cells_is_harmless(train_ctx, dataset):
+    """an empty occupancy grid accepts no ray: the step must report zero samples and leave the weights finite (the reference stops training there)"""
+    import torch
+
+    ctx = train_ctx
+    dev, bf, extra = dataset
+    S = State(ctx)
+    before = S.p32.clone()
+    ctx.trainer_create(target_batch_size=TARGET, rays_per_batch=512)
+    st = ctx.train_nerf(S.optimizer(ctx), torch.zeros_like(bf), extra, torch.tensor([0.02], device="cuda"), get_loss_scalar=True)
+    torch.cuda.synchronize()
+    assert st["n_rays_accepted"] == 0 and st["measured_batch_size"] == 0 and st["measured_batch_size_before_compaction"] == 0 and st["loss"] == 0.0
+    assert st["rays_per_batch"] == 512  # unchanged, as update_after_training returns early
+    assert bool(torch.isfinite(S.p32).all())
+    assert float((S.p32[25600:] - before[25600:]).abs().max()) == 0.0  # untouched grid entries are not updated (adam.h:75-79)
+    ctx.trainer_destroy()
