@@ -40,6 +40,8 @@ def build(force=False, verbose=False):
         common += ["-Xptxas", "-v"]
     if os.environ.get("INSTA_TUNE"):  # extra kernel variants for A/B measurements (tools/tune_deform.py)
         common += ["-DINSTA_TUNE"]
+    if os.environ.get("INSTA_WQ_SLOTS"):
+        common += ["-DINSTA_WQ_SLOTS=" + os.environ["INSTA_WQ_SLOTS"]]
     procs = []
     for s in srcs:
         o = os.path.join(LIB_DIR, os.path.basename(s) + ".o")
