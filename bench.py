@@ -161,7 +161,14 @@ def cpu_reference_leg(verts, faces, masks, frame_verts, n_sample, steps, warmup,
         if it >= warmup:
             times.append(t1 - t0)
     total = float(np.sum(times))
-    return {"value": n_sample * len(times) / total, "unit": UNIT, "cores": int(threads), "kind": kind,
+    # one host thread on a 1/8 slice (SURVEY.md 8d config 1 asks for both figures)
+    n1 = max(1024, n_sample // 8)
+    rec = rec0[:n1].copy()
+    t0 = time.perf_counter()
+    W.warp(rec, STRIDE, -1 if regime != "render" else 0, nodes, tbvh, ttopo, canon, adj, unit, n_threads=1)
+    O.grid_forward(rec, STRIDE, layout, table, n_threads=1)
+    single = n1 / (time.perf_counter() - t0)
+    return {"value": n_sample * len(times) / total, "single_thread_value": single, "unit": UNIT, "cores": int(threads), "kind": kind,
             "sample": "%d of the %d records per step x %d steps, same seed/regime; stage 1 = %s, stage 2 = CPU restatement of kernel_grid" % (
                 n_sample, N_SAMPLES, len(times), "reference host code (libref_host.so)" if kind == "reference" else "oracle port")}, total / len(times)
 
@@ -356,6 +363,7 @@ def run_ours(args):
                          "algorithmic_bytes": dom_bytes, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
                          "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},
             "kernels_ms": {"deform_kernel": float(t_deform.mean()), "hash_fwd_kernel": float(t_encode.mean())},
+            "step_ms_percentiles": {"p10": float(np.percentile(step_ms, 10)), "p50": float(np.percentile(step_ms, 50)), "p90": float(np.percentile(step_ms, 90))},
             "l2_gather_roofline": None if not gather or "error" in gather else dict(gather, **{
                 "hash_fwd_gathered_gbs": 2048 * N_SAMPLES / (float(t_encode.mean()) * 1e-3) / 1e9,
                 "hash_fwd_frac": 2048 * N_SAMPLES / (float(t_encode.mean()) * 1e-3) / 1e9 / gather["l2_16B_gbs"],

@@ -119,6 +119,11 @@ INSTA_API int insta_get_frame_bvh_order(const insta_ctx* ctx, int32_t frame, uin
  * d_coords must be 16-byte aligned. */
 INSTA_API int insta_deform_samples(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id,
                                    int32_t* d_tri_ids, insta_stream stream);
+/* Same with the record count on the DEVICE: only min(n_max, *d_n_valid) records are processed (d_n_valid NULL = n_max).  For callers whose
+ * sample count is produced by a kernel (generate_training_samples_nerf's counter): no host round trip, where the reference deforms
+ * `max_inference` records -- last step's count rounded up (ngp/src/testbed_nerf.cu:3217-3222, 3290). */
+INSTA_API int insta_deform_samples_n(insta_ctx* ctx, float* d_coords, uint32_t n_max, const uint32_t* d_n_valid, uint32_t stride_floats, int32_t frame_id,
+                                     int32_t* d_tri_ids, insta_stream stream);
 /* Replaces the 3-row path of surface_closest_point (kernel `warp_random_samples`, core.cu:528-579, 639-655; called
  * at testbed_nerf.cu:2850 for the occupancy-grid refresh).  d_xyz: n x 3 floats in place.  d_frame_ids NULL = draw
  * the frame per point exactly as the reference: pcg32(rng_seed).advance(i*(n_frames-1)).next_float()*(n_frames-1). */
@@ -226,6 +231,9 @@ INSTA_API uint32_t insta_network_n_params(const insta_ctx* ctx); /* 25,600 + gri
 INSTA_API int insta_network_inference(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_out_f16,
                                       uint32_t out_stride_elems, insta_stream stream);
 
+/* insta_network_inference over min(n_max, *d_n_valid) records (d_n_valid: device pointer, NULL = n_max) */
+INSTA_API int insta_network_inference_n(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n_max, const uint32_t* d_n_valid,
+                                        const void* d_params_f16, void* d_out_f16, uint32_t out_stride_elems, insta_stream stream);
 /* NerfNetwork::density (nerf_network.h:385-414): hash grid + density MLP on bare positions (d_xyz[i * stride_floats + {0,1,2}]), expression
  * inputs all 1 (extract_expressions_random, nerf_network.h:108-128); one fp16 density logit per sample. */
 INSTA_API int insta_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_logits_f16,

@@ -126,7 +126,7 @@ EXPORTS = [
     "insta_params_default", "insta_last_error", "insta_version", "insta_ctx_create", "insta_ctx_destroy",
     "insta_set_canonical", "insta_load_canonical_obj", "insta_add_frame", "insta_add_frames", "insta_add_frame_obj",
     "insta_clear_frames", "insta_n_frames", "insta_get_render_aabb", "insta_set_aabb", "insta_get_topology",
-    "insta_get_frame_bvh_order", "insta_deform_samples", "insta_deform_points", "insta_grid_layout", "insta_grid_n_params",
+    "insta_get_frame_bvh_order", "insta_deform_samples", "insta_deform_samples_n", "insta_network_inference_n", "insta_deform_points", "insta_grid_layout", "insta_grid_n_params",
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
@@ -287,6 +287,12 @@ class Context:
             self._check(self.lib.insta_deform_points(self.h, _dev(coords), C.c_uint32(n), None, _dev(tri_ids), _stream(stream)))
         else:
             self._check(self.lib.insta_deform_samples(self.h, _dev(coords), C.c_uint32(n), C.c_uint32(m), C.c_int32(-1), _dev(tri_ids), _stream(stream)))
+        return coords
+
+    def surface_closest_point_n(self, coords, n_valid, tri_ids=None, frame_id=-1, stream=None):
+        """like surface_closest_point, the record count comes from the device tensor n_valid (uint32 / int32, 1 element)"""
+        n, stride = coords.shape
+        self._check(self.lib.insta_deform_samples_n(self.h, _dev(coords), C.c_uint32(n), _dev(n_valid), C.c_uint32(stride), C.c_int32(frame_id), _dev(tri_ids), _stream(stream)))
         return coords
 
     def render_deformed(self, coords, frame_id, tri_ids=None, stream=None):
@@ -465,6 +471,11 @@ class Context:
         n = records.shape[0] if n is None else n
         self._check(self.lib.insta_network_inference(self.h, _dev(records), C.c_uint32(records.shape[1]), C.c_uint32(n), _dev(params), _dev(out),
                                                      C.c_uint32(out_stride), _stream(stream)))
+        return out
+
+    def network_inference_n(self, records, n_valid, params, out, out_stride=0, stream=None):
+        self._check(self.lib.insta_network_inference_n(self.h, _dev(records), C.c_uint32(records.shape[1]), C.c_uint32(records.shape[0]), _dev(n_valid), _dev(params),
+                                                       _dev(out), C.c_uint32(out_stride), _stream(stream)))
         return out
 
     def network_density(self, xyz, params, logits, stream=None):

@@ -393,6 +393,11 @@ int insta_get_frame_bvh_order(const insta_ctx* ctx, int32_t frame, uint32_t* h_t
 // ---------------------------------------------------------------------------------------------------------------
 int insta_deform_samples(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id, int32_t* d_tri_ids,
                          insta_stream stream) {
+	return insta_deform_samples_n(ctx, d_coords, n, nullptr, stride_floats, frame_id, d_tri_ids, stream);
+}
+
+int insta_deform_samples_n(insta_ctx* ctx, float* d_coords, uint32_t n, const uint32_t* d_n_valid, uint32_t stride_floats, int32_t frame_id, int32_t* d_tri_ids,
+                           insta_stream stream) {
 	if (!ctx || (!d_coords && n)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_samples: bad arguments");
 	const uint32_t extra = ctx->p.exp_params + ctx->p.geo_params;
 	if (stride_floats < 11 + extra) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_samples: stride smaller than NerfCoordinate + extra dims");
@@ -400,7 +405,7 @@ int insta_deform_samples(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t s
 	if (frame_id < -1) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_samples: frame_id must be >= -1");
 	int rc = sync_frame_table(ctx, (cudaStream_t)stream);
 	if (rc) return rc;
-	return launch_deform(ctx, d_coords, n, stride_floats, frame_id, nullptr, false, d_tri_ids, (cudaStream_t)stream);
+	return launch_deform(ctx, d_coords, n, stride_floats, frame_id, nullptr, false, d_tri_ids, (cudaStream_t)stream, d_n_valid);
 }
 
 int insta_deform_points(insta_ctx* ctx, float* d_xyz, uint32_t n, const int32_t* d_frame_ids, int32_t* d_tri_ids, insta_stream stream) {
@@ -635,12 +640,17 @@ uint32_t insta_network_n_params(const insta_ctx* ctx) { return ctx ? network_n_p
 
 int insta_network_inference(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_out_f16,
                             uint32_t out_stride_elems, insta_stream stream) {
+	return insta_network_inference_n(ctx, d_records, stride_floats, n, nullptr, d_params_f16, d_out_f16, out_stride_elems, stream);
+}
+
+int insta_network_inference_n(insta_ctx* ctx, const float* d_records, uint32_t stride_floats, uint32_t n, const uint32_t* d_n_valid, const void* d_params_f16,
+                              void* d_out_f16, uint32_t out_stride_elems, insta_stream stream) {
 	if (!ctx || ((!d_records || !d_params_f16 || !d_out_f16) && n)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: bad arguments");
 	if (stride_floats < 11 + ctx->p.exp_params + ctx->p.geo_params) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: stride smaller than NerfCoordinate + extra dims");
 	if (reinterpret_cast<uintptr_t>(d_params_f16) % 16u) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: parameters must be 16-byte aligned");
 	if (ctx->p.n_levels != 16 || ctx->p.n_features_per_level != 8) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: the density MLP expects 16 levels x 8 features");
 	if (out_stride_elems != 0 && out_stride_elems < n) INSTA_FAIL(INSTA_ERR_INVALID, "insta_network_inference: out_stride_elems < n");
-	return launch_network_fwd(ctx, d_records, stride_floats, n, d_params_f16, d_out_f16, out_stride_elems, (cudaStream_t)stream);
+	return launch_network_fwd(ctx, d_records, stride_floats, n, d_params_f16, d_out_f16, out_stride_elems, (cudaStream_t)stream, d_n_valid);
 }
 
 int insta_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_logits_f16, insta_stream stream) {

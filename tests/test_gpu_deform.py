@@ -219,3 +219,31 @@ def test_full_size_batch_properties(arith_pair, scene):
     assert (t[sub] == want_tri).all()
     got = d.cpu().numpy()[sub]
     assert np.abs(got[:, 0:3] - want[:, 0:3]).max() < POS_TOL_BLEND
+
+
+def test_device_side_count(gpu_ctx, scene):
+    """insta_deform_samples_n / insta_network_inference_n: only min(n_max, *d_n_valid) records are touched"""
+    import torch
+
+    from insta_b200 import synth
+
+    n, k = 6000, 2500
+    rec = scene.golden_records(n, seed=21)
+    a, b = torch.from_numpy(rec.copy()).cuda(), torch.from_numpy(rec.copy()).cuda()
+    ta, tb = torch.full((n,), -7, dtype=torch.int32, device="cuda"), torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    gpu_ctx.surface_closest_point(a[:k], ta[:k])
+    gpu_ctx.surface_closest_point_n(b, torch.tensor([k], dtype=torch.int32, device="cuda"), tb)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32)) and torch.equal(ta, tb)
+    assert bool((tb[k:] == -7).all()) and torch.equal(b[k:].view(torch.int32), torch.from_numpy(rec[k:].copy()).cuda().view(torch.int32))
+    gpu_ctx.surface_closest_point_n(b, torch.tensor([10 * n], dtype=torch.int32, device="cuda"), tb)  # count above n_max: clamped
+    gpu_ctx.surface_closest_point(a[k:], ta[k:])
+    torch.cuda.synchronize()
+    assert torch.equal(ta, tb)
+    params = torch.from_numpy(synth.make_network_params(gpu_ctx.network_n_params, seed=2)).cuda()
+    o1 = torch.zeros((n, 4), dtype=torch.float16, device="cuda")
+    o2 = torch.zeros((n, 4), dtype=torch.float16, device="cuda")
+    gpu_ctx.network_inference(a[:k], params, o1[:k])
+    gpu_ctx.network_inference_n(a, torch.tensor([k], dtype=torch.int32, device="cuda"), params, o2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2) and float(o2[k:].abs().sum()) == 0.0 and float(o2[:k].abs().sum()) > 0
