@@ -236,10 +236,12 @@ def test_device_side_count(gpu_ctx, scene):
     torch.cuda.synchronize()
     assert torch.equal(a.view(torch.int32), b.view(torch.int32)) and torch.equal(ta, tb)
     assert bool((tb[k:] == -7).all()) and torch.equal(b[k:].view(torch.int32), torch.from_numpy(rec[k:].copy()).cuda().view(torch.int32))
-    gpu_ctx.surface_closest_point_n(b, torch.tensor([10 * n], dtype=torch.int32, device="cuda"), tb)  # count above n_max: clamped
-    gpu_ctx.surface_closest_point(a[k:], ta[k:])
+    c, d = torch.from_numpy(rec.copy()).cuda(), torch.from_numpy(rec.copy()).cuda()
+    tc, td = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+    gpu_ctx.surface_closest_point_n(c, torch.tensor([10 * n], dtype=torch.int32, device="cuda"), tc)  # count above n_max: clamped
+    gpu_ctx.surface_closest_point(d, td)
     torch.cuda.synchronize()
-    assert torch.equal(ta, tb)
+    assert torch.equal(tc, td) and torch.equal(c.view(torch.int32), d.view(torch.int32))
     params = torch.from_numpy(synth.make_network_params(gpu_ctx.network_n_params, seed=2)).cuda()
     o1 = torch.zeros((n, 4), dtype=torch.float16, device="cuda")
     o2 = torch.zeros((n, 4), dtype=torch.float16, device="cuda")
