@@ -66,6 +66,7 @@ __device__ __forceinline__ void image_pos_training(Pcg32& rng, const ImageDev& i
 	py = (uint32_t)max(min((int)(y * ry), (int)im.res[1] - 1), 0);
 }
 
+constexpr uint32_t kGenKeep = 64;  // ray parameters kept from the counting march (32 KB of shared memory per 128-thread CTA)
 struct GenArgs {
 	uint32_t n_rays, n_rays_total, max_samples, n_images, stride, n_extra;
 	uint64_t rng_state, rng_inc;
@@ -119,7 +120,10 @@ __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
 	const float startt = fmaf(calc_dt(tmin, a.cone_angle), rng.next_float(), tmin);
 	const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
 
-	// first march: number of occupied samples
+	// first march: number of occupied samples; the ray parameters of the first kGenKeep of them are kept (shared memory, [step][thread]) so
+	// that the emit loop below re-marches only the rays that are longer than that
+	__shared__ float t_keep[kGenKeep * 128];
+	float t_resume = 0.f;
 	uint32_t j = 0;
 	float t = startt;
 	while (j < kNerfSteps) {
@@ -128,8 +132,10 @@ __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
 		const float dt = calc_dt(t, a.cone_angle);
 		const uint32_t mip = (uint32_t)mip_from_dt(dt, qx, qy, qz);
 		if (occupied_at(qx, qy, qz, a.bitfield, mip)) {
+			if (j < kGenKeep) t_keep[j * 128u + threadIdx.x] = t;
 			++j;
 			t += dt;
+			if (j == kGenKeep) t_resume = t;
 		} else {
 			t = advance_to_next_voxel(t, a.cone_angle, qx, qy, qz, dx, dy, dz, ix, iy, iz, kGrid >> mip);
 		}
@@ -152,8 +158,13 @@ __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
 	// second march: only the ray parameter t and the ray's slot per sample (8 bytes); train_emit_kernel expands them into records with
 	// coalesced stores.  (Writing the 27 floats from here costs 27 store instructions per sample, each touching 32 different lines.)
 	float* rec = a.coords + (size_t)base * a.stride;
-	t = startt;
-	j = 0;
+	const uint32_t kept = min(numsteps, kGenKeep);
+	for (j = 0; j < kept; ++j) {
+		rec[0] = t_keep[j * 128u + threadIdx.x];
+		reinterpret_cast<uint32_t*>(rec)[1] = ray_idx;
+		rec += a.stride;
+	}
+	t = t_resume;
 	while (j < numsteps) {
 		const float qx = fmaf(t, dx, ox), qy = fmaf(t, dy, oy), qz = fmaf(t, dz, oz);
 		if (!aabb_contains(a.aabb, qx, qy, qz)) break;
