@@ -73,6 +73,70 @@ public:
 	}
 	uint32_t grid_n_params() const { return insta_grid_n_params(m_ctx); }
 
+	// ngp::NerfNetwork<__half>: inference_mixed_precision_impl / density / forward + backward (ngp nerf_network.h:159-232, 385-414, 238-383)
+	uint32_t network_n_params() const { return insta_network_n_params(m_ctx); }
+	void network_inference(const float* d_records, uint32_t floats_per_coord, uint32_t n, const void* d_params_f16, void* d_rgbsigma_f16, uint32_t out_stride_elems,
+	                       void* stream) {
+		check(insta_network_inference(m_ctx, d_records, floats_per_coord, n, d_params_f16, d_rgbsigma_f16, out_stride_elems, stream));
+	}
+	void network_density(const float* d_xyz, uint32_t stride_floats, uint32_t n, const void* d_params_f16, void* d_logits_f16, void* stream) {
+		check(insta_network_density(m_ctx, d_xyz, stride_floats, n, d_params_f16, d_logits_f16, stream));
+	}
+	void network_forward_backward(const float* d_records, uint32_t floats_per_coord, uint32_t n, const void* d_params_f16, const void* d_dloss_f16, uint32_t dloss_width,
+	                              void* d_gradients_f16, void* d_out_f16, void* stream) {
+		check(insta_network_forward_backward(m_ctx, d_records, floats_per_coord, n, d_params_f16, d_dloss_f16, dloss_width, d_gradients_f16, d_out_f16, stream));
+	}
+
+	// Testbed::render_nerf -> NerfTracer (ngp/src/testbed_nerf.cu:2320-2440, 2030-2244) for frame `target_deform_frame`
+	insta_render_stats render_nerf(const insta_camera& cam, const insta_render_opts& opts, int32_t target_deform_frame, const void* d_params_f16,
+	                               const float* d_extra_dims, float* d_frame_rgba, float* d_frame_depth, void* stream) {
+		insta_render_stats st{};
+		check(insta_render_frame(m_ctx, &cam, &opts, target_deform_frame, d_params_f16, d_extra_dims, d_frame_rgba, d_frame_depth, &st, stream));
+		return st;
+	}
+
+	// Testbed::load_nerf -> metadata_gpu / transforms_gpu (testbed_nerf.cu:2698-2760)
+	void set_training_images(const insta_train_image* images, uint32_t n) { check(insta_training_set_images(m_ctx, images, n)); }
+	// Testbed::train_nerf (testbed_nerf.cu:2916-2992): one step; returns the counters update_after_training would have set
+	void create_trainer(const insta_trainer_config& cfg) { check(insta_trainer_create(m_ctx, &cfg)); }
+	insta_train_stats train_nerf(const insta_optimizer& opt, const void* d_density_grid_bitfield, const float* d_extra_dims, const float* d_density_grid_mean,
+	                             bool get_loss_scalar, void* stream) {
+		insta_train_stats st{};
+		check(insta_train_nerf(m_ctx, &opt, d_density_grid_bitfield, d_extra_dims, d_density_grid_mean, get_loss_scalar ? 1 : 0, &st, stream));
+		return st;
+	}
+	// Testbed::training_prep_nerf / update_density_grid_nerf / update_density_grid_mean_and_bitfield (testbed_nerf.cu:3428-3444, 2774-2878)
+	bool training_prep_nerf(insta_density_grid& grid, const void* d_params_f16, void* stream) {
+		int did = 0;
+		check(insta_training_prep_nerf(m_ctx, &grid, d_params_f16, &did, stream));
+		return did != 0;
+	}
+	void update_density_grid_nerf(insta_density_grid& grid, const void* d_params_f16, uint32_t n_uniform, uint32_t n_nonuniform, void* stream) {
+		check(insta_update_density_grid(m_ctx, &grid, d_params_f16, n_uniform, n_nonuniform, stream));
+	}
+	void update_density_grid_mean_and_bitfield(const insta_density_grid& grid, void* stream) {
+		check(insta_update_density_grid_mean_and_bitfield(m_ctx, &grid, stream));
+	}
+	// data-parallel training (no counterpart in the single-GPU reference)
+	void init_communicator(int world_size, int rank, const void* nccl_unique_id_128) { check(insta_comm_init_rank(m_ctx, world_size, rank, nccl_unique_id_128)); }
+
+	// Testbed::save_snapshot / load_snapshot (ngp/src/testbed.cu:2916-3016); host buffers
+	static void save_snapshot(const std::string& path, const insta_params* p, const insta_snapshot& s) { check(insta_snapshot_save(path.c_str(), p, &s)); }
+	struct LoadedSnapshot {
+		insta_snapshot_file* file = nullptr;
+		insta_snapshot data{};
+		LoadedSnapshot() = default;
+		LoadedSnapshot(const LoadedSnapshot&) = delete;
+		LoadedSnapshot& operator=(const LoadedSnapshot&) = delete;
+		LoadedSnapshot(LoadedSnapshot&& o) noexcept : file(o.file), data(o.data) { o.file = nullptr; }
+		~LoadedSnapshot() { insta_snapshot_close(file); }
+	};
+	static LoadedSnapshot load_snapshot(const std::string& path) {
+		LoadedSnapshot l;
+		check(insta_snapshot_open(path.c_str(), &l.file, &l.data));
+		return l;
+	}
+
 	static void check(int status) {
 		if (status != INSTA_OK) throw std::runtime_error(std::string("insta_b200: ") + insta_last_error());
 	}

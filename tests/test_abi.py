@@ -59,3 +59,47 @@ def test_product_never_imports_oracle():
         for f in fs:
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 assert "oracle" not in open(os.path.join(dp, f), errors="ignore").read().lower(), f
+
+
+def test_hooks_adapter_compiles_and_links(tmp_path):
+    """include/insta_b200_hooks.hpp (the C++ adapter a maintainer includes from src/core.cu) must compile as plain C++14 -- the reference's standard --
+    and link against the library: a snapshot round trip through it needs no GPU."""
+    import shutil
+    import subprocess
+
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not cxx:
+        pytest.skip("no host C++ compiler")
+    src = tmp_path / "use_hooks.cpp"
+    src.write_text(r"""
+#include <insta_b200_hooks.hpp>
+#include <cstdio>
+#include <vector>
+int main(int argc, char** argv) {
+	std::vector<unsigned short> params(1024, 0x3c00);
+	insta_snapshot s{};
+	s.n_params = params.size();
+	s.h_params_f16 = params.data();
+	s.training_step = 42;
+	s.aabb[3] = s.aabb[4] = s.aabb[5] = 1.f;
+	s.render_aabb[3] = s.render_aabb[4] = s.render_aabb[5] = 1.f;
+	insta::Hooks::save_snapshot(argv[1], nullptr, s);
+	auto l = insta::Hooks::load_snapshot(argv[1]);
+	if (l.data.n_params != 1024 || l.data.training_step != 42) return 1;
+	try {
+		insta::Hooks::load_snapshot("/nonexistent/file");
+		return 2;
+	} catch (const std::runtime_error& e) {
+		std::printf("%s\n", e.what());
+	}
+	insta::Hooks h;  // no context: never created without a GPU
+	return h.ctx() == nullptr ? 0 : 3;
+}
+""")
+    exe = tmp_path / "use_hooks"
+    lib_dir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call([cxx, "-std=c++14", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir, "-linsta_b200",
+                           "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe), str(tmp_path / "s.msgpack")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "cannot open" in out.stdout
