@@ -519,6 +519,19 @@ def train_leg(ctx, verts, fv, args, rank, world):
         torch.cuda.synchronize()
         tg.append(e0.elapsed_time(e1))
     ctx.trainer_destroy()
+    ar_ms = None
+    if world > 1:
+        # the exchange step alone: in-place fp16 sum of the gradient buffer over NCCL
+        ta = []
+        for k in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            e0.record()
+            ctx.grad_allreduce(grads)
+            e1.record()
+            torch.cuda.synchronize()
+            ta.append(e0.elapsed_time(e1))
+        ar_ms = float(np.mean(ta[2:]))
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -528,7 +541,8 @@ def train_leg(ctx, verts, fv, args, rank, world):
     return {"ms_per_step": ms, "ms_per_step_min": float(np.min(ts)), "steps_timed": len(ts), "warmup_steps": args.train_warmup, "target_batch_size": 1 << 18,
             "rays_per_step": last["n_rays"], "samples_generated": last["measured_batch_size_before_compaction"], "samples_compacted": last["measured_batch_size"],
             "aggregate_rays_per_s": world * last["n_rays"] / (ms * 1e-3), "loss": last["loss"], "images_per_gpu": n_img, "launches_per_step": launches / max(1, len(ts)),
-            "grad_allreduce": ("NCCL fp16 sum of %d halves per step" % n) if world > 1 else "none (1 GPU)",
+            "grad_allreduce": ("NCCL fp16 sum of %d halves per step" % n) if world > 1 else "none (1 GPU)", "grad_allreduce_ms": ar_ms,
+            "grad_allreduce_busbw_gbs": (2.0 * (world - 1) / world * n * 2 / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
             "grid_update_ms": {"first_256_steps (2^21 uniform points)": float(np.mean(tg_full[1:])), "later (2^19 + 2^19 points)": float(np.mean(tg[1:]))},
             "note": "insta_train_nerf: generate + deform + fused inference + loss/compaction + fused forward/backward (tcgen05) + Adam/EMA; one stream sync per step"}
 
