@@ -161,3 +161,34 @@ def test_network_forward_backward_vs_torch_autograd(gpu_ctx, scene, n):
     assert scale > 0
     assert float((got_grid - want_grid.float()).abs().max()) <= 3e-2 * scale
     assert int((got_grid != 0).sum()) > 1000
+
+
+def test_network_density_mode(gpu_ctx, scene):
+    """NerfNetwork::density (nerf_network.h:385-414): bare positions, expression inputs all 1.  Must equal channel 3 of the full inference on
+    records that carry the same positions and all-one expression dims (bit-for-bit: same encoder and density MLP), and the fp32 PyTorch
+    density within the network tolerance."""
+    import torch
+
+    from insta_b200 import synth
+
+    n = 128 * 21 + 5
+    rec_np = synth.make_records(n, scene.aabb, np.zeros(n, np.int32), seed=31)
+    rec_np[:, 11:27] = 1.0
+    rec = torch.from_numpy(rec_np).cuda()
+    p_np, shapes = make_params(gpu_ctx.network_n_params, seed=9)
+    params = torch.from_numpy(p_np).cuda()
+    full = torch.empty((n, 4), dtype=torch.float16, device="cuda")
+    gpu_ctx.network_inference(rec, params, full)
+    xyz = rec[:, :3].contiguous()
+    dens = torch.full((n,), float("nan"), dtype=torch.float16, device="cuda")
+    gpu_ctx.network_density(xyz, params, dens)
+    wide = torch.zeros((n, 7), device="cuda")  # a wider stride than 3 floats
+    wide[:, :3] = xyz
+    dens2 = torch.empty(n, dtype=torch.float16, device="cuda")
+    gpu_ctx.network_density(wide, params, dens2)
+    torch.cuda.synchronize()
+    assert torch.equal(dens.view(torch.int16), full[:, 3].contiguous().view(torch.int16))
+    assert torch.equal(dens, dens2)
+    want = torch_reference(gpu_ctx, rec, params, shapes)[:, 3]
+    d = (dens.float() - want).abs()
+    assert bool((d <= 2e-3 + 0.01 * want.abs()).all()), float(d.max())
