@@ -624,7 +624,20 @@ def network_leg(ctx, rec_np, args):
         if k >= 3:
             ts.append(e0.elapsed_time(e1))
     ms = float(np.mean(ts))
-    return {"ms": ms, "samples_per_s": rec.shape[0] / (ms * 1e-3), "tflops": rec.shape[0] * 51200 / (ms * 1e-3) / 1e12,
+    nb = 1 << 18
+    dl = torch.zeros((nb, 4), dtype=torch.float16, device="cuda")
+    dl[:] = 0.01
+    grads = torch.empty(ctx.network_n_params, dtype=torch.float16, device="cuda")
+    tb = []
+    for k in range(2 + 4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.network_forward_backward(rec[:nb], params, dl, grads)
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= 2:
+            tb.append(e0.elapsed_time(e1))
+    return {"ms": ms, "forward_backward_ms_2p18": float(np.mean(tb)), "samples_per_s": rec.shape[0] / (ms * 1e-3), "tflops": rec.shape[0] * 51200 / (ms * 1e-3) / 1e12,
             "gather_gbs": rec.shape[0] * 2048 / (ms * 1e-3) / 1e9, "note": "hash grid + density MLP + SH + colour MLP in one tcgen05 kernel, 4 halves out per sample"}
 
 
@@ -663,8 +676,51 @@ def ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args):
             ts_w.append(e[0].elapsed_time(e[1]))
             ts_g.append(e[1].elapsed_time(e[2]))
     ms = float(np.mean(ts_w) + np.mean(ts_g))
-    return {"value": N_SAMPLES / (ms * 1e-3), "unit": UNIT, "warp_ms": float(np.mean(ts_w)), "kernel_grid_ms": float(np.mean(ts_g)),
-            "note": "reference `warp` (src/core.cu:442) + kernel_grid (tcnn grid.h:138), nvcc 12.9 -arch=sm_100, identical device buffers"}
+    res = {"value": N_SAMPLES / (ms * 1e-3), "unit": UNIT, "warp_ms": float(np.mean(ts_w)), "kernel_grid_ms": float(np.mean(ts_g)),
+           "note": "reference `warp` (src/core.cu:442) + kernel_grid (tcnn grid.h:138), nvcc 12.9 -arch=sm_100, identical device buffers"}
+    # the reference's own network (ngp::NerfNetwork<__half> over tiny-cuda-nn, oracle/_ref/libref_net.so) on the same batch
+    try:
+        from oracle import pyrefnet
+
+        if pyrefnet.available():
+            from insta_b200 import synth
+
+            del buf
+            torch.cuda.empty_cache()
+            N = pyrefnet.RefNet()
+            params = torch.from_numpy(synth.make_network_params(N.n_params, seed=1337)).cuda()
+            N.set_params(params)
+            out16 = torch.empty((16, N_SAMPLES), dtype=torch.float16, device="cuda")
+            ts = []
+            for it in range(2 + 4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                N.inference(pristine, out16)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            res["network_inference_ms"] = float(np.mean(ts))
+            del out16
+            nb = 1 << 18
+            dl = torch.zeros((nb, 16), dtype=torch.float16, device="cuda")
+            dl[:, :4] = 0.01
+            o = torch.empty((nb, 16), dtype=torch.float16, device="cuda")
+            gr = torch.empty(N.n_params, dtype=torch.float16, device="cuda")
+            ts = []
+            for it in range(2 + 4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                N.forward_backward(pristine[:nb], dl, o, gr)
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            res["network_forward_backward_ms_2p18"] = float(np.mean(ts))
+            res["network_note"] = "ngp::NerfNetwork<__half>::inference_mixed_precision on the 4,194,304-record batch; forward + backward (Overwrite) on 2^18 records"
+    except Exception as e:
+        res["network_error"] = repr(e)
+    return res
 
 
 def main():
