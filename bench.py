@@ -518,6 +518,12 @@ def train_leg(ctx, verts, fv, args, rank, world):
         e1.record()
         torch.cuda.synchronize()
         tg.append(e0.elapsed_time(e1))
+    ref = None
+    if world == 1 and args.ref_cuda:
+        try:
+            ref = ref_train_leg(verts, fv[:n_img], dev, bf0, extra, p16, hist[-1]["n_rays"], mean_density, args)
+        except Exception as e:
+            ref = {"error": repr(e)}
     ctx.trainer_destroy()
     ar_ms = None
     if world > 1:
@@ -544,6 +550,7 @@ def train_leg(ctx, verts, fv, args, rank, world):
             "grad_allreduce": ("NCCL fp16 sum of %d halves per step" % n) if world > 1 else "none (1 GPU)", "grad_allreduce_ms": ar_ms,
             "grad_allreduce_busbw_gbs": (2.0 * (world - 1) / world * n * 2 / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
             "grid_update_ms": {"first_256_steps (2^21 uniform points)": float(np.mean(tg_full[1:])), "later (2^19 + 2^19 points)": float(np.mean(tg[1:]))},
+            "ref_cuda": ref,
             "note": "insta_train_nerf: generate + deform + fused inference + loss/compaction + fused forward/backward (tcgen05) + Adam/EMA; one stream sync per step"}
 
 
@@ -603,6 +610,77 @@ def stress_leg(args, rank, world):
          "device_memory_gb": torch.cuda.memory_allocated() / 1e9}
     ctx.close()
     return r
+
+
+def ref_train_leg(verts, frame_verts, dev_images, bitfield, extra, params16, n_rays, mean_density, args):
+    """The same training step composed from the REFERENCE's own CUDA code (oracle/_ref: generate_training_samples_nerf, `warp`, NerfNetwork inference,
+    compute_loss_kernel_train_nerf + roll-over, NerfNetwork forward + backward, tcnn Ema{Adam} step, counter read-back) in the order and with the record
+    counts of Testbed::train_nerf_step (testbed_nerf.cu:3170-3426: deformation and inference over `max_inference` = last step's sample count rounded up),
+    on the same images, frames, occupancy grid, ray count and (trained) parameters as our step above.  Reported beside ours; test infrastructure only."""
+    import torch
+
+    from oracle import pyoracle, pyrefcuda, pyrefnerf, pyrefnet
+
+    if not (pyrefcuda.available() and pyrefnerf.available() and pyrefnet.available()):
+        return {"unavailable": "oracle/_ref libraries (refcuda, refnerf, refnet) not all built"}
+    from insta_b200 import synth
+
+    O = pyoracle.Oracle()
+    vts, faces, regions = synth.load_canonical()
+    masks = synth.mask_ids_from_regions(faces, regions)
+    canon = O.build_triangles(vts, faces, masks)
+    adj = O.adjacency(faces, len(vts))
+    nodes, tbvh, ttopo = [], [], []
+    for v in frame_verts:
+        t = O.build_triangles(v, faces, masks, canon)
+        nn, tb = O.bvh_build(t)
+        nodes.append(nn); tbvh.append(tb); ttopo.append(t)
+    R = pyrefcuda.RefCuda()
+    R.upload_scene(nodes, tbvh, ttopo, canon, adj)
+    G = pyrefnerf.RefNerf()
+    G.train_set_images(dev_images)
+    N = pyrefnet.RefNet()
+    N.set_params(params16)
+    target, max_samples = 1 << 18, 16 << 18
+    coords = torch.zeros((max_samples, STRIDE), device="cuda")
+    counters = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ray_indices = torch.zeros(1 << 18, dtype=torch.int32, device="cuda")
+    rays = torch.zeros((1 << 18, 6), device="cuda")
+    numsteps = torch.zeros((1 << 18, 2), dtype=torch.int32, device="cuda")
+    out_cm = torch.zeros((max_samples, 16), dtype=torch.float16, device="cuda")
+    cc = torch.zeros((target, STRIDE), device="cuda")
+    dl = torch.zeros((target, 16), dtype=torch.float16, device="cuda")
+    out_cc = torch.zeros((target, 16), dtype=torch.float16, device="cuda")
+    loss = torch.zeros(1 << 18, device="cuda")
+    grads = torch.zeros(N.n_params, dtype=torch.float16, device="cuda")
+    unit = [0, 0, 0, 1, 1, 1]
+    max_inference, n_total, ts, gen = max_samples, 0, [], 0
+    for it in range(3 + args.ref_train_steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        N.set_params(params16)  # outside the timed region: every step sees the parameters our step saw (the reference's fresh Adam state would drift)
+        e0.record()
+        c = coords[:max_inference]
+        G.train_generate(n_rays, n_total, c, counters, ray_indices, rays, numsteps, bitfield, unit, extra, rng_advances=it)
+        R.warp(c, STRIDE, -1)
+        N.inference_cm(c, out_cm)
+        G.train_loss(n_rays, n_total, target, c, counters, ray_indices, rays, numsteps, out_cm, 16, cc, dl, loss, mean_density, unit, rng_advances=it)
+        N.forward_backward(cc, dl, out_cc, grads)
+        N.optimizer_step(128.0)
+        cnt = counters.cpu()  # Counters::update_after_training reads both counters back every step
+        e1.record()
+        torch.cuda.synchronize()
+        n_total += n_rays
+        gen = int(cnt[1])
+        if gen == 0:
+            break
+        max_inference = min((min(gen, max_samples) + 127) // 128 * 128, max_samples)
+        if it >= 3:
+            ts.append(e0.elapsed_time(e1))
+    if not ts:
+        return {"error": "the reference step generated no samples"}
+    return {"ms_per_step": float(np.mean(ts)), "ms_per_step_min": float(np.min(ts)), "steps_timed": len(ts), "rays_per_step": int(n_rays), "samples_generated": gen,
+            "samples_compacted": int(cnt[2]),
+            "note": "reference kernels / network / optimizer (nvcc 12.9 -arch=sm_100) composed as Testbed::train_nerf_step does, same scene, rays and parameters"}
 
 
 def network_leg(ctx, rec_np, args):
@@ -741,6 +819,7 @@ def main():
     ap.add_argument("--train-images", type=int, default=128, help="synthetic 512^2 training images (= frames) per GPU in the train-step leg")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-warmup", type=int, default=30)
+    ap.add_argument("--ref-train-steps", type=int, default=6)
     ap.add_argument("--stress", action="store_true", help="also run configs[4]: 2048^2 render, 4000 resident BVHs, 2^22-entry hash table")
     ap.add_argument("--stress-frames", type=int, default=4000)
     ap.add_argument("--stress-renders", type=int, default=4)

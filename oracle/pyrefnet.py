@@ -59,3 +59,12 @@ class RefNet:
         assert n % 128 == 0 and dloss_cm.shape == (n, self.out_width) and out_cm.shape == (n, self.out_width) and grads.numel() == self.n_params
         self._check(self.lib.refnet_forward_backward(C.c_void_p(records.data_ptr()), C.c_uint32(n), C.c_void_p(dloss_cm.data_ptr()), C.c_void_p(out_cm.data_ptr()),
                                                      C.c_void_p(grads.data_ptr()), self._s()), "forward_backward")
+
+    def inference_cm(self, records, out_cm):
+        """out_cm fp16 [n, out_width] (one row of out_width halves per sample, as train_nerf_step reads it)"""
+        n = records.shape[0]
+        assert n % 128 == 0 and out_cm.shape[1] == self.out_width and out_cm.shape[0] >= n
+        self._check(self.lib.refnet_inference_cm(C.c_void_p(records.data_ptr()), C.c_uint32(n), C.c_void_p(out_cm.data_ptr()), self._s()), "inference_cm")
+
+    def optimizer_step(self, loss_scale=128.0):
+        self._check(self.lib.refnet_optimizer_step(C.c_float(loss_scale), self._s()), "optimizer_step")

@@ -14,6 +14,7 @@
 #include <tiny-cuda-nn/common.h>
 #include <tiny-cuda-nn/gpu_matrix.h>
 #include <tiny-cuda-nn/gpu_memory.h>
+#include <tiny-cuda-nn/optimizer.h>
 
 #include <memory>
 #include <string>
@@ -25,6 +26,8 @@ using precision_t = network_precision_t;
 namespace {
 std::shared_ptr<NerfNetwork<precision_t>> g_net;
 GPUMemory<precision_t> g_params, g_grads;
+GPUMemory<float> g_params_fp32;
+std::shared_ptr<Optimizer<precision_t>> g_opt;
 uint32_t g_stride = 0;
 std::string g_err;
 }  // namespace
@@ -104,6 +107,38 @@ int refnet_forward_backward(const float* d_records, uint32_t n, const void* d_dl
 		auto ctx = g_net->forward(stream, in, &out, false, false);
 		g_net->backward(stream, *ctx, in, out, dl, nullptr, false, EGradientMode::Overwrite);
 		if (d_grads_f16) cudaMemcpyAsync(d_grads_f16, g_grads.data(), g_grads.get_bytes(), cudaMemcpyDeviceToDevice, stream);
+		return 0;
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return -1;
+	}
+}
+
+// inference with the column-major output train_nerf_step uses ([padded_output_width] halves per sample, testbed_nerf.cu:3225)
+int refnet_inference_cm(const float* d_records, uint32_t n, void* d_out_cm, cudaStream_t stream) {
+	try {
+		GPUMatrix<float> in((float*)d_records, g_stride, n);
+		GPUMatrix<precision_t> out((precision_t*)d_out_cm, g_net->padded_output_width(), n);
+		g_net->inference_mixed_precision(stream, in, out, false);
+		return 0;
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return -1;
+	}
+}
+
+// tcnn::Trainer::optimizer_step with the optimizer of configs/nerf/main.json:21-32 (Ema{Adam}); the fp32 master copy is made on first use
+int refnet_optimizer_step(float loss_scale, cudaStream_t stream) {
+	try {
+		if (!g_opt) {
+			nlohmann::json cfg = {{"otype", "Ema"}, {"decay", 0.95},
+			                      {"nested", {{"otype", "Adam"}, {"learning_rate", 0.00175}, {"beta1", 0.9}, {"beta2", 0.99}, {"epsilon", 1e-15}, {"l2_reg", 1e-6}}}};
+			g_opt.reset(create_optimizer<precision_t>(cfg));
+			g_opt->allocate(g_net);
+			g_params_fp32.resize(g_params.size());
+			parallel_for_gpu(stream, g_params.size(), [dst = g_params_fp32.data(), src = g_params.data()] __device__(size_t i) { dst[i] = (float)src[i]; });
+		}
+		g_opt->step(stream, loss_scale, g_params_fp32.data(), g_params.data(), g_grads.data());
 		return 0;
 	} catch (const std::exception& e) {
 		g_err = e.what();
