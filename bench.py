@@ -419,8 +419,10 @@ def render_leg(ctx, verts, fv, args, rank, world):
     extra = torch.zeros(16, device="cuda")
     focal = 1200.0 * res[0] / 512.0
     ms, samples, iters = [], [], []
+    cams_frames = []
     for k in range(2 + n_local):
         f = k % min(n_local, 8)
+        cams_frames.append((synth.random_camera(1000 * rank + k), f))
         cam = capi.make_camera(synth.random_camera(1000 * rank + k), focal, res)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -429,9 +431,16 @@ def render_leg(ctx, verts, fv, args, rank, world):
         torch.cuda.synchronize()
         if k >= 2:
             ms.append(e0.elapsed_time(e1)); samples.append(smp); iters.append(it)
+    ref = None
+    if world == 1 and rank == 0 and args.ref_cuda and res[0] * res[1] <= (1 << 20):
+        try:
+            ref = ref_render_leg(ctx, fv, params, bf, extra, focal, res, cams_frames)
+        except Exception as e:
+            ref = {"error": repr(e)}
     return {"ms_per_frame": float(np.mean(ms)), "ms_per_frame_min": float(np.min(ms)), "resolution": list(res), "frames_timed": len(ms),
             "samples_per_frame": float(np.mean(samples)), "march_iterations_per_frame": float(np.mean(iters)),
-            "hit_fraction": float((fr[:, 3] > 0.2).float().mean()), "note": "deform + fused encode/MLP (tcgen05) + composite per iteration; one stream sync per iteration"}
+            "hit_fraction": float((fr[:, 3] > 0.2).float().mean()), "note": "deform + fused encode/MLP (tcgen05) + composite per iteration; one stream sync per iteration",
+            "ref_cuda": ref}
 
 
 def train_leg(ctx, verts, fv, args, rank, world):
@@ -681,6 +690,67 @@ def ref_train_leg(verts, frame_verts, dev_images, bitfield, extra, params16, n_r
     return {"ms_per_step": float(np.mean(ts)), "ms_per_step_min": float(np.min(ts)), "steps_timed": len(ts), "rays_per_step": int(n_rays), "samples_generated": gen,
             "samples_compacted": int(cnt[2]),
             "note": "reference kernels / network / optimizer (nvcc 12.9 -arch=sm_100) composed as Testbed::train_nerf_step does, same scene, rays and parameters"}
+
+
+def ref_render_leg(ctx, fv, params, bf, extra, focal, res, cams_frames):
+    """Testbed::render_nerf composed from the REFERENCE's own CUDA code (oracle/_ref: init_rays_with_payload_kernel_nerf + advance_pos_nerf, compact_kernel_nerf,
+    generate_next_nerf_network_inputs, `warp` with the frame fixed, NerfNetwork inference, composite_kernel_nerf, shade_kernel_nerf; one host read-back per march
+    iteration as NerfTracer::trace does) for the same cameras, frames, occupancy grid and parameters as our render leg.  Test infrastructure only."""
+    import torch
+
+    from oracle import pyoracle, pyrefcuda, pyrefnerf, pyrefnet
+
+    if not (pyrefcuda.available() and pyrefnerf.available() and pyrefnet.available()):
+        return {"unavailable": "oracle/_ref libraries (refcuda, refnerf, refnet) not all built"}
+    from insta_b200 import synth
+
+    O = pyoracle.Oracle()
+    vts, faces, regions = synth.load_canonical()
+    masks = synth.mask_ids_from_regions(faces, regions)
+    canon = O.build_triangles(vts, faces, masks)
+    adj = O.adjacency(faces, len(vts))
+    frames = sorted(set(f for _, f in cams_frames))
+    nodes, tbvh, ttopo = [], [], []
+    for f in range(max(frames) + 1):
+        t = O.build_triangles(fv[f], faces, masks, canon)
+        nn, tb = O.bvh_build(t)
+        nodes.append(nn); tbvh.append(tb); ttopo.append(t)
+    R = pyrefcuda.RefCuda()
+    R.upload_scene(nodes, tbvh, ttopo, canon, adj)
+    G = pyrefnerf.RefNerf()
+    N = pyrefnet.RefNet()
+    N.set_params(params)
+    n = res[0] * res[1]
+    aabb = ctx.render_aabb()
+    fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+    cap = (n + 127) // 128 * 128
+    rec = torch.zeros((cap, STRIDE), device="cuda")
+    out = torch.zeros((16, cap), dtype=torch.float16, device="cuda")
+    ms, iters = [], []
+    for k, (cam, f) in enumerate(cams_frames):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fr.zero_()
+        G.init_rays(cam, focal, (0.5, 0.5), res, 0, True, aabb, [0, 0, 0, 1, 1, 1], bf, 0.0, 0.01, fr, fd)
+        it = 0
+        while True:
+            na, ns = G.compact_and_generate(rec, 16, extra, f)
+            if na == 0:
+                break
+            m = na * ns
+            mp = (m + 127) // 128 * 128
+            R.warp(rec[:m], STRIDE, f)
+            N.inference(rec[:mp], out[:, :mp])
+            G.composite(rec, 16, out[:, :mp], mp, ns)
+            it += 1
+        G.shade(fr, fd)
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= 2:
+            ms.append(e0.elapsed_time(e1)); iters.append(it)
+    return {"ms_per_frame": float(np.mean(ms)), "ms_per_frame_min": float(np.min(ms)), "frames_timed": len(ms), "march_iterations_per_frame": float(np.mean(iters)),
+            "hit_fraction": float((fr[:, 3] > 0.2).float().mean()),
+            "note": "reference tracer kernels + `warp` + NerfNetwork (nvcc 12.9 -arch=sm_100) composed as Testbed::render_nerf / NerfTracer::trace, same cameras / frames / parameters"}
 
 
 def network_leg(ctx, rec_np, args):

@@ -147,7 +147,8 @@ struct insta_ctx {
 	bool frame_table_dirty = false;
 	uint32_t stack_need = 0;          // traversal stack entries a query can need for the loaded topology
 	bool compact_entries = false;     // every reference of the loaded topology fits the 16-bit stack code
-	bool force_legacy_deform = false; // INSTA_DEFORM_KERNEL=legacy: thread-per-query kernel (A/B measurements)
+	bool force_legacy_deform = false; // INSTA_DEFORM_KERNEL=legacy: thread-per-query kernel everywhere (A/B measurements)
+	bool force_wq_deform = false;     // INSTA_DEFORM_KERNEL=wq: warp-queue kernel everywhere
 	uint32_t* d_counter = nullptr;    // 32 sample counters (128 B apart) of the persistent deform kernel
 	std::atomic<uint32_t> counter_rr{0};
 	// grid
@@ -174,7 +175,7 @@ namespace insta {
 // deform.cu
 int launch_build_xf(insta_ctx* ctx, const float* d_verts, TriXf* d_xf, const float* d_canon_area, float* d_area_out, cudaStream_t s);
 int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, int32_t frame_id, const int32_t* d_frame_ids,
-                  bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr);
+                  bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr, bool coherent_hint = false);
 // hashgrid.cu
 int init_grid_levels(insta_ctx* ctx);
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s);

@@ -453,7 +453,7 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 		rc = tracer_generate(ctx, t->d_records, stride, ns, frame_id, d_extra_dims ? d_extra_dims : t->d_zero_extra, &n_rec, s);
 		if (rc) return rc;
 		if (deform) {
-			rc = launch_deform(ctx, t->d_records, n_rec, stride, frame_id, nullptr, false, nullptr, s);
+			rc = launch_deform(ctx, t->d_records, n_rec, stride, frame_id, nullptr, false, nullptr, s, nullptr, /*coherent_hint=*/true);
 			if (rc) return rc;
 		}
 		rc = launch_network_fwd(ctx, t->d_records, stride, n_rec, d_params, t->d_net_out, 0, s);
