@@ -826,6 +826,40 @@ def ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args):
     ms = float(np.mean(ts_w) + np.mean(ts_g))
     res = {"value": N_SAMPLES / (ms * 1e-3), "unit": UNIT, "warp_ms": float(np.mean(ts_w)), "kernel_grid_ms": float(np.mean(ts_g)),
            "note": "reference `warp` (src/core.cu:442) + kernel_grid (tcnn grid.h:138), nvcc 12.9 -arch=sm_100, identical device buffers"}
+    # stage 2 backward (scatter-add) on the 2^18-sample training batch: reference kernel_grid_backward (+ its memset) vs insta_hash_encode_bwd
+    try:
+        nb = 1 << 18
+        g = torch.Generator(device="cuda").manual_seed(1)
+        dy = (torch.randn((128, nb), device="cuda", generator=g) * 0.01).half()
+        grad_r = torch.empty((table.shape[0], 8), dtype=torch.float16, device="cuda")
+        pos = pristine[:nb].contiguous()
+        tr = []
+        for it in range(2 + 5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            grad_r.zero_()
+            R.grid_backward(pos, STRIDE, dy, grad_r)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tr.append(e0.elapsed_time(e1))
+        res["kernel_grid_backward_ms_2p18"] = float(np.mean(tr))
+        from insta_b200 import capi as _capi
+        c2 = _capi.Context(device=torch.cuda.current_device())
+        to = []
+        for it in range(2 + 5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c2.hash_encode_bwd(pos, dy, grad_r, zero_first=True)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                to.append(e0.elapsed_time(e1))
+        res["ours_hash_bwd_ms_2p18"] = float(np.mean(to))
+        c2.close()
+        del dy, grad_r
+    except Exception as e:
+        res["backward_error"] = repr(e)
     # the reference's own network (ngp::NerfNetwork<__half> over tiny-cuda-nn, oracle/_ref/libref_net.so) on the same batch
     try:
         from oracle import pyrefnet
