@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY: ctypes launcher for the reference's own CUDA kernels (oracle/_ref/libref_cuda.so).
-Device buffers are torch tensors; used by tests/test_gpu_vs_ref_cuda.py and bench.py's reported ref_cuda timing."""
+Device buffers are torch tensors; used by tests/test_gpu_vs_ref_cuda.py and tests/bench_ref_cuda.py."""
 import ctypes as C
 import os
 

@@ -5,7 +5,7 @@ import bench
 from insta_b200 import capi
 
 class A: pass
-a = A(); a.render_res = 512; a.render_frames = int(os.environ.get("FRAMES", 3)); a.ref_cuda = False
+a = A(); a.render_res = 512; a.render_frames = int(os.environ.get("FRAMES", 3))
 verts, faces, masks, fv = bench.build_scene(8, 0, 1)
 ctx = capi.Context(device=0)
 ctx.set_canonical(verts, faces, masks); ctx.add_frames(fv)

@@ -5,7 +5,7 @@ import bench
 from insta_b200 import capi
 
 class A: pass
-a = A(); a.train_images = int(os.environ.get("IMAGES", 128)); a.train_steps = int(os.environ.get("STEPS", 4)); a.train_warmup = int(os.environ.get("WARMUP", 40)); a.ref_cuda = False; a.ref_train_steps = 0
+a = A(); a.train_images = int(os.environ.get("IMAGES", 128)); a.train_steps = int(os.environ.get("STEPS", 4)); a.train_warmup = int(os.environ.get("WARMUP", 40)); 
 verts, faces, masks, fv = bench.build_scene(a.train_images, 0, 1)
 ctx = capi.Context(device=0)
 ctx.set_canonical(verts, faces, masks); ctx.add_frames(fv)
