@@ -421,7 +421,7 @@ def render_leg(ctx, verts, fv, args, rank, world, ref_hook=None):
         cam = capi.make_camera(synth.random_camera(1000 * rank + k), focal, res)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        it, smp = ctx.render_frame(cam, f, params, fr, fd, bitfield=bf, extra_dims=extra)
+        it, smp = ctx.render_frame(cam, f, params, fr, fd, bitfield=bf, extra_dims=extra, max_steps=getattr(args, "render_max_steps", 0))
         e1.record()
         torch.cuda.synchronize()
         if k >= 2:
@@ -429,7 +429,8 @@ def render_leg(ctx, verts, fv, args, rank, world, ref_hook=None):
     ref = ref_hook(ctx, fv, params, bf, extra, focal, res, cams_frames) if ref_hook else None
     return {"ms_per_frame": float(np.mean(ms)), "ms_per_frame_min": float(np.min(ms)), "resolution": list(res), "frames_timed": len(ms),
             "samples_per_frame": float(np.mean(samples)), "march_iterations_per_frame": float(np.mean(iters)),
-            "hit_fraction": float((fr[:, 3] > 0.2).float().mean()), "note": "deform + fused encode/MLP (tcgen05) + composite per iteration; one stream sync per iteration",
+            "hit_fraction": float((fr[:, 3] > 0.2).float().mean()), "max_steps_per_iteration": getattr(args, "render_max_steps", 0),
+            "note": "deform + fused encode/MLP (tcgen05) + composite per iteration; one stream sync per iteration; max_steps_per_iteration 0 = library default (up to 16 steps, 2^21 records per iteration), 8 = the reference's schedule",
             "ref_cuda": ref}
 
 
@@ -581,7 +582,7 @@ def stress_leg(args, rank, world):
         cam = capi.make_camera(synth.random_camera(777 + k), 1200.0 * res[0] / 512.0, res)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        it, smp = ctx.render_frame(cam, f, params, fr, fd, bitfield=bf, extra_dims=extra)
+        it, smp = ctx.render_frame(cam, f, params, fr, fd, bitfield=bf, extra_dims=extra, max_steps=getattr(args, "render_max_steps", 0))
         e1.record()
         torch.cuda.synchronize()
         if k >= 2:
@@ -658,6 +659,7 @@ def main():
     ap.add_argument("--no-render", action="store_true", help="skip the network / 512^2 render legs")
     ap.add_argument("--render-res", type=int, default=512)
     ap.add_argument("--render-frames", type=int, default=8)
+    ap.add_argument("--render-max-steps", type=int, default=0, help="insta_render_opts.max_steps_per_iteration of the render leg (0 = library default, 8 = the reference's schedule)")
     ap.add_argument("--train-images", type=int, default=128, help="synthetic 512^2 training images (= frames) per GPU in the train-step leg")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-warmup", type=int, default=30)

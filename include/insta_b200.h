@@ -180,7 +180,12 @@ typedef struct insta_render_opts {
 	uint32_t use_render_aabb;            /* 0 = the canonical mesh's render AABB (core.cu:289), 1 = render_aabb below */
 	float    render_aabb[6];
 	uint32_t linear_colors;              /* Testbed::Nerf::Training::linear_colors (false: sRGB -> linear when accumulating) */
-	uint32_t reserved_;
+	uint32_t max_steps_per_iteration;    /* insta_render_frame only.  March steps per ray between two compactions: clamp(budget / n_alive, 1, this).
+	                                      * 8 = the reference's schedule (MAX_STEPS_INBETWEEN_COMPACTION, budget = rays initialised,
+	                                      * testbed_nerf.cu:68, 2172); 0 = library default (16, budget = max(pixels, 2^21) records): fewer,
+	                                      * larger deformation / network batches.  The frame does not depend on the schedule (a ray's samples
+	                                      * and their compositing order are the same), only the number of samples evaluated past a ray's
+	                                      * termination does. */
 } insta_render_opts;
 
 typedef struct insta_render_stats {
@@ -193,7 +198,8 @@ typedef struct insta_render_stats {
  * (rta::Core::render_deformed; frame_id < 0 = no deformation) / network / composite until no ray is alive, result
  * accumulated into d_frame_rgba (res.x*res.y float4, zeroed first) and d_frame_depth.  d_extra_dims: the frame's exp_params
  * expression coefficients (Testbed::get_inference_extra_dims), NULL = zeros.  Synchronises the stream once per march
- * iteration like NerfTracer::trace (testbed_nerf.cu:2164-2165). */
+ * iteration like NerfTracer::trace (testbed_nerf.cu:2164-2165); opts->max_steps_per_iteration sets how many steps an
+ * iteration marches. */
 INSTA_API int insta_render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, const void* d_params_f16,
                                  const float* d_extra_dims, float* d_frame_rgba, float* d_frame_depth, insta_render_stats* h_stats, insta_stream stream);
 

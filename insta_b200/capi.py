@@ -103,7 +103,7 @@ class RenderStats(C.Structure):
 
 class RenderOpts(C.Structure):
     _fields_ = [("d_density_grid_bitfield", C.c_void_p), ("cone_angle_constant", C.c_float), ("min_transmittance", C.c_float), ("use_render_aabb", C.c_uint32),
-                ("render_aabb", C.c_float * 6), ("linear_colors", C.c_uint32), ("reserved_", C.c_uint32)]
+                ("render_aabb", C.c_float * 6), ("linear_colors", C.c_uint32), ("max_steps_per_iteration", C.c_uint32)]
 
 
 def make_camera(cam3x4, focal, resolution, screen_center=(0.5, 0.5), sample_index=0, snap=True):
@@ -507,8 +507,9 @@ class Context:
                                                     C.byref(n), _stream(stream)))
         return n.value
 
-    def _opts(self, bitfield, render_aabb, cone_angle, min_transmittance, linear_colors):
+    def _opts(self, bitfield, render_aabb, cone_angle, min_transmittance, linear_colors, max_steps=0):
         o = RenderOpts()
+        o.max_steps_per_iteration = int(max_steps)
         o.d_density_grid_bitfield = bitfield.data_ptr() if bitfield is not None else None
         o.cone_angle_constant = cone_angle
         o.min_transmittance = min_transmittance
@@ -519,9 +520,10 @@ class Context:
         return o
 
     def render_frame(self, cam, frame_id, params, frame_rgba, frame_depth, bitfield=None, extra_dims=None, render_aabb=None, cone_angle=0.0,
-                     min_transmittance=0.01, linear_colors=False, stream=None):
-        """Testbed::render_nerf with this library's deformation + network; returns (iterations, samples)."""
-        o = self._opts(bitfield, render_aabb, cone_angle, min_transmittance, linear_colors)
+                     min_transmittance=0.01, linear_colors=False, stream=None, max_steps=0):
+        """Testbed::render_nerf with this library's deformation + network; returns (iterations, samples).  max_steps: march steps per
+        iteration (8 = the reference's schedule, 0 = library default; the frame is the same either way)."""
+        o = self._opts(bitfield, render_aabb, cone_angle, min_transmittance, linear_colors, max_steps)
         st = RenderStats()
         self._check(self.lib.insta_render_frame(self.h, C.byref(cam), C.byref(o), C.c_int32(frame_id), _dev(params), _dev(extra_dims), _dev(frame_rgba),
                                                 _dev(frame_depth), C.byref(st), _stream(stream)))

@@ -149,6 +149,7 @@ struct insta_ctx {
 	bool compact_entries = false;     // every reference of the loaded topology fits the 16-bit stack code
 	bool force_legacy_deform = false; // INSTA_DEFORM_KERNEL=legacy: thread-per-query kernel everywhere (A/B measurements)
 	bool force_wq_deform = false;     // INSTA_DEFORM_KERNEL=wq: warp-queue kernel everywhere
+	uint32_t coherent_max_n = 1u << 19; // tracer batches below this many records use the thread-per-query kernel (INSTA_DEFORM_COHERENT_MAX)
 	uint32_t* d_counter = nullptr;    // 32 sample counters (128 B apart) of the persistent deform kernel
 	std::atomic<uint32_t> counter_rr{0};
 	// grid

@@ -421,15 +421,22 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 	Tracer* t = tracer_of(ctx);
 	const uint32_t n_pix = cam->resolution[0] * cam->resolution[1];
 	const uint32_t stride = 11 + ctx->p.exp_params + ctx->p.geo_params;
-	if (n_pix > t->scratch_cap || stride != t->scratch_stride) {
+	// Steps per iteration: the reference marches clamp(rays initialised / n_alive, 1, 8) steps between two compactions, i.e. at most one record per
+	// pixel and launch -- a few hundred thousand records, which neither the deformation nor the network kernel can turn into throughput.  The frame
+	// does not depend on that schedule, so by default an iteration fills a budget of max(pixels, 2^21) records with up to 16 steps per ray
+	// (512^2, B200: 9.55 ms per frame with the reference's schedule, 7.00 with 16 steps, 7.24 with 32, 7.76 with 64 -- profiles/r1_render_schedule.txt).
+	const uint32_t max_steps = opts && opts->max_steps_per_iteration ? std::min(opts->max_steps_per_iteration, 0xffffu) : 16u;
+	const uint32_t budget = max_steps <= 8u ? n_pix : std::max(n_pix, 1u << 21);
+	if (budget > t->scratch_cap || stride != t->scratch_stride) {
 		INSTA_CUDA(cudaDeviceSynchronize());
 		if (t->d_records) cudaFree(t->d_records);
 		if (t->d_net_out) cudaFree(t->d_net_out);
 		t->d_records = nullptr;
 		t->d_net_out = nullptr;
-		INSTA_CUDA(cudaMalloc(&t->d_records, (size_t)n_pix * stride * 4));
-		INSTA_CUDA(cudaMalloc(&t->d_net_out, (size_t)n_pix * 8));
-		t->scratch_cap = n_pix;
+		t->scratch_cap = 0;
+		INSTA_CUDA(cudaMalloc(&t->d_records, (size_t)budget * stride * 4));
+		INSTA_CUDA(cudaMalloc(&t->d_net_out, (size_t)budget * 8));
+		t->scratch_cap = budget;
 		t->scratch_stride = stride;
 	}
 	if (!t->d_zero_extra) {
@@ -448,7 +455,7 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 		if (rc) return rc;
 	}
 	while (n_alive > 0) {
-		const uint32_t ns = tracer_n_steps(ctx);
+		const uint32_t ns = std::min(std::max(budget / n_alive, 1u), max_steps);  // max_steps == 8: tracer_n_steps(ctx), the reference's
 		uint32_t n_rec = 0;
 		rc = tracer_generate(ctx, t->d_records, stride, ns, frame_id, d_extra_dims ? d_extra_dims : t->d_zero_extra, &n_rec, s);
 		if (rc) return rc;

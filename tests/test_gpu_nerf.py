@@ -149,7 +149,7 @@ def test_render_frame_vs_reference_tracer(gpu_ctx, scene, refnerf):
     pn[13312:13312 + 64] = np.float16(0.6)
     params = torch.from_numpy(pn).cuda()
     fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
-    iters, samples = gpu_ctx.render_frame(capi.make_camera(cam, FOCAL, RES), 1, params, fr, fd, bitfield=bf, extra_dims=extra)
+    iters, samples = gpu_ctx.render_frame(capi.make_camera(cam, FOCAL, RES), 1, params, fr, fd, bitfield=bf, extra_dims=extra, max_steps=8)  # the reference's schedule
     assert iters > 3 and samples > 10000
     rfr, rfd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
     rrec = torch.zeros((n * 8, 27), device="cuda")
@@ -173,3 +173,61 @@ def test_render_frame_vs_reference_tracer(gpu_ctx, scene, refnerf):
     hit = rfr[:, 3] > 0.2
     assert int(hit.sum()) > 500
     assert float((fd[hit] - rfd[hit]).abs().max()) < 1e-4
+
+
+def test_render_frame_schedule_independent(gpu_ctx, scene):
+    """The number of march steps per iteration (insta_render_opts.max_steps_per_iteration: 8 = the reference's schedule, 0 = the library's larger
+    batches, 1 = one step per iteration) changes how many iterations a frame takes and which deformation kernel its batches use -- not the frame:
+    a ray's samples and their compositing order are the same, so RGBA and depth must be bit-identical."""
+    import torch
+
+    from insta_b200 import capi, synth
+
+    cam = capi.make_camera(synth.random_camera(5), FOCAL, RES)
+    bf = _bitfield(scene)
+    n = RES[0] * RES[1]
+    extra = torch.linspace(-1, 1, 16, device="cuda")
+    pn = synth.make_network_params(gpu_ctx.network_n_params, seed=11)
+    pn[13312:13312 + 64] = np.float16(0.6)  # rays saturate (see test_render_frame_vs_reference_tracer)
+    params = torch.from_numpy(pn).cuda()
+    frames = {}
+    for ms in (8, 0, 1, 3):
+        fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+        iters, samples = gpu_ctx.render_frame(cam, 1, params, fr, fd, bitfield=bf, extra_dims=extra, max_steps=ms)
+        torch.cuda.synchronize()
+        frames[ms] = (fr, fd, iters, samples)
+    ref = frames[8]
+    assert int((ref[0][:, 3] > 0.2).sum()) > 500
+    assert frames[0][2] < ref[2] < frames[1][2]  # fewer, larger iterations by default; one step per iteration needs the most
+    for ms in (0, 1, 3):
+        assert torch.equal(frames[ms][0].view(torch.int32), ref[0].view(torch.int32)), ms
+        assert torch.equal(frames[ms][1].view(torch.int32), ref[1].view(torch.int32)), ms
+
+
+def test_render_frame_warp_queue_batches(scene, gpu_ctx, monkeypatch):
+    """Large tracer batches go through the warp-queue deformation kernel, small ones through the thread-per-query kernel (launch_deform): a
+    context that uses the warp-queue kernel for every batch renders the same frame bit for bit."""
+    import torch
+
+    from conftest import _make_ctx
+    from insta_b200 import capi, synth
+
+    cam = capi.make_camera(synth.random_camera(5), FOCAL, RES)
+    bf = _bitfield(scene)
+    n = RES[0] * RES[1]
+    extra = torch.linspace(-1, 1, 16, device="cuda")
+    pn = synth.make_network_params(gpu_ctx.network_n_params, seed=11)
+    pn[13312:13312 + 64] = np.float16(0.6)
+    params = torch.from_numpy(pn).cuda()
+    fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+    gpu_ctx.render_frame(cam, 1, params, fr, fd, bitfield=bf, extra_dims=extra)
+    monkeypatch.setenv("INSTA_DEFORM_COHERENT_MAX", "0")
+    ctx = _make_ctx(scene)
+    try:
+        fr2, fd2 = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
+        ctx.render_frame(cam, 1, params, fr2, fd2, bitfield=bf, extra_dims=extra)
+        torch.cuda.synchronize()
+    finally:
+        ctx.close()
+    assert torch.equal(fr2.view(torch.int32), fr.view(torch.int32))
+    assert torch.equal(fd2.view(torch.int32), fd.view(torch.int32))
