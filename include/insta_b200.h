@@ -223,6 +223,24 @@ INSTA_API int insta_tracer_composite(insta_ctx* ctx, const float* d_records, uin
                                      uint32_t n_steps, float* d_frame_rgba, float* d_frame_depth, uint32_t* h_n_alive, insta_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Recorder read-back -- rta::Recorder::dump_frame_buffer (src/recorder.cu:299-359).  The reference copies the float4 frame
+ * buffer and the float depth buffer to the host with two blocking cudaMemcpy (20 bytes per pixel) and converts them on one
+ * host thread; here the conversion runs on the GPU and 8 bytes per pixel leave the device with asynchronous copies on
+ * `stream` (no synchronisation: the host buffers are valid after the caller's next sync; pinned buffers keep it asynchronous).
+ *   h_rgba8    : width*height*4 bytes, (uint8_t) clamp(transform(v) * 255, 0, 255) per channel incl. alpha (save_rgba,
+ *                recorder.cu:36-60); transform = identity, or srgb_to_linear when srgb_to_linear != 0 (Normals mode, 341-343)
+ *   h_depth_mm : width*(height-1) values, uint32(d * 1000) with d = 0 outside [0, 5] (save_depth, recorder.cu:75-105; the
+ *                reference reads depth[x + width + y*width] for output pixel (x, y) and skips indices past the buffer, so
+ *                the file holds rows 1 .. height-1 -- kept, the .bin files are what downstream scripts read)
+ * Either host pointer may be NULL. */
+INSTA_API int insta_recorder_readback(insta_ctx* ctx, const float* d_frame_rgba, const float* d_frame_depth, uint32_t width, uint32_t height,
+                                      uint32_t srgb_to_linear, uint8_t* h_rgba8, uint32_t* h_depth_mm, insta_stream stream);
+/* Host only.  8-bit RGBA PNG (stb's stbi_write_png in the reference, recorder.cu:59; stored deflate blocks here -- the decoded
+ * pixels are what agrees) and the depth .bin (raw little-endian uint32 millimetres, recorder.cu:88-103). */
+INSTA_API int insta_host_write_png(const char* path, uint32_t width, uint32_t height, const uint8_t* h_rgba8);
+INSTA_API int insta_host_write_depth_bin(const char* path, const uint32_t* h_depth_mm, uint64_t n_values);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Network -- ngp::NerfNetwork<__half> (ngp/include/neural-graphics-primitives/nerf_network.h) with the shipped
  * configuration (configs/nerf/main.json:33-69): HashGrid 16x8 -> (+16 expression rows) -> density MLP 144-64-64-16 ->
  * (16 density outputs | SH degree 4 of the direction) -> colour MLP 32-64-64-64-16.  d_params_f16 is the trainer's fp16

@@ -129,7 +129,7 @@ EXPORTS = [
     "insta_get_frame_bvh_order", "insta_deform_samples", "insta_deform_samples_n", "insta_network_inference_n", "insta_deform_points", "insta_grid_layout", "insta_grid_n_params",
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
-    "insta_host_load_canonical_obj", "insta_host_mesh_aabb",
+    "insta_host_load_canonical_obj", "insta_host_mesh_aabb", "insta_recorder_readback", "insta_host_write_png", "insta_host_write_depth_bin",
     "insta_network_n_params", "insta_network_inference", "insta_network_density", "insta_network_forward_backward", "insta_training_set_images", "insta_generate_training_samples", "insta_compute_loss",
     "insta_optimizer_step",
     "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
@@ -544,6 +544,14 @@ class Context:
                                                     _dev(frame_rgba), _dev(frame_depth), C.byref(n), _stream(stream)))
         return n.value
 
+    # ---- recorder read-back (rta::Recorder::dump_frame_buffer) ----
+    def recorder_readback(self, frame_rgba, frame_depth, width, height, h_rgba8=None, h_depth_mm=None, srgb_to_linear=False, stream=None):
+        """frame_rgba [w*h, 4] float32 / frame_depth [w*h] float32 on the device -> h_rgba8 (uint8 [h, w, 4]) and h_depth_mm (int32 / uint32
+        [h-1, w]) host tensors (pinned for asynchronous copies).  No synchronisation: sync the stream before reading them."""
+        self._check(self.lib.insta_recorder_readback(self.h, _dev(frame_rgba), _dev(frame_depth), C.c_uint32(width), C.c_uint32(height), C.c_uint32(int(srgb_to_linear)),
+                                                     C.c_void_p(h_rgba8.data_ptr()) if h_rgba8 is not None else None,
+                                                     C.c_void_p(h_depth_mm.data_ptr()) if h_depth_mm is not None else None, _stream(stream)))
+
     # ---- host-buffer path ----
     def deform_encode_host(self, h_coords, frame_id, table, h_out):
         """h_coords: pinned float32 torch tensor [n, stride] (mutated in place); h_out: pinned fp16 [L*8, n]."""
@@ -587,6 +595,18 @@ def host_bvh_build(tris, leaf_size=2):
     nn = C.c_uint32(0)
     _hcheck(load_library().insta_host_bvh_build(_vp(t), C.c_uint32(len(t)), C.c_uint32(leaf_size), _vp(nodes), C.c_uint32(len(nodes)), C.byref(nn)))
     return nodes[: nn.value].copy(), t
+
+
+def host_write_png(path, rgba8):
+    """rgba8: uint8 [h, w, 4] -> PNG (rta::Recorder save_rgba's stbi_write_png, recorder.cu:59)."""
+    a = _np(rgba8, np.uint8)
+    h, w = a.shape[:2]
+    _hcheck(load_library().insta_host_write_png(str(path).encode(), C.c_uint32(w), C.c_uint32(h), _vp(a)))
+
+
+def host_write_depth_bin(path, depth_mm):
+    a = _np(depth_mm, np.uint32)
+    _hcheck(load_library().insta_host_write_depth_bin(str(path).encode(), _vp(a), C.c_uint64(a.size)))
 
 
 def host_adjacency(faces, n_verts):

@@ -188,6 +188,7 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 		const char* k = getenv("INSTA_DEFORM_KERNEL");
 		ctx->force_legacy_deform = k && std::string(k) == "legacy";
 		ctx->force_wq_deform = k && std::string(k) == "wq";
+		if (const char* sd = getenv("INSTA_DEFORM_SEED")) ctx->disable_seed_bound = std::string(sd) == "0";
 		if (const char* m = getenv("INSTA_DEFORM_COHERENT_MAX")) ctx->coherent_max_n = (uint32_t)strtoul(m, nullptr, 10);
 	}
 	int rc = init_grid_levels(ctx);
@@ -211,8 +212,10 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (ctx->d_adjacency) cudaFree(ctx->d_adjacency);
 	if (ctx->d_canon_area) cudaFree(ctx->d_canon_area);
 	if (ctx->d_canon_xf) cudaFree(ctx->d_canon_xf);
+	if (ctx->d_seed_grid) cudaFree(ctx->d_seed_grid);
 	if (ctx->d_counter) cudaFree(ctx->d_counter);
 	tracer_destroy(ctx);
+	recorder_destroy(ctx);
 	network_bwd_destroy(ctx);
 	trainer_destroy(ctx);
 	comm_destroy(ctx);
@@ -271,6 +274,7 @@ int insta_set_canonical(insta_ctx* ctx, const float* h_verts, uint32_t n_verts, 
 	INSTA_CUDA(cudaMemcpyAsync(ctx->d_adjacency, ctx->adjacency.data(), (size_t)n_faces * 12, cudaMemcpyHostToDevice, s));
 	INSTA_CUDA(cudaMemcpyAsync(d_verts, h_verts, (size_t)n_verts * 12, cudaMemcpyHostToDevice, s));
 	rc = launch_build_xf(ctx, d_verts, ctx->d_canon_xf, nullptr, ctx->d_canon_area, s);
+	if (!rc) rc = launch_build_seed_grid(ctx, s);
 	cudaError_t e = cudaStreamSynchronize(s);
 	cudaFree(d_verts);
 	if (rc) return rc;
@@ -696,6 +700,27 @@ int insta_tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stri
 	if (!ctx || !ctx->tracer || !d_records || !d_net_out_f16 || !d_frame_rgba || !d_frame_depth) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_composite: bad arguments");
 	return tracer_composite(ctx, d_records, stride_floats, d_net_out_f16, out_stride_elems, n_steps, d_frame_rgba, d_frame_depth, (int)ctx->render_opts.linear_colors,
 	                        h_n_alive, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Recorder read-back
+int insta_recorder_readback(insta_ctx* ctx, const float* d_frame_rgba, const float* d_frame_depth, uint32_t width, uint32_t height, uint32_t srgb_to_linear,
+                            uint8_t* h_rgba8, uint32_t* h_depth_mm, insta_stream stream) {
+	if (!ctx || !d_frame_rgba || width == 0 || height == 0 || (!h_rgba8 && !h_depth_mm)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_recorder_readback: bad arguments");
+	if (h_depth_mm && !d_frame_depth) INSTA_FAIL(INSTA_ERR_INVALID, "insta_recorder_readback: depth requested without a depth buffer");
+	if ((uint64_t)width * height > 0x7fffffffu) INSTA_FAIL(INSTA_ERR_INVALID, "insta_recorder_readback: frame too large");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	return recorder_readback(ctx, d_frame_rgba, d_frame_depth, width, height, (int)srgb_to_linear, h_rgba8, h_depth_mm, (cudaStream_t)stream);
+}
+
+int insta_host_write_png(const char* path, uint32_t width, uint32_t height, const uint8_t* h_rgba8) {
+	if (!path || !h_rgba8 || width == 0 || height == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_write_png: bad arguments");
+	return write_png_rgba8(path, width, height, h_rgba8);
+}
+
+int insta_host_write_depth_bin(const char* path, const uint32_t* h_depth_mm, uint64_t n_values) {
+	if (!path || (!h_depth_mm && n_values)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_write_depth_bin: bad arguments");
+	return write_depth_bin(path, h_depth_mm, (size_t)n_values);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

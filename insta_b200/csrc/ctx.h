@@ -149,6 +149,11 @@ struct insta_ctx {
 	bool compact_entries = false;     // every reference of the loaded topology fits the 16-bit stack code
 	bool force_legacy_deform = false; // INSTA_DEFORM_KERNEL=legacy: thread-per-query kernel everywhere (A/B measurements)
 	bool force_wq_deform = false;     // INSTA_DEFORM_KERNEL=wq: warp-queue kernel everywhere
+	void* d_recorder = nullptr;       // recorder read-back staging: 8-bit RGBA + millimetre depth (recorder.cu)
+	size_t recorder_cap = 0;          // pixels
+	uint16_t* d_seed_grid = nullptr;  // 32^3 cells over render_aabb -> topology id of a nearby canonical triangle (deform.cu seed_bound)
+	float seed_lo[3] = {0, 0, 0}, seed_scale[3] = {0, 0, 0};
+	bool disable_seed_bound = false;  // INSTA_DEFORM_SEED=0: traversals start from FLT_MAX like the reference's (A/B measurements)
 	uint32_t coherent_max_n = 1u << 19; // tracer batches below this many records use the thread-per-query kernel (INSTA_DEFORM_COHERENT_MAX)
 	uint32_t* d_counter = nullptr;    // 32 sample counters (128 B apart) of the persistent deform kernel
 	std::atomic<uint32_t> counter_rr{0};
@@ -175,6 +180,13 @@ struct insta_ctx {
 namespace insta {
 // deform.cu
 int launch_build_xf(insta_ctx* ctx, const float* d_verts, TriXf* d_xf, const float* d_canon_area, float* d_area_out, cudaStream_t s);
+int launch_build_seed_grid(insta_ctx* ctx, cudaStream_t s);
+// recorder.cu
+int recorder_readback(insta_ctx* ctx, const float* d_rgba, const float* d_depth, uint32_t w, uint32_t h, int srgb_to_linear, uint8_t* h_rgba8, uint32_t* h_depth_mm,
+                      cudaStream_t s);
+void recorder_destroy(insta_ctx* ctx);
+int write_png_rgba8(const char* path, uint32_t w, uint32_t h, const uint8_t* rgba8);
+int write_depth_bin(const char* path, const uint32_t* depth_mm, size_t n);
 int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, int32_t frame_id, const int32_t* d_frame_ids,
                   bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr, bool coherent_hint = false);
 // hashgrid.cu

@@ -245,3 +245,29 @@ def have_ref_host():
 
 def have_ref_cuda():
     return os.path.exists(REF_CUDA_SO)
+
+
+# ---- recorder read-back (numpy restatement of rta::Recorder save_rgba / save_depth, src/recorder.cu:36-60, 75-105) ----
+def recorder_rgba8(rgba, srgb_to_linear=False):
+    """rgba float32 [n, 4] -> uint8 [n, 4]: (uint8_t) tcnn::clamp(transform(v) * 255.f, 0.f, 255.f) per channel incl. alpha (recorder.cu:46-49);
+    transform = identity, or srgb_to_linear (recorder.cu:116-122) in Normals mode (341-343)."""
+    v = np.asarray(rgba, np.float32)
+    if srgb_to_linear:
+        v = np.where(v <= np.float32(0.04045), v / np.float32(12.92), np.power((v + np.float32(0.055)) / np.float32(1.055), np.float32(2.4), dtype=np.float32)).astype(np.float32)
+    s = (v * np.float32(255.0)).astype(np.float32)
+    s = np.where(s < 0, np.float32(0), np.where(s > 255, np.float32(255), s))
+    return np.nan_to_num(s, nan=0.0).astype(np.uint8)  # truncation, like the C cast
+
+
+def recorder_depth_mm(depth, w, h):
+    """depth float32 [w*h] -> uint32 [(h-1)*w]: output pixel (x, y) reads index x + w + y*w and is skipped when that is past the buffer
+    (recorder.cu:93-94); d outside [0, 5] -> 0; uint32(d * 1000.0f) (recorder.cu:96-99)."""
+    d = np.asarray(depth, np.float32).reshape(-1)
+    out = []
+    for y in range(h):
+        i = np.arange(w) + w + y * w
+        i = i[i < d.size]
+        v = d[i].copy()
+        v[(v < 0) | (v > 5) | np.isnan(v)] = 0
+        out.append((v * np.float32(1000.0)).astype(np.float32).astype(np.uint32))
+    return np.concatenate(out) if out else np.zeros(0, np.uint32)
