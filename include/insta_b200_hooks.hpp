@@ -95,6 +95,13 @@ public:
 		return st;
 	}
 
+	// rta::Recorder::dump_frame_buffer (src/recorder.cu:299-359): the frame as the recorder stores it, converted on the GPU; host buffers valid after the
+	// caller's next stream synchronisation
+	void read_back_frame(const float* d_frame_rgba, const float* d_frame_depth, uint32_t width, uint32_t height, bool normals_mode, uint8_t* h_rgba8,
+	                     uint32_t* h_depth_mm, void* stream) {
+		check(insta_recorder_readback(m_ctx, d_frame_rgba, d_frame_depth, width, height, normals_mode ? 1u : 0u, h_rgba8, h_depth_mm, stream));
+	}
+
 	// Testbed::load_nerf -> metadata_gpu / transforms_gpu (testbed_nerf.cu:2698-2760)
 	void set_training_images(const insta_train_image* images, uint32_t n) { check(insta_training_set_images(m_ctx, images, n)); }
 	// Testbed::train_nerf (testbed_nerf.cu:2916-2992): one step; returns the counters update_after_training would have set
