@@ -213,7 +213,9 @@ def run_ours(args):
     verts, faces, masks, fv = build_scene(n_frames, rank, world)
     ctx = capi.Context(device=local)
     ctx.set_canonical(verts, faces, masks)
-    ctx.add_frames(fv)
+    t_ing = time.perf_counter()
+    ctx.add_frames(fv)  # Core::load_meshes: host BVH builds on a thread pool (the reference's nth_element order) + upload + per-triangle transform tables
+    t_ing = time.perf_counter() - t_ing
     n_local = ctx.n_frames
     layout = ctx.grid_layout()
     n_entries = int(layout[0][-1])
@@ -374,6 +376,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_SAMPLES * STRIDE * 4,
                     "d2h_bytes_per_step": N_SAMPLES * STRIDE * 4 + N_SAMPLES * 128 * 2, "steps": len(e2e_t)},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t1 - t0,
+            "ingest": {"frames": int(n_local), "seconds": t_ing, "frames_per_s": n_local / max(t_ing, 1e-9), "host_threads": os.cpu_count(),
+                       "note": "insta_add_frames (rta::Core::load_meshes, core.cu:294-334): per-frame host BVH build + H2D + transform table; outside the timed region"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -540,7 +544,9 @@ def train_leg(ctx, verts, fv, args, rank, world, ref_hook=None):
         ms = float(t.item())
         ctx.comm_destroy()
     last = hist[-1]
-    return {"ms_per_step": ms, "ms_per_step_min": float(np.min(ts)), "steps_timed": len(ts), "warmup_steps": args.train_warmup, "target_batch_size": 1 << 18,
+    return {"ms_per_step": ms, "ms_per_step_min": float(np.min(ts)), "ms_per_step_p50": float(np.median(ts)), "steps_timed": len(ts), "warmup_steps": args.train_warmup, "target_batch_size": 1 << 18,
+            "ms_steps": [round(float(x), 2) for x in ts], "samples_generated_steps": [int(h["measured_batch_size_before_compaction"]) for h in hist[-len(ts):]],
+            "rays_steps": [int(h["n_rays"]) for h in hist[-len(ts):]],
             "rays_per_step": last["n_rays"], "samples_generated": last["measured_batch_size_before_compaction"], "samples_compacted": last["measured_batch_size"],
             "aggregate_rays_per_s": world * last["n_rays"] / (ms * 1e-3), "loss": last["loss"], "images_per_gpu": n_img, "launches_per_step": launches / max(1, len(ts)),
             "grad_allreduce": ("NCCL fp16 sum of %d halves per step" % n) if world > 1 else "none (1 GPU)", "grad_allreduce_ms": ar_ms,
@@ -662,7 +668,7 @@ def main():
     ap.add_argument("--render-max-steps", type=int, default=0, help="insta_render_opts.max_steps_per_iteration of the render leg (0 = library default, 8 = the reference's schedule)")
     ap.add_argument("--train-images", type=int, default=128, help="synthetic 512^2 training images (= frames) per GPU in the train-step leg")
     ap.add_argument("--train-steps", type=int, default=20)
-    ap.add_argument("--train-warmup", type=int, default=30)
+    ap.add_argument("--train-warmup", type=int, default=70, help="untimed steps before the timed ones: rays_per_batch grows ~9 % per step from 4096 and needs ~65 steps to reach its fixed point")
     ap.add_argument("--stress", action="store_true", help="also run configs[4]: 2048^2 render, 4000 resident BVHs, 2^22-entry hash table")
     ap.add_argument("--stress-frames", type=int, default=4000)
     ap.add_argument("--stress-renders", type=int, default=4)

@@ -61,6 +61,54 @@ static int upload_frame(insta_ctx* ctx, const float* h_verts, const HostBvh& bvh
 	return INSTA_OK;
 }
 
+// Upload a batch of prepared frames: one allocation (owned by the batch's first frame), asynchronous copies, one sync.
+static int upload_frames(insta_ctx* ctx, const float* h_verts, const std::vector<HostBvh>& bvhs) {
+	if (bvhs.empty()) return INSTA_OK;
+	const size_t xf_b = align_up((size_t)ctx->n_faces * sizeof(TriXf), 256);
+	const size_t verts_b = align_up((size_t)ctx->n_verts * 12, 256);
+	std::vector<size_t> off(bvhs.size() + 1, 0);
+	for (size_t i = 0; i < bvhs.size(); ++i)
+		off[i + 1] = off[i] + align_up(bvhs[i].quads.size() * sizeof(Quad), 256) + align_up(bvhs[i].tris.size() * sizeof(Tri), 256) + xf_b + verts_b;
+	void* slab = nullptr;
+	INSTA_CUDA(cudaMalloc(&slab, off.back()));
+	cudaStream_t s = ctx->streams[0];
+	std::vector<insta_ctx::Frame> frames(bvhs.size());
+	int rc = INSTA_OK;
+	cudaError_t e = cudaSuccess;
+	for (size_t i = 0; i < bvhs.size() && !rc && e == cudaSuccess; ++i) {
+		const HostBvh& bvh = bvhs[i];
+		unsigned char* base = (unsigned char*)slab + off[i];
+		const size_t quads_b = align_up(bvh.quads.size() * sizeof(Quad), 256), tris_b = align_up(bvh.tris.size() * sizeof(Tri), 256);
+		Quad* d_quads = (Quad*)base;
+		Tri* d_tris = (Tri*)(base + quads_b);
+		TriXf* d_xf = (TriXf*)(base + quads_b + tris_b);
+		float* d_verts = (float*)(base + quads_b + tris_b + xf_b);
+		const float* hv = h_verts + (size_t)ctx->n_verts * 3 * i;
+		e = cudaMemcpyAsync(d_quads, bvh.quads.data(), bvh.quads.size() * sizeof(Quad), cudaMemcpyHostToDevice, s);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(Tri), cudaMemcpyHostToDevice, s);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_verts, hv, (size_t)ctx->n_verts * 12, cudaMemcpyHostToDevice, s);
+		if (e != cudaSuccess) break;
+		rc = launch_build_xf(ctx, d_verts, d_xf, ctx->d_canon_area, nullptr, s);
+		insta_ctx::Frame& fr = frames[i];
+		fr.slab = i == 0 ? slab : nullptr;
+		fr.dev.quads = d_quads;
+		fr.dev.tris = d_tris;
+		fr.dev.xf = d_xf;
+		fr.n_nodes = (uint32_t)bvh.nodes.size();
+		fr.n_quads = (uint32_t)bvh.quads.size();
+		fr.bvh_order_ids.resize(bvh.tris.size());
+		for (size_t k = 0; k < bvh.tris.size(); ++k) fr.bvh_order_ids[k] = bvh.tris[k].id;
+	}
+	const cudaError_t es = cudaStreamSynchronize(s);
+	if (rc || e != cudaSuccess || es != cudaSuccess) {
+		cudaFree(slab);
+		if (rc) return rc;
+		INSTA_CUDA(e != cudaSuccess ? e : es);
+	}
+	for (auto& fr : frames) ctx->frames.push_back(std::move(fr));
+	return INSTA_OK;
+}
+
 static void prepare_frame(const insta_ctx* ctx, const float* h_verts, HostBvh& bvh) {
 	std::vector<Tri> tris(ctx->n_faces);
 	build_triangles(h_verts, ctx->faces.data(), ctx->n_faces, ctx->mask_ids.data(), ctx->canon_tris.data(), tris.data());
@@ -319,27 +367,32 @@ int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t 
 	if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
 	n_threads = std::min(n_threads, std::max(1u, n));
 	const size_t per = (size_t)ctx->n_verts * 3;
-	// host BVH builds in parallel batches, uploads in order
-	const uint32_t batch = n_threads * 4;
-	for (uint32_t b0 = 0; b0 < n; b0 += batch) {
-		const uint32_t b1 = std::min(n, b0 + batch);
-		std::vector<HostBvh> built(b1 - b0);
+	// Host BVH builds (the reference's build order needs libstdc++'s nth_element, SURVEY hard part 1) run on a thread pool one batch AHEAD of the uploads:
+	// while batch k+1 is being built, batch k goes to the device as ONE allocation with asynchronous copies and one stream sync (a cudaMalloc, three
+	// blocking copies and a sync per frame made the upload, not the build, the bottleneck: 523 frames/s on 16 threads).
+	const uint32_t batch = std::max(32u, n_threads * 4);
+	auto build_batch = [&](uint32_t b0, uint32_t b1, std::vector<HostBvh>& out) {
+		out.clear();
+		out.resize(b1 - b0);
 		std::atomic<uint32_t> next{b0};
 		std::vector<std::thread> pool;
-		for (uint32_t t = 0; t < n_threads; ++t)
+		const uint32_t nt = std::min(n_threads, b1 - b0);
+		for (uint32_t t = 0; t < nt; ++t)
 			pool.emplace_back([&]() {
-				for (uint32_t i; (i = next.fetch_add(1)) < b1;) prepare_frame(ctx, h_verts + per * i, built[i - b0]);
+				for (uint32_t i; (i = next.fetch_add(1)) < b1;) prepare_frame(ctx, h_verts + per * i, out[i - b0]);
 			});
 		for (auto& t : pool) t.join();
-		for (uint32_t i = b0; i < b1; ++i) {
-			insta_ctx::Frame fr;
-			int rc = upload_frame(ctx, h_verts + per * i, built[i - b0], fr);
-			if (rc) {
-				if (fr.slab) cudaFree(fr.slab);
-				return rc;
-			}
-			ctx->frames.push_back(std::move(fr));
-		}
+	};
+	std::vector<HostBvh> cur, nxt;
+	build_batch(0, std::min(n, batch), cur);
+	for (uint32_t b0 = 0; b0 < n; b0 += batch) {
+		const uint32_t b1 = std::min(n, b0 + batch), b2 = std::min(n, b1 + batch);
+		std::thread builder;
+		if (b1 < n) builder = std::thread([&]() { build_batch(b1, b2, nxt); });
+		const int rc = upload_frames(ctx, h_verts + per * b0, cur);
+		if (builder.joinable()) builder.join();
+		if (rc) return rc;
+		cur.swap(nxt);
 	}
 	ctx->frame_table_dirty = true;
 	return INSTA_OK;
