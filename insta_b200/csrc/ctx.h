@@ -154,6 +154,7 @@ struct insta_ctx {
 	uint16_t* d_seed_grid = nullptr;  // 32^3 cells over render_aabb -> topology id of a nearby canonical triangle (deform.cu seed_bound)
 	float seed_lo[3] = {0, 0, 0}, seed_scale[3] = {0, 0, 0};
 	bool disable_seed_bound = false;  // INSTA_DEFORM_SEED=0: traversals start from FLT_MAX like the reference's (A/B measurements)
+	bool render_full_records = false; // INSTA_RENDER_RECORDS=full: insta_render_frame keeps the 27-float records between its kernels (A/B, parity tests)
 	uint32_t coherent_max_n = 1u << 19; // tracer batches below this many records use the thread-per-query kernel (INSTA_DEFORM_COHERENT_MAX)
 	uint32_t* d_counter = nullptr;    // 32 sample counters (128 B apart) of the persistent deform kernel
 	std::atomic<uint32_t> counter_rr{0};
@@ -188,7 +189,8 @@ void recorder_destroy(insta_ctx* ctx);
 int write_png_rgba8(const char* path, uint32_t w, uint32_t h, const uint8_t* rgba8);
 int write_depth_bin(const char* path, const uint32_t* depth_mm, size_t n);
 int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, int32_t frame_id, const int32_t* d_frame_ids,
-                  bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr, bool coherent_hint = false);
+                  bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr, bool coherent_hint = false,
+                  bool compact_extra = false);
 // hashgrid.cu
 int init_grid_levels(insta_ctx* ctx);
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s);
@@ -199,7 +201,8 @@ int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
 // mlp.cu
 uint32_t network_n_params(const insta_ctx* ctx);
 int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s,
-                       const uint32_t* d_n = nullptr);
+                       const uint32_t* d_n = nullptr,
+                       const float* d_uniform_extra = nullptr);
 // mlp_bwd.cu
 void network_bwd_destroy(insta_ctx* ctx);
 int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,

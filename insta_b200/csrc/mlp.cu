@@ -144,6 +144,7 @@ struct NetArgs {
 	const __half* params;   // MLP weights then the grid table
 	__half* out;
 	uint32_t out_stride;    // 0: 4 halves per sample; else out[i + c * out_stride]
+	const float* uniform_extra;  // nullable: records carry no expression floats; every sample takes these n_extra values, or all ones when its holder is -2
 	const uint32_t* n_ptr;  // nullable: device-side count, only min(n, *n_ptr) samples are evaluated
 	uint32_t density_only;  // NerfNetwork::density: records are bare positions, expression inputs = 1, out = one density logit per sample
 	GridLevels L;
@@ -214,10 +215,12 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 				}
 				// expression dims: floats [stride - n_extra, stride) -> K = 128 + 8 half_id .. (extract_expressions)
 				float ex[8];
+				const bool ones = a.density_only || (a.uniform_extra && __ldg(rec + 4) == -2.0f);
+				const float* exsrc = a.uniform_extra ? a.uniform_extra : rec + a.stride - a.n_extra;
 #pragma unroll
 				for (uint32_t k = 0; k < 8; ++k) {
 					const uint32_t d = half_id * 8 + k;
-					ex[k] = d < a.n_extra ? (a.density_only ? 1.0f : __ldg(rec + a.stride - a.n_extra + d)) : 0.0f;
+					ex[k] = d < a.n_extra ? (ones ? 1.0f : __ldg(exsrc + d)) : 0.0f;
 				}
 				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = make_uint4(pack2(ex[0], ex[1]), pack2(ex[2], ex[3]), pack2(ex[4], ex[5]), pack2(ex[6], ex[7]));
 			} else {
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 uint32_t network_n_params(const insta_ctx* ctx) { return kOffGrid + ctx->levels.offset[ctx->levels.n_levels] * 8u; }
 
 int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s,
-                       const uint32_t* d_n) {
+                       const uint32_t* d_n, const float* d_uniform_extra) {
 	if (n == 0) return INSTA_OK;
 	NetArgs a{};
 	a.records = d_records;
@@ -341,6 +344,7 @@ int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, 
 	a.out = (__half*)d_out;
 	a.out_stride = out_stride;
 	a.n_ptr = d_n;
+	a.uniform_extra = d_uniform_extra;
 	a.L = ctx->levels;
 	if (a.n_extra > 16) INSTA_FAIL(INSTA_ERR_INVALID, "network: more than 16 extra dims are not supported by the density MLP input (144 = 128 + 16)");
 	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));

@@ -420,7 +420,12 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
                  float* d_frame_rgba, float* d_frame_depth, insta_render_stats* stats, cudaStream_t s) {
 	Tracer* t = tracer_of(ctx);
 	const uint32_t n_pix = cam->resolution[0] * cam->resolution[1];
-	const uint32_t stride = 11 + ctx->p.exp_params + ctx->p.geo_params;
+	// Between this function's own kernels a record needs no expression floats: they are the same n_extra values for every sample of the frame, except
+	// that `warp` overwrites them with ones for samples whose triangle is outside the lips region (core.cu:515-519).  The compact record is the 11
+	// NerfCoordinate floats; the deformation flags "ones" in the holder slot (-2) and the network kernel reads the frame's values from d_extra_dims:
+	// 44 instead of 108 bytes per sample through march / deformation / network.  The frame is bit-identical (tests/test_gpu_nerf.py).
+	const bool compact = ctx->p.geo_params == 0 && !ctx->render_full_records;
+	const uint32_t stride = compact ? 11u : 11 + ctx->p.exp_params + ctx->p.geo_params;
 	// Steps per iteration: the reference marches clamp(rays initialised / n_alive, 1, 8) steps between two compactions, i.e. at most one record per
 	// pixel and launch -- a few hundred thousand records, which neither the deformation nor the network kernel can turn into throughput.  The frame
 	// does not depend on that schedule, so by default an iteration fills a budget of max(pixels, 2^21) records with up to 16 steps per ray
@@ -460,10 +465,10 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 		rc = tracer_generate(ctx, t->d_records, stride, ns, frame_id, d_extra_dims ? d_extra_dims : t->d_zero_extra, &n_rec, s);
 		if (rc) return rc;
 		if (deform) {
-			rc = launch_deform(ctx, t->d_records, n_rec, stride, frame_id, nullptr, false, nullptr, s, nullptr, /*coherent_hint=*/true);
+			rc = launch_deform(ctx, t->d_records, n_rec, stride, frame_id, nullptr, false, nullptr, s, nullptr, /*coherent_hint=*/true, compact);
 			if (rc) return rc;
 		}
-		rc = launch_network_fwd(ctx, t->d_records, stride, n_rec, d_params, t->d_net_out, 0, s);
+		rc = launch_network_fwd(ctx, t->d_records, stride, n_rec, d_params, t->d_net_out, 0, s, nullptr, compact ? (d_extra_dims ? d_extra_dims : t->d_zero_extra) : nullptr);
 		if (rc) return rc;
 		rc = tracer_composite(ctx, t->d_records, stride, t->d_net_out, 0, ns, d_frame_rgba, d_frame_depth, opts ? (int)opts->linear_colors : 0, &n_alive, s);
 		if (rc) return rc;

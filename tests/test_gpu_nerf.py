@@ -204,9 +204,12 @@ def test_render_frame_schedule_independent(gpu_ctx, scene):
         assert torch.equal(frames[ms][1].view(torch.int32), ref[1].view(torch.int32)), ms
 
 
-def test_render_frame_warp_queue_batches(scene, gpu_ctx, monkeypatch):
-    """Large tracer batches go through the warp-queue deformation kernel, small ones through the thread-per-query kernel (launch_deform): a
-    context that uses the warp-queue kernel for every batch renders the same frame bit for bit."""
+@pytest.mark.parametrize("env", [{"INSTA_DEFORM_COHERENT_MAX": "0"}, {"INSTA_RENDER_RECORDS": "full"}, {"INSTA_RENDER_RECORDS": "full", "INSTA_DEFORM_SEED": "0"}])
+def test_render_frame_internal_variants(scene, gpu_ctx, monkeypatch, env):
+    """insta_render_frame's internal choices do not change the frame, bit for bit: (a) large tracer batches go through the warp-queue deformation
+    kernel, small ones through the thread-per-query kernel -- a context that uses the warp-queue kernel for every batch; (b) between its own kernels
+    the records are the 11 NerfCoordinate floats (expression values from the frame's vector, `all ones` flagged in the holder slot) -- a context that
+    keeps the reference's 27-float records; (c) additionally without the seed bound of the traversal."""
     import torch
 
     from conftest import _make_ctx
@@ -221,7 +224,8 @@ def test_render_frame_warp_queue_batches(scene, gpu_ctx, monkeypatch):
     params = torch.from_numpy(pn).cuda()
     fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
     gpu_ctx.render_frame(cam, 1, params, fr, fd, bitfield=bf, extra_dims=extra)
-    monkeypatch.setenv("INSTA_DEFORM_COHERENT_MAX", "0")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     ctx = _make_ctx(scene)
     try:
         fr2, fd2 = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
@@ -229,5 +233,6 @@ def test_render_frame_warp_queue_batches(scene, gpu_ctx, monkeypatch):
         torch.cuda.synchronize()
     finally:
         ctx.close()
+    assert int((fr[:, 3] > 0.2).sum()) > 500
     assert torch.equal(fr2.view(torch.int32), fr.view(torch.int32))
     assert torch.equal(fd2.view(torch.int32), fd.view(torch.int32))
