@@ -28,8 +28,8 @@ BYTES_DEFORM = 1012
 BYTES_DEFORM_BLEND = 1300
 BYTES_ENCODE = 2316
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4,194,304-sample batch, from `ncu --set full` captures of this command
-# (profiles/r1_deform_wq_v11_ncu_summary.txt, profiles/r1_hash_fwd_v9_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = {"deform_kernel": 1049367000, "hash_fwd_kernel": 519730000}
+# (profiles/r1_deform_wq_v12_ncu_summary.txt, profiles/r1_hash_fwd_v9_ncu_summary.txt)
+NCU_TRAFFIC_BYTES = {"deform_kernel": 1042003000, "hash_fwd_kernel": 519730000}
 METRIC = "deformed+encoded samples/s (BVH+TBN+hash)"
 UNIT = "samples/s"
 
@@ -361,7 +361,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (453 MB records + 1.07 GB encodings per step, fresh record buffer each step)",
                        "timing": "CUDA events on the launching stream around the K timed steps (per-kernel events inside apportion it), max over ranks"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full, profiles/r1_%s_ncu_summary.txt" % ("deform_wq_v11" if dom == "deform_kernel" else "hash_fwd_v9"),
+                         "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full, profiles/r1_%s_ncu_summary.txt" % ("deform_wq_v12" if dom == "deform_kernel" else "hash_fwd_v9"),
                          "algorithmic_bytes": dom_bytes, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
                          "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},
             "kernels_ms": {"deform_kernel": float(t_deform.mean()), "hash_fwd_kernel": float(t_encode.mean())},

@@ -330,7 +330,9 @@ def main():
                        "network inference": ratio(ref.get("network_inference_ms"), ours["network"]["ms"]),
                        "network forward+backward (2^18)": ratio(ref.get("network_forward_backward_ms_2p18"), ours["network"]["forward_backward_ms_2p18"]),
                        "hash backward (2^18)": ratio(ref.get("kernel_grid_backward_ms_2p18"), ref.get("ours_hash_bwd_ms_2p18")),
-                       "training step": ratio((ref["train_step"] or {}).get("ms_per_step"), train["ms_per_step"]),
+                       # the ray count still drifts while the model trains: compare at the ray count the reference leg ran (= our last timed steps)
+                       "training step": ratio((ref["train_step"] or {}).get("ms_per_step"), float(np.mean(train["ms_steps"][-4:]))),
+                       "training step: ours ms at the reference leg's ray count": float(np.mean(train["ms_steps"][-4:])),
                        "512^2 frame": ratio((ref["render"] or {}).get("ms_per_frame"), render["ms_per_frame"])}}
     print(json.dumps(res))
     ctx.close()
