@@ -236,6 +236,7 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 		const char* k = getenv("INSTA_DEFORM_KERNEL");
 		ctx->force_legacy_deform = k && std::string(k) == "legacy";
 		ctx->force_wq_deform = k && std::string(k) == "wq";
+		if (const char* tr = getenv("INSTA_TRAIN_ROUNDS")) ctx->train_all_samples = std::string(tr) == "0";
 		if (const char* rr = getenv("INSTA_RENDER_RECORDS")) ctx->render_full_records = std::string(rr) == "full";
 		if (const char* sd = getenv("INSTA_DEFORM_SEED")) ctx->disable_seed_bound = std::string(sd) == "0";
 		if (const char* m = getenv("INSTA_DEFORM_COHERENT_MAX")) ctx->coherent_max_n = (uint32_t)strtoul(m, nullptr, 10);

@@ -154,6 +154,7 @@ struct insta_ctx {
 	uint16_t* d_seed_grid = nullptr;  // 32^3 cells over render_aabb -> topology id of a nearby canonical triangle (deform.cu seed_bound)
 	float seed_lo[3] = {0, 0, 0}, seed_scale[3] = {0, 0, 0};
 	bool disable_seed_bound = false;  // INSTA_DEFORM_SEED=0: traversals start from FLT_MAX like the reference's (A/B measurements)
+	bool train_all_samples = false;   // INSTA_TRAIN_ROUNDS=0: insta_train_nerf deforms / evaluates every generated sample like the reference (A/B, parity tests)
 	bool render_full_records = false; // INSTA_RENDER_RECORDS=full: insta_render_frame keeps the 27-float records between its kernels (A/B, parity tests)
 	uint32_t coherent_max_n = 1u << 19; // tracer batches below this many records use the thread-per-query kernel (INSTA_DEFORM_COHERENT_MAX)
 	uint32_t* d_counter = nullptr;    // 32 sample counters (128 B apart) of the persistent deform kernel
@@ -190,7 +191,8 @@ int write_png_rgba8(const char* path, uint32_t w, uint32_t h, const uint8_t* rgb
 int write_depth_bin(const char* path, const uint32_t* depth_mm, size_t n);
 int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, int32_t frame_id, const int32_t* d_frame_ids,
                   bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr, bool coherent_hint = false,
-                  bool compact_extra = false);
+                  bool compact_extra = false, const uint32_t* d_index = nullptr);
+bool deform_supports_index(const insta_ctx* ctx);
 // hashgrid.cu
 int init_grid_levels(insta_ctx* ctx);
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s);
@@ -202,7 +204,7 @@ int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
 uint32_t network_n_params(const insta_ctx* ctx);
 int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s,
                        const uint32_t* d_n = nullptr,
-                       const float* d_uniform_extra = nullptr);
+                       const float* d_uniform_extra = nullptr, const uint32_t* d_index = nullptr);
 // mlp_bwd.cu
 void network_bwd_destroy(insta_ctx* ctx);
 int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,
@@ -211,6 +213,8 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 void pcg_seed(uint64_t seed, uint64_t advance_steps, uint64_t& state, uint64_t& inc);  // pcg32{seed} advanced `advance_steps` x advance()
 int training_set_images(insta_ctx* ctx, const insta_train_image* h, uint32_t n);
 int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s);
+int train_round(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out, uint32_t out_width, uint32_t prev_lo, uint32_t prev_hi, uint32_t lo, uint32_t hi,
+                float* d_ray_T, uint32_t* d_index, uint32_t* d_count, cudaStream_t s);
 int train_loss(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out, uint32_t out_width, float* d_coords_compacted, void* d_dloss, float* d_loss,
                const float* d_mean_density, cudaStream_t s);
 int optimizer_step(insta_ctx* ctx, const insta_optimizer* o, uint32_t n_params, uint32_t n_matrix, cudaStream_t s);

@@ -144,6 +144,7 @@ struct NetArgs {
 	const __half* params;   // MLP weights then the grid table
 	__half* out;
 	uint32_t out_stride;    // 0: 4 halves per sample; else out[i + c * out_stride]
+	const uint32_t* index;       // nullable: sample k of the launch is record / output index[k] (the trainer's lazily evaluated rounds)
 	const float* uniform_extra;  // nullable: records carry no expression floats; every sample takes these n_extra values, or all ones when its holder is -2
 	const uint32_t* n_ptr;  // nullable: device-side count, only min(n, *n_ptr) samples are evaluated
 	uint32_t density_only;  // NerfNetwork::density: records are bare positions, expression inputs = 1, out = one density logit per sample
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 			unsigned char* A0 = smem + kSmA0 + b * kBytesA0 + (row >> 3) * 128 + (row & 7) * 16;
 			const uint32_t i = tile * kTileM + row;
 			if (i < n_samples) {
-				const float* rec = a.records + (size_t)i * a.stride;
+				const float* rec = a.records + (size_t)(a.index ? __ldg(a.index + i) : i) * a.stride;
 				const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
 #pragma unroll 2
 				for (uint32_t l = 0; l < 8; ++l) {
@@ -246,10 +247,11 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
 			const uint32_t b = it & 1u;
 			const uint32_t i = tile * kTileM + row;
+			const uint32_t si = (a.index && i < n_samples) ? __ldg(a.index + i) : i;  // record / output slot of this row's sample
 			// SH of the view direction while the first GEMM is in flight
 			float dx = 0.5f, dy = 0.5f, dz = 0.5f;
 			if (i < n_samples && !a.density_only) {
-				const float* rec = a.records + (size_t)i * a.stride;
+				const float* rec = a.records + (size_t)si * a.stride;
 				dx = __ldg(rec + 8); dy = __ldg(rec + 9); dz = __ldg(rec + 10);
 			}
 			// ---- density layer 1: A0 (144) -> 64 ----
@@ -308,14 +310,14 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 			if (i < n_samples) {
 				const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], sigma);
 				if (a.density_only) {
-					a.out[i] = __high2half(bs);
+					a.out[si] = __high2half(bs);
 				} else if (a.out_stride == 0) {
-					*reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
+					*reinterpret_cast<uint2*>(a.out + (size_t)si * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
 				} else {
-					a.out[i] = __low2half(rg);
-					a.out[i + (size_t)a.out_stride] = __high2half(rg);
-					a.out[i + 2 * (size_t)a.out_stride] = __low2half(bs);
-					a.out[i + 3 * (size_t)a.out_stride] = __high2half(bs);
+					a.out[si] = __low2half(rg);
+					a.out[si + (size_t)a.out_stride] = __high2half(rg);
+					a.out[si + 2 * (size_t)a.out_stride] = __low2half(bs);
+					a.out[si + 3 * (size_t)a.out_stride] = __high2half(bs);
 				}
 			}
 			// the next tile's first GEMM overwrites the accumulator columns: all reads above must have completed
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 uint32_t network_n_params(const insta_ctx* ctx) { return kOffGrid + ctx->levels.offset[ctx->levels.n_levels] * 8u; }
 
 int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, void* d_out, uint32_t out_stride, cudaStream_t s,
-                       const uint32_t* d_n, const float* d_uniform_extra) {
+                       const uint32_t* d_n, const float* d_uniform_extra, const uint32_t* d_index) {
 	if (n == 0) return INSTA_OK;
 	NetArgs a{};
 	a.records = d_records;
@@ -345,6 +347,7 @@ int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, 
 	a.out_stride = out_stride;
 	a.n_ptr = d_n;
 	a.uniform_extra = d_uniform_extra;
+	a.index = d_index;
 	a.L = ctx->levels;
 	if (a.n_extra > 16) INSTA_FAIL(INSTA_ERR_INVALID, "network: more than 16 extra dims are not supported by the density MLP input (144 = 128 + 16)");
 	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));

@@ -446,6 +446,78 @@ __global__ void __launch_bounds__(128) train_loss_kernel(const LossArgs a) {
 	}
 }
 
+// ---- lazily evaluated rounds ------------------------------------------------------------------------------------------------------------------
+// The reference deforms and evaluates EVERY generated sample before the loss kernel walks each ray front to back and stops at T < 1e-4
+// (testbed_nerf.cu:3290-3292, 1379-1401): nothing behind that sample is ever read -- not by the loss, not by the compaction, not by the backward pass.
+// With a trained model that is most of them (bench workload: 2.6 M generated, 0.27 M used).  The trainer therefore evaluates a ray's samples in rounds
+// ([0, 8), [8, 32), [32, end)): after each round this kernel replays the loss kernel's transmittance recurrence over the samples evaluated so far --
+// same expressions, same order, hence the same bits and the same stopping sample -- and only rays that are still transparent contribute their next
+// chunk to the index list the deformation and network kernels of the next round run over.  Everything the loss kernel reads has been evaluated by then.
+struct RoundArgs {
+	uint32_t stride, out_width;
+	uint32_t prev_lo, prev_hi, lo, hi;   // sample ranges (per ray) evaluated by the previous round / to be evaluated by this one; prev_hi == 0: first round
+	const uint32_t* ray_counter;
+	const uint32_t* numsteps;            // (count, base)
+	const float* coords;
+	const __half* net_out;
+	float* ray_T;                        // transmittance after the evaluated samples; < 0: the ray needs nothing more
+	uint32_t* index;                     // out: sample indices of this round
+	uint32_t* count;                     // out: their number
+};
+
+__global__ void __launch_bounds__(128) train_round_kernel(const RoundArgs a) {
+	constexpr uint32_t FULL = 0xffffffffu;
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+	if (i >= *a.ray_counter) return;
+	const uint32_t numsteps = a.numsteps[i * 2 + 0];
+	const uint32_t base = a.numsteps[i * 2 + 1];
+	const float EPSILON = 1e-4f;
+	const float max_step = min_stepsize() * (1 << (kCascades - 1));
+	float T = 1.f;
+	if (a.prev_hi > 0) {
+		T = a.ray_T[i];
+		if (T < 0.f) return;
+		const uint32_t end = min(a.prev_hi, numsteps);
+		bool stop = false;
+		for (uint32_t j0 = a.prev_lo; j0 < end && !stop; j0 += 32) {
+			const uint32_t cnt = min(32u, end - j0);
+			float alpha = 0.f;
+			if (lane < cnt) {
+				// exactly train_loss_kernel's `sample`: o3 = fourth half of the sample's output, density = __expf(o3), alpha = 1 - __expf(-density dt)
+				const size_t j = (size_t)base + j0 + lane;
+				const uint2 raw = *reinterpret_cast<const uint2*>(a.net_out + j * a.out_width);
+				const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+				const float o3 = hi.y;
+				const float dt = fmaf(a.coords[j * a.stride + 3], max_step - min_stepsize(), min_stepsize());
+				const float density = __expf(o3);
+				alpha = 1.f - __expf(-density * dt);
+			}
+			for (uint32_t k = 0; k < cnt; ++k) {
+				if (T < EPSILON) {
+					stop = true;
+					break;
+				}
+				const float ak = __shfl_sync(FULL, alpha, k);
+				T *= (1.f - ak);
+			}
+		}
+		// the loss kernel tests T before it touches the next sample
+		if (stop || T < EPSILON || end >= numsteps) {
+			if (lane == 0) a.ray_T[i] = -1.f;
+			return;
+		}
+	} else if (numsteps == 0) {
+		if (lane == 0) a.ray_T[i] = -1.f;
+		return;
+	}
+	const uint32_t n = min(a.hi, numsteps) - a.lo;
+	uint32_t pos = 0;
+	if (lane == 0) pos = atomicAdd(a.count, n);
+	pos = __shfl_sync(FULL, pos, 0);
+	for (uint32_t k = lane; k < n; k += 32) a.index[pos + k] = base + a.lo + k;
+	if (lane == 0) a.ray_T[i] = T;
+}
+
 // fill_rollover(_and_rescale): pad the compacted batch to exactly n_elements samples by repeating it
 template <typename T, bool RESCALE>
 __global__ void rollover_kernel(uint32_t n_elements, uint32_t stride, const uint32_t* __restrict__ n_input_ptr, T* __restrict__ inout) {
@@ -631,6 +703,26 @@ int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s) {
 	if (emit_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(train_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
 	train_emit_kernel<<<(a.max_samples + kEmitWarps * 32 - 1) / (kEmitWarps * 32), kEmitWarps * 32, emit_smem, s>>>(a);
 	ctx->launches += 2;
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+int train_round(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out, uint32_t out_width, uint32_t prev_lo, uint32_t prev_hi, uint32_t lo, uint32_t hi,
+                float* d_ray_T, uint32_t* d_index, uint32_t* d_count, cudaStream_t s) {
+	if (t->n_rays == 0) return INSTA_OK;
+	RoundArgs a{};
+	a.stride = t->stride_floats;
+	a.out_width = out_width;
+	a.prev_lo = prev_lo; a.prev_hi = prev_hi; a.lo = lo; a.hi = hi;
+	a.ray_counter = t->d_counters;
+	a.numsteps = t->d_numsteps;
+	a.coords = t->d_coords;
+	a.net_out = (const __half*)d_net_out;
+	a.ray_T = d_ray_T;
+	a.index = d_index;
+	a.count = d_count;
+	train_round_kernel<<<(t->n_rays + 3) / 4, 128, 0, s>>>(a);  // one warp per ray
+	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
 }

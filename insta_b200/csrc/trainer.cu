@@ -84,6 +84,10 @@ struct Trainer {
 	float* loss = nullptr;          // per ray
 	float* loss_sum = nullptr;      // one float
 	uint32_t* h_counters = nullptr; // pinned: 3 counters + loss sum
+	// lazily evaluated rounds (train.cu train_round_kernel)
+	float* ray_T = nullptr;         // per ray
+	uint32_t* round_index = nullptr; // sample indices of the current round (max_samples)
+	uint32_t* round_count = nullptr; // one counter per round
 	// Testbed::Nerf::Training::Counters (testbed.h:638-650)
 	uint32_t rays_per_batch = 1u << 12;
 	uint32_t n_rays_total = 0;
@@ -115,6 +119,7 @@ void free_trainer(Trainer* t) {
 	if (!t) return;
 	cudaFree(t->ray_indices); cudaFree(t->rays); cudaFree(t->numsteps); cudaFree(t->coords); cudaFree(t->mlp_out); cudaFree(t->dloss);
 	cudaFree(t->coords_compacted); cudaFree(t->counters); cudaFree(t->loss); cudaFree(t->loss_sum);
+	cudaFree(t->ray_T); cudaFree(t->round_index); cudaFree(t->round_count);
 	if (t->h_counters) cudaFreeHost(t->h_counters);
 	delete t;
 }
@@ -207,6 +212,9 @@ int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
 	if ((e = cudaMalloc(&t->coords_compacted, sizeof(float) * (size_t)target * stride)) != cudaSuccess) return fail(e);
 	if ((e = cudaMalloc(&t->counters, sizeof(uint32_t) * 4)) != cudaSuccess) return fail(e);
 	if ((e = cudaMalloc(&t->loss, sizeof(float) * kMaxRays)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->ray_T, sizeof(float) * kMaxRays)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->round_index, sizeof(uint32_t) * (size_t)max_samples)) != cudaSuccess) return fail(e);
+	if ((e = cudaMalloc(&t->round_count, sizeof(uint32_t) * 8)) != cudaSuccess) return fail(e);
 	if ((e = cudaMalloc(&t->loss_sum, sizeof(float))) != cudaSuccess) return fail(e);
 	if ((e = cudaHostAlloc(&t->h_counters, sizeof(uint32_t) * 4, cudaHostAllocDefault)) != cudaSuccess) return fail(e);
 	// the reference's arena memory is not cleared either, but stale records must at least be finite for the first step's kernels
@@ -288,10 +296,28 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 		rc = sync_frame_table(ctx, s);
 	}
 	if (rc) return rc;
-	rc = launch_deform(ctx, t->coords, st.max_samples, stride, -1, nullptr, false, nullptr, s, t->counters + 1);
-	if (rc) return rc;
-	rc = launch_network_fwd(ctx, t->coords, stride, st.max_samples, opt->d_params_f16, t->mlp_out, 0, s, t->counters + 1);
-	if (rc) return rc;
+	if (ctx->train_all_samples || !deform_supports_index(ctx)) {
+		rc = launch_deform(ctx, t->coords, st.max_samples, stride, -1, nullptr, false, nullptr, s, t->counters + 1);
+		if (rc) return rc;
+		rc = launch_network_fwd(ctx, t->coords, stride, st.max_samples, opt->d_params_f16, t->mlp_out, 0, s, t->counters + 1);
+		if (rc) return rc;
+	} else {
+		// Only the samples the loss kernel will read: rounds of [0, 8), [8, 32), [32, end) samples per ray, a ray drops out once its transmittance is
+		// below the loss kernel's threshold (train_round_kernel).  Device-side counts, no host round trip.
+		static const uint32_t kRounds[4] = {0u, 8u, 32u, 0xffffffffu};
+		INSTA_CUDA(cudaMemsetAsync(t->round_count, 0, sizeof(uint32_t) * 8, s));
+		for (int r = 0; r < 3; ++r) {
+			rc = train_round(ctx, &st, t->mlp_out, kOutWidth, r ? kRounds[r - 1] : 0u, r ? kRounds[r] : 0u, kRounds[r], kRounds[r + 1], t->ray_T, t->round_index,
+			                 t->round_count + r, s);
+			if (rc) return rc;
+			// upper bound of the round's size for the launch geometry; the kernels read the real count on the device
+			const uint64_t bound = r < 2 ? std::min<uint64_t>((uint64_t)n_rays * (kRounds[r + 1] - kRounds[r]), st.max_samples) : st.max_samples;
+			rc = launch_deform(ctx, t->coords, (uint32_t)bound, stride, -1, nullptr, false, nullptr, s, t->round_count + r, false, false, t->round_index);
+			if (rc) return rc;
+			rc = launch_network_fwd(ctx, t->coords, stride, (uint32_t)bound, opt->d_params_f16, t->mlp_out, 0, s, t->round_count + r, nullptr, t->round_index);
+			if (rc) return rc;
+		}
+	}
 	rc = train_loss(ctx, &st, t->mlp_out, kOutWidth, t->coords_compacted, t->dloss, t->loss, d_mean_density, s);
 	if (rc) return rc;
 	// forward + backward on the compacted, rolled-over batch (testbed_nerf.cu:3366-3371)

@@ -187,3 +187,53 @@ def test_step_without_occupied_cells_is_harmless(train_ctx, dataset):
     assert bool(torch.isfinite(S.p32).all())
     assert float((S.p32[25600:] - before[25600:]).abs().max()) == 0.0  # untouched grid entries are not updated (adam.h:75-79)
     ctx.trainer_destroy()
+
+
+def test_lazy_rounds_equal_full_evaluation(scene, train_ctx, dataset, monkeypatch):
+    """insta_train_nerf deforms / evaluates a ray's samples in rounds and drops a ray once its transmittance is below the loss kernel's threshold
+    (train_round_kernel); INSTA_TRAIN_ROUNDS=0 evaluates every generated sample like the reference.  The loss kernel reads nothing behind the stopping
+    sample, so one step from the same state must give the same counters (exactly), loss and gradients (up to the order of the compaction atomics,
+    as in test_full_step_matches_manual_composition) -- with a network dense enough that most rays stop within their first samples."""
+    import torch
+
+    from insta_b200 import capi
+
+    dev, bf, extra = dataset
+    mean_density = torch.tensor([0.02], device="cuda")
+    cfg = dict(target_batch_size=TARGET_STEP, rays_per_batch=1536, depth_weight=1.25, seg_weight=40.0, rng_seed=321)
+
+    def one_step(ctx):
+        S = State(ctx, seed=23)
+        S.p16[13312:13312 + 64] = 0.6  # positive density-logit row: rays saturate as with a trained model
+        S.p32 = S.p16.float()
+        ctx.trainer_create(**cfg)
+        hist = [ctx.train_nerf(S.optimizer(ctx), bf, extra, mean_density, get_loss_scalar=True)]
+        torch.cuda.synchronize()
+        ctx.trainer_destroy()
+        return S, hist
+
+    A, ha = one_step(train_ctx)
+    monkeypatch.setenv("INSTA_TRAIN_ROUNDS", "0")
+    full = capi.Context(device=0)
+    try:
+        full.set_canonical(scene.verts, scene.faces, scene.masks)
+        for v in train_ctx._frame_verts:
+            full.add_frame(v)
+        full.training_set_images(dev)
+        B, hb = one_step(full)
+    finally:
+        full.close()
+    a, b = ha[0], hb[0]
+    for k in ("n_rays", "n_rays_accepted", "measured_batch_size_before_compaction", "measured_batch_size", "rays_per_batch"):
+        assert a[k] == b[k], k
+    # a good part of the generated samples lies behind their ray's stopping point, i.e. the rounds had something to skip
+    assert a["measured_batch_size"] < 0.7 * a["measured_batch_size_before_compaction"] and a["measured_batch_size"] > 1000
+    assert abs(a["loss"] - b["loss"]) <= 1e-4 * abs(b["loss"]) and b["loss"] > 0
+    ga, gb = A.grads.float(), B.grads.float()
+    cos = torch.nn.functional.cosine_similarity
+    assert float(gb.abs().sum()) > 0
+    assert float(cos(ga[:25600], gb[:25600], dim=0)) > 0.99
+    assert float((touched := gb[25600:] != 0).float().sum()) > 0
+    assert float((touched != (ga[25600:] != 0)).float().mean()) < 2e-3
+    assert float(cos(ga[25600:], gb[25600:], dim=0)) > 0.98
+    assert float((A.p32 - B.p32).abs().mean()) < 1e-5
