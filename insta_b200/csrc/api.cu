@@ -237,6 +237,18 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 		ctx->force_legacy_deform = k && std::string(k) == "legacy";
 		ctx->force_wq_deform = k && std::string(k) == "wq";
 		if (const char* tr = getenv("INSTA_TRAIN_ROUNDS")) ctx->train_all_samples = std::string(tr) == "0";
+		if (const char* te = getenv("INSTA_TRAIN_ROUND_EDGES")) {  // e.g. "4,16,48": rounds [0,4) [4,16) [16,48) [48,end)
+			std::vector<uint32_t> e{0u};
+			for (const char* p = te; *p && e.size() < 7;) {
+				char* end = nullptr;
+				const unsigned long v = strtoul(p, &end, 10);
+				if (end == p) break;
+				if (v > e.back() && v < 0xffffffffu) e.push_back((uint32_t)v);
+				p = *end ? end + 1 : end;
+			}
+			e.push_back(0xffffffffu);
+			ctx->train_round_edges = e;
+		}
 		if (const char* rr = getenv("INSTA_RENDER_RECORDS")) ctx->render_full_records = std::string(rr) == "full";
 		if (const char* sd = getenv("INSTA_DEFORM_SEED")) ctx->disable_seed_bound = std::string(sd) == "0";
 		if (const char* m = getenv("INSTA_DEFORM_COHERENT_MAX")) ctx->coherent_max_n = (uint32_t)strtoul(m, nullptr, 10);

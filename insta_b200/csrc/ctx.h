@@ -154,6 +154,7 @@ struct insta_ctx {
 	uint16_t* d_seed_grid = nullptr;  // 32^3 cells over render_aabb -> topology id of a nearby canonical triangle (deform.cu seed_bound)
 	float seed_lo[3] = {0, 0, 0}, seed_scale[3] = {0, 0, 0};
 	bool disable_seed_bound = false;  // INSTA_DEFORM_SEED=0: traversals start from FLT_MAX like the reference's (A/B measurements)
+	std::vector<uint32_t> train_round_edges{0u, 8u, 32u, 0xffffffffu};  // per-ray sample ranges of the training step's rounds (at most 7 rounds)
 	bool train_all_samples = false;   // INSTA_TRAIN_ROUNDS=0: insta_train_nerf deforms / evaluates every generated sample like the reference (A/B, parity tests)
 	bool render_full_records = false; // INSTA_RENDER_RECORDS=full: insta_render_frame keeps the 27-float records between its kernels (A/B, parity tests)
 	uint32_t coherent_max_n = 1u << 19; // tracer batches below this many records use the thread-per-query kernel (INSTA_DEFORM_COHERENT_MAX)

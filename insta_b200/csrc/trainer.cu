@@ -304,14 +304,15 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	} else {
 		// Only the samples the loss kernel will read: rounds of [0, 8), [8, 32), [32, end) samples per ray, a ray drops out once its transmittance is
 		// below the loss kernel's threshold (train_round_kernel).  Device-side counts, no host round trip.
-		static const uint32_t kRounds[4] = {0u, 8u, 32u, 0xffffffffu};
+		const std::vector<uint32_t>& edges = ctx->train_round_edges;  // {0, 8, 32, UINT32_MAX} by default (INSTA_TRAIN_ROUND_EDGES)
+		const int n_rounds = (int)edges.size() - 1;
 		INSTA_CUDA(cudaMemsetAsync(t->round_count, 0, sizeof(uint32_t) * 8, s));
-		for (int r = 0; r < 3; ++r) {
-			rc = train_round(ctx, &st, t->mlp_out, kOutWidth, r ? kRounds[r - 1] : 0u, r ? kRounds[r] : 0u, kRounds[r], kRounds[r + 1], t->ray_T, t->round_index,
+		for (int r = 0; r < n_rounds; ++r) {
+			rc = train_round(ctx, &st, t->mlp_out, kOutWidth, r ? edges[r - 1] : 0u, r ? edges[r] : 0u, edges[r], edges[r + 1], t->ray_T, t->round_index,
 			                 t->round_count + r, s);
 			if (rc) return rc;
 			// upper bound of the round's size for the launch geometry; the kernels read the real count on the device
-			const uint64_t bound = r < 2 ? std::min<uint64_t>((uint64_t)n_rays * (kRounds[r + 1] - kRounds[r]), st.max_samples) : st.max_samples;
+			const uint64_t bound = edges[r + 1] != 0xffffffffu ? std::min<uint64_t>((uint64_t)n_rays * (edges[r + 1] - edges[r]), st.max_samples) : st.max_samples;
 			rc = launch_deform(ctx, t->coords, (uint32_t)bound, stride, -1, nullptr, false, nullptr, s, t->round_count + r, false, false, t->round_index);
 			if (rc) return rc;
 			rc = launch_network_fwd(ctx, t->coords, stride, (uint32_t)bound, opt->d_params_f16, t->mlp_out, 0, s, t->round_count + r, nullptr, t->round_index);
