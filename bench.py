@@ -363,6 +363,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full, profiles/r1_%s_ncu_summary.txt" % ("deform_wq_v12" if dom == "deform_kernel" else "hash_fwd_v9"),
                          "algorithmic_bytes": dom_bytes, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
+                         "note": ("deform_wq_kernel is bound by instruction issue and L1/LSU, not by HBM: ncu 48 % issue slots, LSU pipe 68 %, DRAM 3 % "
+                                  "(profiles/r1_deform_wq_v12_ncu_summary.txt); traffic = the record buffer read + written once; the 1,012 algorithmic bytes are "
+                                  "mostly BVH node / triangle gathers served by L1 / L2 (see l2_gather_roofline)") if dom == "deform_kernel" else
+                                 "hash_fwd_kernel is bound by L1 gather wavefronts (16-byte entries from the L2-resident table), see l2_gather_roofline",
                          "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},
             "kernels_ms": {"deform_kernel": float(t_deform.mean()), "hash_fwd_kernel": float(t_encode.mean())},
             "step_ms_percentiles": {"p10": float(np.percentile(step_ms, 10)), "p50": float(np.percentile(step_ms, 50)), "p90": float(np.percentile(step_ms, 90))},
