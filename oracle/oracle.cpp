@@ -122,12 +122,14 @@ inline void box_of(const orc_tri* begin, const orc_tri* end, float* mn, float* m
 	}
 }
 
-// closest_triangle, bvh.cuh:48-96.  Returns BVH-order index; *dist = sqrt(best).
-inline int closest_tri(V3 p, const orc_node* nodes, const orc_tri* tris, float* dist) {
+// closest_triangle, bvh.cuh:48-96.  Returns BVH-order index; *dist = sqrt(best).  init_best: the reference's max_distance_sq argument (bvh.cuh:48,
+// FLT_MAX at every call site of the path); the product starts from a finite upper bound instead, tests/test_oracle_seed_bound.py checks that this
+// cannot change the triangle.
+inline int closest_tri(V3 p, const orc_node* nodes, const orc_tri* tris, float* dist, float init_best = std::numeric_limits<float>::max()) {
 	int stack[64];
 	int sp = 0;
 	stack[sp++] = 0;
-	float best = std::numeric_limits<float>::max();
+	float best = init_best;
 	int best_i = -1;
 	while (sp > 0) {
 		int idx = stack[--sp];
@@ -544,6 +546,11 @@ void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const 
 	}
 }
 
+
+void orc_closest_triangle_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, int* out_idx, int n_threads) {
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+	for (int i = 0; i < n; ++i) out_idx[i] = closest_tri(v3(pts + 3 * i), nodes, tris, nullptr, init_best[i]);
+}
 
 // Diagnostic (design studies only): traversal statistics of closest_tri with the product's pop-time rule for inner nodes.
 // out8 = {expands, inner entries dropped at pop, leaf visits, triangle tests, leaf visits whose box distance exceeded

@@ -51,6 +51,8 @@ void orc_triangle_masks(const uint32_t* faces, uint32_t n_faces, const int32_t* 
 int orc_bvh_build(orc_tri* tris_inout, int n_tris, int leaf_size, orc_node* nodes_out, int max_nodes);
 void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, int* out_idx, float* out_dist,
                           int n_threads);
+/* closest_triangle started from max_distance_sq = init_best[i] instead of FLT_MAX (bvh.cuh:48) */
+void orc_closest_triangle_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, int* out_idx, int n_threads);
 /* diagnostic: traversal statistics (see oracle.cpp) */
 void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, double* out8);
 void orc_closest_stats_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, double* out8);

@@ -68,6 +68,14 @@ class _Lib:
         self._fn("closest_triangle")(_p(pts), C.c_int(n), _p(nodes), _p(tris), _p(idx), _p(dist), C.c_int(n_threads or self.max_threads))
         return idx, dist
 
+    def closest_triangle_bounded(self, pts, nodes, tris, init_best, n_threads=None):
+        """closest_triangle with max_distance_sq = init_best[i] (bvh.cuh:48) instead of FLT_MAX; oracle only."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        ib = np.ascontiguousarray(init_best, np.float32)
+        idx = np.empty(len(pts), np.int32)
+        self._fn("closest_triangle_bounded")(_p(pts), C.c_int(len(pts)), _p(nodes), _p(tris), _p(ib), _p(idx), C.c_int(n_threads or self.max_threads))
+        return idx
+
     def warp(self, samples, stride, frame_id, nodes_list, tris_bvh_list, tris_topo_list, tris_canon, adjacency, aabb6,
              disable_interp=False, extra_dims=16, use_geo=False, frame_ids=None, n_threads=None):
         """In-place on `samples` (float32, n*stride). Returns (topology tri id, bvh-order idx) per sample."""
