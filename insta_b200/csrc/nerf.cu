@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(128) nerf_init_rays_kernel(const RenderArgs a,
 // buffer; records of steps the ray never reaches keep holder = -1 (so the deformation skips them).
 // The 32 records a warp produces for one step are contiguous in the buffer ((i0 + j n_alive) .. + 31): they are assembled in shared
 // memory and leave as full-line stores (27 scalar stores per record, each touching 32 different lines, otherwise).
+constexpr int kMarchChunk = 16;  // steps marched per lane before the warp writes their records
+
 __global__ void __launch_bounds__(128) nerf_march_kernel(const RenderArgs a, RaySet rays, const uint32_t n_alive, float* __restrict__ records, const uint32_t stride,
                                                          const uint32_t n_steps, const float frame_id, const float* __restrict__ extra_dims, const uint32_t n_extra) {
 	extern __shared__ float march_smem[];
@@ -153,38 +155,51 @@ __global__ void __launch_bounds__(128) nerf_march_kernel(const RenderArgs a, Ray
 	}
 	uint32_t steps = 0;   // samples this ray generated in this round
 	bool left = !mine;    // steps after the one where the ray left the box are never composited: holder = -1 marks them as padding
-	for (uint32_t j = 0; j < n_steps; ++j) {
-		if (!left) {
-			float px, py, pz, dt;
-			while (true) {
-				px = fmaf(dx, t, ox); py = fmaf(dy, t, oy); pz = fmaf(dz, t, oz);
-				if (!aabb_contains(a.render_aabb, px, py, pz)) {
-					left = true;
-					break;
-				}
-				dt = calc_dt(t, a.cone_angle);
-				const uint32_t mip = max(a.min_mip, (uint32_t)mip_from_dt(dt, px, py, pz));
-				if (!a.bitfield || occupied_at(px, py, pz, a.bitfield, mip)) break;
-				t = advance_to_next_voxel(t, a.cone_angle, px, py, pz, dx, dy, dz, ix, iy, iz, kGrid >> mip);
+	// Phase 1 (per lane, no warp synchronisation): the ray's next <= kMarchChunk samples.  ONE loop whose iteration is one probe of the occupancy
+	// grid -- it either emits a sample or skips to the next voxel -- so lanes that are at different steps still execute the same instructions
+	// together and the warp takes as long as its longest ray.  (A loop over steps with the skip loop inside made every step wait for the one lane
+	// that was crossing empty space at that step: ncu showed the skip loop running with 1 of 32 threads, 215 us per launch whatever the ray count.)
+	// Phase 2: the 32 records of a step are assembled in shared memory and leave as full-line stores.
+	float4* stepbuf = reinterpret_cast<float4*>(march_smem + (size_t)(blockDim.x >> 5) * 32u * stride) + (size_t)warp * kMarchChunk * 32u;
+	for (uint32_t j0 = 0; j0 < n_steps; j0 += kMarchChunk) {
+		const uint32_t cn = min((uint32_t)kMarchChunk, n_steps - j0);
+		uint32_t k = 0;
+		while (!left && k < cn) {
+			const float px = fmaf(dx, t, ox), py = fmaf(dy, t, oy), pz = fmaf(dz, t, oz);
+			if (!aabb_contains(a.render_aabb, px, py, pz)) {
+				left = true;
+				break;
 			}
-			if (!left) {
-				// warp_position(pos, train_aabb) = (pos - min) / diag
-				const float wx = (px - a.train_aabb[0]) / (a.train_aabb[3] - a.train_aabb[0]);
-				const float wy = (py - a.train_aabb[1]) / (a.train_aabb[4] - a.train_aabb[1]);
-				const float wz = (pz - a.train_aabb[2]) / (a.train_aabb[5] - a.train_aabb[2]);
-				my[0] = wx; my[1] = wy; my[2] = wz;
-				my[3] = (dt - min_stepsize()) / (max_step - min_stepsize());  // warp_dt
-				my[4] = frame_id;
-				my[5] = wx; my[6] = wy; my[7] = wz;
+			const float dt = calc_dt(t, a.cone_angle);
+			const uint32_t mip = max(a.min_mip, (uint32_t)mip_from_dt(dt, px, py, pz));
+			if (!a.bitfield || occupied_at(px, py, pz, a.bitfield, mip)) {
+				// warp_position(pos, train_aabb) = (pos - min) / diag; warp_dt
+				stepbuf[k * 32u + lane] = make_float4((px - a.train_aabb[0]) / (a.train_aabb[3] - a.train_aabb[0]), (py - a.train_aabb[1]) / (a.train_aabb[4] - a.train_aabb[1]),
+				                                      (pz - a.train_aabb[2]) / (a.train_aabb[5] - a.train_aabb[2]), (dt - min_stepsize()) / (max_step - min_stepsize()));
 				t += dt;
 				++steps;
+				++k;
+			} else {
+				t = advance_to_next_voxel(t, a.cone_angle, px, py, pz, dx, dy, dz, ix, iy, iz, kGrid >> mip);
 			}
 		}
-		if (left) my[4] = -1.0f;
+		for (; k < cn; ++k) stepbuf[k * 32u + lane] = make_float4(0.f, 0.f, 0.f, -1.0f);  // warped dt is never negative: marks a step the ray does not reach
 		__syncwarp();
-		float* dst = records + (size_t)(i0 + j * n_alive) * stride;
-		for (uint32_t k = lane; k < cnt * stride; k += 32) dst[k] = tile[k];
-		__syncwarp();
+		for (k = 0; k < cn; ++k) {
+			const float4 v = stepbuf[k * 32u + lane];
+			if (v.w >= 0.0f) {
+				my[0] = v.x; my[1] = v.y; my[2] = v.z;
+				my[3] = v.w;
+				my[4] = frame_id;
+				my[5] = v.x; my[6] = v.y; my[7] = v.z;
+			} else {
+				my[4] = -1.0f;
+			}
+			__syncwarp();
+			float* dst = records + (size_t)(i0 + (j0 + k) * n_alive) * stride;
+			for (uint32_t q = lane; q < cnt * stride; q += 32) dst[q] = tile[q];
+			__syncwarp();
+		}
 	}
 	if (mine) {
 		rays.o_t[i].w = t;
@@ -381,7 +396,7 @@ int tracer_generate(insta_ctx* ctx, float* d_records, uint32_t stride, uint32_t 
 	if (n_records) *n_records = t->n_alive * n_steps;
 	if (t->n_alive == 0) return INSTA_OK;
 	if (stride < 11) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_generate_samples: stride < 11");
-	const size_t march_smem = (size_t)4 * 32 * stride * sizeof(float);
+	const size_t march_smem = (size_t)4 * 32 * stride * sizeof(float) + (size_t)4 * kMarchChunk * 32 * sizeof(float4);
 	if (march_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(nerf_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem));
 	nerf_march_kernel<<<(t->n_alive + 127) / 128, 128, march_smem, s>>>(t->args, t->set[t->cur], t->n_alive, d_records, stride, n_steps, (float)frame_id,
 	                                                                    d_extra_dims, stride - 11);
