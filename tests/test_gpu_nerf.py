@@ -191,7 +191,7 @@ def test_render_frame_schedule_independent(gpu_ctx, scene):
     pn[13312:13312 + 64] = np.float16(0.6)  # rays saturate (see test_render_frame_vs_reference_tracer)
     params = torch.from_numpy(pn).cuda()
     frames = {}
-    for ms in (8, 0, 1, 3):
+    for ms in (8, 0, 1, 3, 40):  # 40: more than one 16-step chunk of the march kernel per iteration
         fr, fd = torch.zeros((n, 4), device="cuda"), torch.zeros(n, device="cuda")
         iters, samples = gpu_ctx.render_frame(cam, 1, params, fr, fd, bitfield=bf, extra_dims=extra, max_steps=ms)
         torch.cuda.synchronize()
@@ -199,7 +199,7 @@ def test_render_frame_schedule_independent(gpu_ctx, scene):
     ref = frames[8]
     assert int((ref[0][:, 3] > 0.2).sum()) > 500
     assert frames[0][2] < ref[2] < frames[1][2]  # fewer, larger iterations by default; one step per iteration needs the most
-    for ms in (0, 1, 3):
+    for ms in (0, 1, 3, 40):
         assert torch.equal(frames[ms][0].view(torch.int32), ref[0].view(torch.int32)), ms
         assert torch.equal(frames[ms][1].view(torch.int32), ref[1].view(torch.int32)), ms
 
