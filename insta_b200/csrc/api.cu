@@ -385,16 +385,30 @@ int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t 
 	// while batch k+1 is being built, batch k goes to the device as ONE allocation with asynchronous copies and one stream sync (a cudaMalloc, three
 	// blocking copies and a sync per frame made the upload, not the build, the bottleneck: 523 frames/s on 16 threads).
 	const uint32_t batch = std::max(32u, n_threads * 4);
+	std::atomic<bool> build_failed{false};  // an exception must not leave a worker thread (std::terminate): it becomes an error return
 	auto build_batch = [&](uint32_t b0, uint32_t b1, std::vector<HostBvh>& out) {
-		out.clear();
-		out.resize(b1 - b0);
+		try {
+			out.clear();
+			out.resize(b1 - b0);
+		} catch (...) {
+			build_failed = true;
+			return;
+		}
 		std::atomic<uint32_t> next{b0};
 		std::vector<std::thread> pool;
 		const uint32_t nt = std::min(n_threads, b1 - b0);
-		for (uint32_t t = 0; t < nt; ++t)
-			pool.emplace_back([&]() {
+		auto work = [&]() {
+			try {
 				for (uint32_t i; (i = next.fetch_add(1)) < b1;) prepare_frame(ctx, h_verts + per * i, out[i - b0]);
-			});
+			} catch (...) {
+				build_failed = true;
+			}
+		};
+		try {
+			for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(work);
+		} catch (...) {  // thread creation failed: the calling thread finishes the batch alone
+		}
+		work();
 		for (auto& t : pool) t.join();
 	};
 	std::vector<HostBvh> cur, nxt;
@@ -403,8 +417,9 @@ int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t 
 		const uint32_t b1 = std::min(n, b0 + batch), b2 = std::min(n, b1 + batch);
 		std::thread builder;
 		if (b1 < n) builder = std::thread([&]() { build_batch(b1, b2, nxt); });
-		const int rc = upload_frames(ctx, h_verts + per * b0, cur);
+		const int rc = build_failed ? INSTA_OK : upload_frames(ctx, h_verts + per * b0, cur);
 		if (builder.joinable()) builder.join();
+		if (build_failed) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frames: a host BVH build failed (out of memory?)");
 		if (rc) return rc;
 		cur.swap(nxt);
 	}
