@@ -672,7 +672,7 @@ def main():
     ap.add_argument("--render-max-steps", type=int, default=0, help="insta_render_opts.max_steps_per_iteration of the render leg (0 = library default, 8 = the reference's schedule)")
     ap.add_argument("--train-images", type=int, default=128, help="synthetic 512^2 training images (= frames) per GPU in the train-step leg")
     ap.add_argument("--train-steps", type=int, default=20)
-    ap.add_argument("--train-warmup", type=int, default=70, help="untimed steps before the timed ones: rays_per_batch grows ~9 % per step from 4096 and needs ~65 steps to reach its fixed point")
+    ap.add_argument("--train-warmup", type=int, default=70, help="untimed steps before the timed ones: rays_per_batch grows ~9 %% per step from 4096 and needs ~65 steps to reach its fixed point")
     ap.add_argument("--stress", action="store_true", help="also run configs[4]: 2048^2 render, 4000 resident BVHs, 2^22-entry hash table")
     ap.add_argument("--stress-frames", type=int, default=4000)
     ap.add_argument("--stress-renders", type=int, default=4)

@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1700)
     ap.add_argument("--train-images", type=int, default=128)
     ap.add_argument("--train-steps", type=int, default=20)
-    ap.add_argument("--train-warmup", type=int, default=70, help="untimed steps before the timed ones: rays_per_batch grows ~9 % per step from 4096 and needs ~65 steps to reach its fixed point")
+    ap.add_argument("--train-warmup", type=int, default=70, help="untimed steps before the timed ones: rays_per_batch grows ~9 %% per step from 4096 and needs ~65 steps to reach its fixed point")
     ap.add_argument("--ref-train-steps", type=int, default=6)
     ap.add_argument("--render-res", type=int, default=512)
     ap.add_argument("--render-frames", type=int, default=8)

@@ -29,3 +29,13 @@ def test_other_ranks_of_the_reference_arm_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"], capture_output=True, text=True, timeout=300,
                          cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_help_prints():
+    """argparse %-formats help strings: a stray percent sign only shows up when somebody asks for --help"""
+    import subprocess
+    import sys
+
+    for script in ("bench.py", os.path.join("tests", "bench_ref_cuda.py")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, script), "--help"], capture_output=True, text=True)
+        assert r.returncode == 0 and "--steps" in r.stdout, (script, r.stderr[-300:])
