@@ -27,9 +27,11 @@ STRIDE = 27
 BYTES_DEFORM = 1012
 BYTES_DEFORM_BLEND = 1300
 BYTES_ENCODE = 2316
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4,194,304-sample batch, from `ncu --set full` captures of this command
-# (profiles/r1_deform_wq_v12_ncu_summary.txt, profiles/r1_hash_fwd_v9_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = {"deform_kernel": 1042003000, "hash_fwd_kernel": 519730000}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4,194,304-sample batch, from `ncu --set full` captures of THIS command's configuration
+# (1,700 frames; profiles/r2_deform_ncu_summary.txt: deform_pf_kernel + transform_kernel, profiles/r2_hash_fwd_ncu_summary.txt; tools/ncu_summary.py adds
+# the two counters in bytes)
+NCU_TRAFFIC_BYTES = {"deform_kernel": None, "hash_fwd_kernel": None}
+NCU_TRAFFIC_SOURCE = {"deform_kernel": "profiles/r2_deform_ncu_summary.txt", "hash_fwd_kernel": "profiles/r2_hash_fwd_ncu_summary.txt"}
 METRIC = "deformed+encoded samples/s (BVH+TBN+hash)"
 UNIT = "samples/s"
 
@@ -99,6 +101,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Host threads the CPU legs may use: the cores this process is allowed on, NOT omp_get_max_threads() -- torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which made the round-1 reference arm run on one core at N >= 2."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def build_scene(n_frames, rank, world):
     """Canonical mesh + this rank's shard of the synthetic frames (rank r holds frames r, r+R, ...: SURVEY.md 8e)."""
     from insta_b200 import shard, synth
@@ -150,7 +161,7 @@ def cpu_reference_leg(verts, faces, masks, frame_verts, n_sample, steps, warmup,
     table = synth.make_grid_table(int(layout[0][-1]))
     rec0, _ = make_batch(verts, n_sample, len(frame_verts), regime, seed=7)
     unit = np.array([0, 0, 0, 1, 1, 1], np.float32)
-    threads = W.max_threads
+    threads = host_threads()
     times = []
     for it in range(warmup + steps):
         rec = rec0.copy()
@@ -177,7 +188,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    n_frames = min(args.frames, 64)  # host BVH builds only for the frames the bounded sample touches
+    n_frames = args.frames if args.regime == "train" else 1  # the same scene as our arm (host BVH builds for every frame: a few seconds, untimed)
     verts, faces, masks, fv = build_scene(n_frames, 0, 1)
     n_sample = args.cpu_sample
     cb, sec_per_step = cpu_reference_leg(verts, faces, masks, list(fv), n_sample, args.steps, args.warmup, args.regime)
@@ -312,18 +323,33 @@ def run_ours(args):
         e2e_total = float(t.item())
     e2e_value = world * N_SAMPLES * len(e2e_t) / e2e_total
 
+    # ---- the reference's own CUDA kernels on the same device buffers (test infrastructure, oracle/ref_legs.py): AFTER our timed regions, rank 0 at N = 1 ----
+    refc = None
+    ref_hooks = {}
+    if rank == 0 and world == 1 and not args.no_ref_cuda:
+        try:
+            from oracle import pyrefcuda, ref_legs
+
+            if pyrefcuda.available():
+                args.ref_train_steps = 6
+                refc = ref_legs.ref_cuda_leg(verts, faces, masks, fv, rec_np, table, out, args)
+                ref_hooks = {"train": ref_legs.ref_train_leg, "render": ref_legs.ref_render_leg}
+            else:
+                refc = {"unavailable": "oracle/_ref/libref_cuda.so not built (oracle/Makefile: refcuda)"}
+        except Exception as e:
+            refc = {"error": repr(e)}
     net = rnd = trn = None
     if not args.no_render:
         net = network_leg(ctx, rec_np, args) if rank == 0 else None
         del bufs, pristine, h_rec0, h_rec, h_out  # the legs below bring their own buffers
         torch.cuda.empty_cache()
         try:
-            trn = train_leg(ctx, verts, fv, args, rank, world)
+            trn = train_leg(ctx, verts, fv, args, rank, world, ref_hook=ref_hooks.get("train"))
         except Exception as e:
             if world > 1:
                 raise
             trn = {"error": repr(e)}
-        rnd = render_leg(ctx, verts, fv, args, rank, world)
+        rnd = render_leg(ctx, verts, fv, args, rank, world, ref_hook=ref_hooks.get("render"))
         if world > 1:
             # frames are sharded over ranks: aggregate frames/s = sum over ranks, ms/frame reported = max over ranks
             t = torch.tensor([rnd["ms_per_frame"] if rnd else 0.0], device="cuda", dtype=torch.float64)
@@ -343,7 +369,7 @@ def run_ours(args):
         except Exception as e:
             gather = {"error": repr(e)}
     stress = None
-    if args.stress:
+    if not args.no_stress:
         stress = stress_leg(args, rank, world)
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -361,11 +387,11 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (453 MB records + 1.07 GB encodings per step, fresh record buffer each step)",
                        "timing": "CUDA events on the launching stream around the K timed steps (per-kernel events inside apportion it), max over ranks"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full, profiles/r1_%s_ncu_summary.txt" % ("deform_wq_v12" if dom == "deform_kernel" else "hash_fwd_v9"),
+                         "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full of this configuration, %s" % NCU_TRAFFIC_SOURCE.get(dom),
                          "algorithmic_bytes": dom_bytes, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
-                         "note": ("deform_wq_kernel is bound by instruction issue and L1/LSU, not by HBM: ncu 48 % issue slots, LSU pipe 68 %, DRAM 3 % "
-                                  "(profiles/r1_deform_wq_v12_ncu_summary.txt); traffic = the record buffer read + written once; the 1,012 algorithmic bytes are "
-                                  "mostly BVH node / triangle gathers served by L1 / L2 (see l2_gather_roofline)") if dom == "deform_kernel" else
+                         "note": ("stage 1 = deform_pf_kernel (closest triangle) + transform_kernel (TBN): bound by instruction issue and the LSU / shared-memory pipe, "
+                                  "not by HBM (ncu: profiles/r2_deform_ncu_summary.txt); traffic = the record buffer read twice + written once; the 1,012 algorithmic "
+                                  "bytes are mostly BVH node / triangle gathers served by L2 (see l2_gather_roofline)") if dom == "deform_kernel" else
                                  "hash_fwd_kernel is bound by L1 gather wavefronts (16-byte entries from the L2-resident table), see l2_gather_roofline",
                          "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},
             "kernels_ms": {"deform_kernel": float(t_deform.mean()), "hash_fwd_kernel": float(t_encode.mean())},
@@ -389,11 +415,21 @@ def run_ours(args):
                 line["cpu_baseline"] = cb
             except Exception as e:  # the checker is optional for the measurement itself
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+        line["ref_cuda"] = refc
+        if refc and refc.get("value"):
+            line["speedup_vs_ref_cuda"] = {"deformed+encoded samples/s": line["value"] / refc["value"],
+                                           "note": "device-timed value over the reference's own `warp` + kernel_grid (nvcc 12.9, sm_100) on the same buffers, same run"}
+            if rnd and isinstance(rnd.get("ref_cuda"), dict) and rnd["ref_cuda"].get("ms_per_frame"):
+                line["speedup_vs_ref_cuda"]["512^2 frame"] = rnd["ref_cuda"]["ms_per_frame"] / rnd["ms_per_frame"]
+            if trn and isinstance(trn.get("ref_cuda"), dict) and trn["ref_cuda"].get("ms_per_step"):
+                line["speedup_vs_ref_cuda"]["training step"] = trn["ref_cuda"]["ms_per_step"] / float(np.mean(trn["ms_steps"][-4:]))
+            if net and refc.get("network_inference_ms"):
+                line["speedup_vs_ref_cuda"]["network inference"] = refc["network_inference_ms"] / net["ms"]
         if not args.no_render:
             line["network"] = net
             line["render"] = rnd
             line["train_step"] = trn
-        if args.stress:
+        if not args.no_stress:
             line["stress"] = stress
         print(json.dumps(line))
     ctx.close()
@@ -673,10 +709,11 @@ def main():
     ap.add_argument("--train-images", type=int, default=128, help="synthetic 512^2 training images (= frames) per GPU in the train-step leg")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-warmup", type=int, default=70, help="untimed steps before the timed ones: rays_per_batch grows ~9 %% per step from 4096 and needs ~65 steps to reach its fixed point")
-    ap.add_argument("--stress", action="store_true", help="also run configs[4]: 2048^2 render, 4000 resident BVHs, 2^22-entry hash table")
+    ap.add_argument("--stress", action="store_true", help="accepted for compatibility: configs[4] (2048^2 render, 4000 resident BVHs, 2^22-entry hash table) runs by default")
+    ap.add_argument("--no-stress", action="store_true", help="skip configs[4]")
     ap.add_argument("--stress-frames", type=int, default=4000)
     ap.add_argument("--stress-renders", type=int, default=4)
-    ap.add_argument("--no-ref-cuda", action="store_true", help="accepted for compatibility: the reference-CUDA comparison lives in tests/bench_ref_cuda.py")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the legs that run the reference's own CUDA kernels (oracle/_ref) beside ours after the timed regions")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

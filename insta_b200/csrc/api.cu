@@ -24,6 +24,20 @@ int sync_frame_table(insta_ctx* ctx, cudaStream_t s) {
 	}
 	std::vector<FrameDev> host(n);
 	for (uint32_t i = 0; i < n; ++i) host[i] = ctx->frames[i].dev;
+	ctx->layout_uniform = n > 0;
+	uint64_t lo = ~0ull, hi = 0;
+	for (uint32_t i = 0; i < n; ++i) {
+		const uint64_t q = (uint64_t)host[i].quads, to = (uint64_t)host[i].tris - q, xo = (uint64_t)host[i].xf - q;
+		if (i == 0) {
+			ctx->tris_off = (uint32_t)to;
+			ctx->xf_off = (uint32_t)xo;
+		}
+		if (to != ctx->tris_off || xo != ctx->xf_off || (uint64_t)host[i].tris < q || (uint64_t)host[i].xf < (uint64_t)host[i].tris) ctx->layout_uniform = false;
+		lo = std::min(lo, q);
+		hi = std::max(hi, (uint64_t)host[i].xf + (uint64_t)ctx->n_faces * sizeof(TriXf));
+	}
+	ctx->arena = (const unsigned char*)lo;
+	if (n && ((lo & 15u) || ((uint64_t)ctx->tris_off & 15u) || hi - lo >= (1ull << 36))) ctx->layout_uniform = false;
 	if (n) INSTA_CUDA(cudaMemcpyAsync(ctx->d_frame_table, host.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice, s));
 	INSTA_CUDA(cudaStreamSynchronize(s));  // `host` is pageable and goes out of scope
 	ctx->frame_table_dirty = false;
@@ -227,6 +241,16 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 			return INSTA_ERR_CUDA;
 		}
 	}
+	{
+		// launch_deform takes its per-launch scratch from the device's default stream-ordered pool: keep freed blocks cached instead of returning them to
+		// the driver at every synchronisation
+		cudaMemPool_t pool = nullptr;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+			uint64_t keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		cudaGetLastError();
+	}
 	if (cudaMalloc(&ctx->d_counter, 32 * 128) != cudaSuccess) {
 		set_error("counter allocation failed");
 		insta_ctx_destroy(ctx);
@@ -235,7 +259,8 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 	{
 		const char* k = getenv("INSTA_DEFORM_KERNEL");
 		ctx->force_legacy_deform = k && std::string(k) == "legacy";
-		ctx->force_wq_deform = k && std::string(k) == "wq";
+		ctx->force_wq_deform = k && (std::string(k) == "wq" || std::string(k) == "wq1");
+		ctx->no_prefetch_deform = k && std::string(k) == "wq1";
 		if (const char* tr = getenv("INSTA_TRAIN_ROUNDS")) ctx->train_all_samples = std::string(tr) == "0";
 		if (const char* te = getenv("INSTA_TRAIN_ROUND_EDGES")) {  // e.g. "4,16,48": rounds [0,4) [4,16) [16,48) [48,end)
 			std::vector<uint32_t> e{0u};

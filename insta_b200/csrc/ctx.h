@@ -52,8 +52,8 @@ struct Node {
 //   ref[k] <  0 : leaf, -(ref+1) = (first_triangle << 3) | count   (count <= 7)
 struct __align__(128) Quad {
 	float mnx[4], mny[4], mnz[4], mxx[4], mxy[4], mxz[4];
-	int32_t ref[4];
-	int32_t pad[4];  // the same references as 16-bit stack codes (bit 15 = leaf; quad index | first << 2 | count), -1 = n/a
+	int32_t code[4];  // the same references as 16-bit stack codes (bit 15 = leaf; quad index | first << 2 | count), -1 = n/a
+	int32_t ref[4];   // last, so that the first 112 bytes are all a compact-code traversal reads (deform_pf_kernel stages exactly those)
 };
 static_assert(sizeof(Quad) == 128, "Quad must be one cache line");
 
@@ -149,6 +149,10 @@ struct insta_ctx {
 	bool compact_entries = false;     // every reference of the loaded topology fits the 16-bit stack code
 	bool force_legacy_deform = false; // INSTA_DEFORM_KERNEL=legacy: thread-per-query kernel everywhere (A/B measurements)
 	bool force_wq_deform = false;     // INSTA_DEFORM_KERNEL=wq: warp-queue kernel everywhere
+	bool no_prefetch_deform = false;  // INSTA_DEFORM_KERNEL=wq1: round-1 warp-queue kernel (deform_wq_kernel) instead of deform_pf_kernel (A/B measurements)
+	bool layout_uniform = false;      // every resident frame has its triangle / transform tables at the same byte offsets from its quads (sync_frame_table)
+	uint32_t tris_off = 0, xf_off = 0;
+	const unsigned char* arena = nullptr;  // lowest frame allocation; layout_uniform also requires every frame to end within 64 GB of it (32-bit offsets in 16-byte units)
 	void* d_recorder = nullptr;       // recorder read-back staging: 8-bit RGBA + millimetre depth (recorder.cu)
 	size_t recorder_cap = 0;          // pixels
 	uint16_t* d_seed_grid = nullptr;  // 32^3 cells over render_aabb -> topology id of a nearby canonical triangle (deform.cu seed_bound)

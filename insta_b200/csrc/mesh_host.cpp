@@ -300,13 +300,13 @@ void build_bvh(std::vector<Tri>& tris_in, uint32_t leaf_size, HostBvh& out) {
 			q.mxx[k] = c.mx[0]; q.mxy[k] = c.mx[1]; q.mxz[k] = c.mx[2];
 			if (c.left_idx >= 0) {
 				q.ref[k] = quad_of[nodes[i].left_idx + k];
-				q.pad[k] = q.ref[k] < 0x7fff ? q.ref[k] : -1;  // 16-bit stack code of the warp-queue kernel (deform.cu)
+				q.code[k] = q.ref[k] < 0x7fff ? q.ref[k] : -1;  // 16-bit stack code of the warp-queue kernel (deform.cu)
 			} else {
 				const uint32_t first = (uint32_t)(-c.left_idx - 1), count = (uint32_t)(-c.right_idx - 1) - first;
 				// An empty leaf (count 0) keeps its degenerate box: it takes part in the child sort exactly as in the
 				// reference, because the order among tied box distances decides the order in which tied triangles are met.
 				q.ref[k] = -(int32_t)((first << 3) | (count & 7u)) - 1;
-				q.pad[k] = (first < 8192u && count <= 3u) ? (int32_t)(0x8000u | (first << 2) | count) : -1;
+				q.code[k] = (first < 8192u && count <= 3u) ? (int32_t)(0x8000u | (first << 2) | count) : -1;
 			}
 		}
 	}

@@ -28,8 +28,10 @@ def main(path):
             if k in d and d[k] != "":
                 print("  %-95s %s %s" % (k, d[k], units[hdr.index(k)]))
         try:
-            tr = float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])
-            print("  traffic (dram read+write) = %.3f %s per launch" % (tr, units[hdr.index("dram__bytes_read.sum")]))
+            # the two counters may come in different units (Mbyte / Gbyte): convert both to bytes before adding
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            tr = sum(float(d[k]) * mult[units[hdr.index(k)]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            print("  traffic (dram read+write) = %.0f bytes per launch" % tr)
         except Exception:
             pass
 
