@@ -16,6 +16,8 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 #include "ctx.h"
 #include "grid_device.cuh"
@@ -94,6 +96,61 @@ __global__ void __launch_bounds__(kFwdThreads) hash_fwd_kernel(const __grid_cons
 	for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
 		if (L.hashed[level]) fwd_level<true>(L, level, n, i0, one, two, s_pos + 6 * lane, table, out);
 		else fwd_level<false>(L, level, n, i0, one, two, s_pos + 6 * lane, table, out);
+	}
+}
+
+// Lane-pair version (default): lane l = x-side (l & 1) of the samples 4 (l >> 1) + {0, 1, 2, 3} of the tile; see pair_load / pair_accumulate.  A lane ends up
+// with 4 features x 4 consecutive samples: one 8-byte store per feature row, 16 lanes of a warp complete a 128-byte line per row.
+template <bool HASHED>
+__device__ __forceinline__ void fwd_level_pairs(const GridLevels& L, uint32_t level, uint32_t n, uint32_t tile_first, uint32_t lane, const float* __restrict__ s_pos,
+                                                const uint4* __restrict__ table, __half* __restrict__ out) {
+	const uint32_t b = lane & 1u, g = lane >> 1;
+	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
+	const float scale = L.scale[level];
+	table += L.offset[level];
+	__half2 acc[4][2];
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		uint4 v[2][4];
+		float w[2][4];
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			const float* sp = s_pos + 3u * (4u * g + 2u * h + q);
+			pair_load<HASHED>(table, pos_fract3(sp[0], sp[1], sp[2], scale), b, size, mul1, mul2, v[q], w[q]);
+		}
+#pragma unroll
+		for (int q = 0; q < 2; ++q) pair_accumulate(v[q], w[q], b, acc[2 * h + q][0], acc[2 * h + q][1]);
+	}
+	const uint32_t i0 = tile_first + 4u * g;
+	if (i0 >= n) return;
+#pragma unroll
+	for (int j = 0; j < 2; ++j) {
+		__half* row = out + (size_t)(level * 8u + 4u * b + 2u * j) * n + i0;  // features 4b + 2j (low halves) and 4b + 2j + 1 (high halves)
+		if (i0 + 3u < n && (n % 4u == 0)) {
+			const __half2 l01 = __lows2half2(acc[0][j], acc[1][j]), l23 = __lows2half2(acc[2][j], acc[3][j]);
+			const __half2 h01 = __highs2half2(acc[0][j], acc[1][j]), h23 = __highs2half2(acc[2][j], acc[3][j]);
+			st_stream_v2_u32(row, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+			st_stream_v2_u32(row + n, *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+		} else {
+#pragma unroll
+			for (uint32_t p = 0; p < 4; ++p)
+				if (i0 + p < n) {
+					st_stream_u16(row + p, __half_as_ushort(__low2half(acc[p][j])));
+					st_stream_u16(row + n + p, __half_as_ushort(__high2half(acc[p][j])));
+				}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 2) hash_fwd_pairs_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
+                                                                     uint32_t stride, const uint4* __restrict__ table, __half* __restrict__ out) {
+	__shared__ float s_pos[kTile * 3];
+	const uint32_t tile_first = blockIdx.x * kTile;
+	stage_positions(s_pos, pos, stride, n, tile_first);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
+		if (L.hashed[level]) fwd_level_pairs<true>(L, level, n, tile_first, lane, s_pos, table, out);
+		else fwd_level_pairs<false>(L, level, n, tile_first, lane, s_pos, table, out);
 	}
 }
 
@@ -204,7 +261,7 @@ int init_grid_levels(insta_ctx* ctx) {
 	float pls = p.per_level_scale;
 	if (pls <= 0.f) {
 		// ngp/src/testbed.cu:2246-2258: desired_resolution 2048
-		pls = std::exp(std::log(2048.0f * (float)p.aabb_scale / (float)p.base_resolution) / (float)(p.n_levels - 1));
+		pls = p.n_levels > 1 ? std::exp(std::log(2048.0f * (float)p.aabb_scale / (float)p.base_resolution) / (float)(p.n_levels - 1)) : 1.0f;  // ngp testbed.cu:2255 guards the same way
 		ctx->p.per_level_scale = pls;
 	}
 	float* d_scales = nullptr;
@@ -250,7 +307,9 @@ int init_grid_levels(insta_ctx* ctx) {
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s) {
 	if (n == 0) return INSTA_OK;
 	const dim3 grid((n + kTile - 1) / kTile);
-	hash_fwd_kernel<<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out);
+	static const bool v1 = [] { const char* e = getenv("INSTA_HASH_FWD"); return e && std::string(e) == "v1"; }();  // A/B: the sample-pair-per-lane kernel of round 1
+	if (v1) hash_fwd_kernel<<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out);
+	else hash_fwd_pairs_kernel<<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;

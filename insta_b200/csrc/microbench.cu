@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(512) gather_kernel(const uint4* __restrict__ b
 }  // namespace
 
 int microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, cudaStream_t s) {
-	if (chunk_bytes != 16 && chunk_bytes != 128) INSTA_FAIL(INSTA_ERR_INVALID, "insta_microbench_gather: chunk_bytes must be 16 or 128");
+	if (chunk_bytes != 16 && chunk_bytes != 32 && chunk_bytes != 64 && chunk_bytes != 128) INSTA_FAIL(INSTA_ERR_INVALID, "insta_microbench_gather: chunk_bytes must be 16, 32, 64 or 128");
 	if (buffer_bytes < 4096 || buffer_bytes % 128 || buffer_bytes / chunk_bytes > 0xffffffffull) INSTA_FAIL(INSTA_ERR_INVALID, "insta_microbench_gather: bad buffer size");
 	uint4* buf = nullptr;
 	uint32_t* sink = nullptr;
@@ -57,6 +57,8 @@ int microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_byte
 	for (uint32_t it = 0; it < iters + 2; ++it) {  // two warm-up launches bring the buffer into L2 when it fits
 		INSTA_CUDA(cudaEventRecord(e0, s));
 		if (chunk_bytes == 16) gather_kernel<1><<<blocks, threads, 0, s>>>(buf, n_chunks, per_thread, 17u * it + 1u, sink);
+		else if (chunk_bytes == 32) gather_kernel<2><<<blocks, threads, 0, s>>>(buf, n_chunks, per_thread, 17u * it + 1u, sink);  // 2 adjacent lanes share a 32-byte sector
+		else if (chunk_bytes == 64) gather_kernel<4><<<blocks, threads, 0, s>>>(buf, n_chunks, per_thread, 17u * it + 1u, sink);
 		else gather_kernel<8><<<blocks, threads, 0, s>>>(buf, n_chunks, per_thread, 17u * it + 1u, sink);
 		ctx->launches++;
 		INSTA_CUDA(cudaEventRecord(e1, s));
