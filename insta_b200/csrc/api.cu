@@ -12,15 +12,19 @@
 namespace insta {
 const char* last_error_cstr();
 
-int sync_frame_table(insta_ctx* ctx, cudaStream_t s) {
-	if (!ctx->frame_table_dirty) return INSTA_OK;
+// The device copy of the frame table (FrameDev per frame) is brought up to date by the ingest entry points (insta_add_frame[s], insta_replace_frames,
+// insta_clear_frames), which synchronise anyway; it is allocated once at max_cached_bvh entries, so it never moves while kernels read it.  Caller holds ctx->mu.
+static int upload_frame_table(insta_ctx* ctx) {
 	const uint32_t n = (uint32_t)ctx->frames.size();
-	if (n > ctx->frame_table_cap) {
-		// growing the table must not race with kernels still reading the old one
+	const uint32_t cap = std::max<uint32_t>(std::max<uint32_t>(ctx->p.max_cached_bvh, n), 64u);
+	if (cap > ctx->frame_table_cap) {
+		// only when max_cached_bvh was raised behind our back: nothing may be in flight then
 		INSTA_CUDA(cudaDeviceSynchronize());
 		if (ctx->d_frame_table) cudaFree(ctx->d_frame_table);
-		ctx->frame_table_cap = std::max<uint32_t>(n, std::max<uint32_t>(64, ctx->frame_table_cap * 2));
-		INSTA_CUDA(cudaMalloc(&ctx->d_frame_table, sizeof(FrameDev) * ctx->frame_table_cap));
+		ctx->d_frame_table = nullptr;
+		ctx->frame_table_cap = 0;
+		INSTA_CUDA(cudaMalloc(&ctx->d_frame_table, sizeof(FrameDev) * cap));
+		ctx->frame_table_cap = cap;
 	}
 	std::vector<FrameDev> host(n);
 	for (uint32_t i = 0; i < n; ++i) host[i] = ctx->frames[i].dev;
@@ -38,9 +42,14 @@ int sync_frame_table(insta_ctx* ctx, cudaStream_t s) {
 	}
 	ctx->arena = (const unsigned char*)lo;
 	if (n && ((lo & 15u) || ((uint64_t)ctx->tris_off & 15u) || hi - lo >= (1ull << 36))) ctx->layout_uniform = false;
-	if (n) INSTA_CUDA(cudaMemcpyAsync(ctx->d_frame_table, host.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice, s));
-	INSTA_CUDA(cudaStreamSynchronize(s));  // `host` is pageable and goes out of scope
+	if (n) INSTA_CUDA(cudaMemcpy(ctx->d_frame_table, host.data(), sizeof(FrameDev) * n, cudaMemcpyHostToDevice));
 	ctx->frame_table_dirty = false;
+	return INSTA_OK;
+}
+
+// Launch paths only check (no lock, no synchronisation): every ingest call leaves the table current, also when it fails half-way.
+int sync_frame_table(insta_ctx* ctx, cudaStream_t) {
+	if (ctx->frame_table_dirty) INSTA_FAIL(INSTA_ERR_INVALID, "the device frame table is out of date (an ingest call failed while uploading it)");
 	return INSTA_OK;
 }
 
@@ -225,6 +234,9 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 	INSTA_CUDA(cudaGetDeviceProperties(&prop, device));
 	if (prop.major != 10) INSTA_FAIL(INSTA_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library carries sm_100a code only");
 	if (def.arith > 1) INSTA_FAIL(INSTA_ERR_INVALID, "insta_params.arith must be 0 (reference CUDA build) or 1 (reference host build)");
+	// 0 never terminates the host BVH build (a 1-triangle range is split for ever); the leaf references carry the count in 3 bits
+	if (def.n_primitives_per_leaf < 1 || def.n_primitives_per_leaf > 7) INSTA_FAIL(INSTA_ERR_INVALID, "insta_params.n_primitives_per_leaf must be in 1..7");
+	if (def.max_cached_bvh == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_params.max_cached_bvh must be positive");
 	insta_ctx* ctx = new insta_ctx();
 	ctx->p = def;
 	ctx->device = device;
@@ -392,10 +404,11 @@ int insta_add_frame(insta_ctx* ctx, const float* h_verts, int32_t* frame_index) 
 		if (fr.slab) cudaFree(fr.slab);
 		return rc;
 	}
+	std::lock_guard<std::mutex> lock(ctx->mu);
 	ctx->frames.push_back(std::move(fr));
 	ctx->frame_table_dirty = true;
 	if (frame_index) *frame_index = (int32_t)ctx->frames.size() - 1;
-	return INSTA_OK;
+	return upload_frame_table(ctx);
 }
 
 int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t n_threads) {
@@ -436,20 +449,27 @@ int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t 
 		work();
 		for (auto& t : pool) t.join();
 	};
+	std::lock_guard<std::mutex> lock(ctx->mu);
 	std::vector<HostBvh> cur, nxt;
 	build_batch(0, std::min(n, batch), cur);
-	for (uint32_t b0 = 0; b0 < n; b0 += batch) {
+	int rc = INSTA_OK;
+	for (uint32_t b0 = 0; b0 < n && !rc; b0 += batch) {
 		const uint32_t b1 = std::min(n, b0 + batch), b2 = std::min(n, b1 + batch);
 		std::thread builder;
 		if (b1 < n) builder = std::thread([&]() { build_batch(b1, b2, nxt); });
-		const int rc = build_failed ? INSTA_OK : upload_frames(ctx, h_verts + per * b0, cur);
+		if (!build_failed) {
+			rc = upload_frames(ctx, h_verts + per * b0, cur);
+			ctx->frame_table_dirty = true;  // earlier batches stay appended when a later one fails: the table must follow ctx->frames on every exit
+		}
 		if (builder.joinable()) builder.join();
-		if (build_failed) INSTA_FAIL(INSTA_ERR_INVALID, "insta_add_frames: a host BVH build failed (out of memory?)");
-		if (rc) return rc;
+		if (build_failed && !rc) {
+			set_error("insta_add_frames: a host BVH build failed (out of memory?)");
+			rc = INSTA_ERR_INVALID;
+		}
 		cur.swap(nxt);
 	}
-	ctx->frame_table_dirty = true;
-	return INSTA_OK;
+	const int rc_table = upload_frame_table(ctx);
+	return rc ? rc : rc_table;
 }
 
 int insta_add_frame_obj(insta_ctx* ctx, const char* obj_path, int32_t* frame_index) {
@@ -467,11 +487,12 @@ int insta_clear_frames(insta_ctx* ctx) {
 	if (!ctx) INSTA_FAIL(INSTA_ERR_INVALID, "ctx is null");
 	INSTA_CUDA(cudaSetDevice(ctx->device));
 	INSTA_CUDA(cudaDeviceSynchronize());
+	std::lock_guard<std::mutex> lock(ctx->mu);
 	for (auto& f : ctx->frames)
 		if (f.slab) cudaFree(f.slab);
 	ctx->frames.clear();
 	ctx->frame_table_dirty = true;
-	return INSTA_OK;
+	return upload_frame_table(ctx);
 }
 
 uint32_t insta_n_frames(const insta_ctx* ctx) { return ctx ? (uint32_t)ctx->frames.size() : 0; }
@@ -781,7 +802,8 @@ int insta_tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_
 	if ((d_dbg_origin_t == nullptr) != (d_dbg_dir_alive == nullptr)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_init_rays: give both debug arrays or none");
 	if (ctx->n_faces == 0 && !(opts && opts->use_render_aabb)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_tracer_init_rays: no canonical mesh and no render_aabb");
 	ctx->render_opts = opts ? *opts : insta_render_opts{nullptr, 0.f, 0.01f, 0, {0, 0, 0, 1, 1, 1}, 0, 0};
-	return tracer_init_rays(ctx, cam, &ctx->render_opts, d_frame_rgba, d_frame_depth, d_dbg_origin_t, d_dbg_dir_alive, h_n_alive, (cudaStream_t)stream);
+	uint32_t n_alive = 0;  // the step-by-step entry points keep the live-ray count on the host, as NerfTracer does
+	return tracer_init_rays(ctx, cam, &ctx->render_opts, d_frame_rgba, d_frame_depth, d_dbg_origin_t, d_dbg_dir_alive, h_n_alive ? h_n_alive : &n_alive, (cudaStream_t)stream);
 }
 
 int insta_render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, const void* d_params_f16, const float* d_extra_dims,

@@ -129,9 +129,45 @@ __global__ void __launch_bounds__(128) nerf_init_rays_kernel(const RenderArgs a,
 // memory and leave as full-line stores (27 scalar stores per record, each touching 32 different lines, otherwise).
 constexpr int kMarchChunk = 16;  // steps marched per lane before the warp writes their records
 
-__global__ void __launch_bounds__(128) nerf_march_kernel(const RenderArgs a, RaySet rays, const uint32_t n_alive, float* __restrict__ records, const uint32_t stride,
-                                                         const uint32_t n_steps, const float frame_id, const float* __restrict__ extra_dims, const uint32_t n_extra) {
+// Device-side schedule of insta_render_frame: what NerfTracer::trace keeps on the host between two march iterations (testbed_nerf.cu:2156-2172: live-ray
+// count read back, steps per iteration derived from it) lives here, so that the iterations of a frame are enqueued without a host round trip.  The
+// kernels of an iteration take their sizes from this block when they are handed one (launch grids are sized for the upper bounds).
+struct RenderSched {
+	uint32_t n_alive;     // rays entering the iteration
+	uint32_t n_steps;     // steps marched per ray in it
+	uint32_t n_records;   // = n_alive * n_steps: what the deformation and the network process
+	uint32_t step;        // NerfTracer's running step counter (composite: current_step)
+	uint32_t iterations;  // iterations with work so far
+	uint32_t pad;
+	unsigned long long samples;
+};
+
+// one thread: closes iteration k - 1 (survivor count -> n_alive) and sets up iteration k
+__global__ void render_schedule_kernel(RenderSched* __restrict__ sc, const uint32_t* __restrict__ n_survivors, uint32_t* __restrict__ counter_to_zero, uint32_t budget,
+                                       uint32_t max_steps, int first) {
+	const uint32_t n = *n_survivors;
+	const uint32_t prev_steps = first ? 0u : sc->n_steps;
+	const uint32_t ns = n ? min(max(budget / n, 1u), max_steps) : 0u;
+	sc->step = first ? 1u : sc->step + prev_steps;
+	sc->n_alive = n;
+	sc->n_steps = ns;
+	sc->n_records = n * ns;
+	if (first) {
+		sc->iterations = 0;
+		sc->samples = 0ull;
+	}
+	if (n) {
+		sc->iterations += 1;
+		sc->samples += (unsigned long long)n * ns;
+	}
+	*counter_to_zero = 0;
+}
+
+__global__ void __launch_bounds__(128) nerf_march_kernel(const RenderArgs a, RaySet rays, const uint32_t n_alive_arg, float* __restrict__ records, const uint32_t stride,
+                                                         const uint32_t n_steps_arg, const float frame_id, const float* __restrict__ extra_dims, const uint32_t n_extra,
+                                                         const RenderSched* __restrict__ sched) {
 	extern __shared__ float march_smem[];
+	const uint32_t n_alive = sched ? sched->n_alive : n_alive_arg, n_steps = sched ? sched->n_steps : n_steps_arg;
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 	float* tile = march_smem + (size_t)warp * 32u * stride;
 	const uint32_t i0 = blockIdx.x * blockDim.x + warp * 32u;
@@ -211,10 +247,12 @@ __device__ __forceinline__ float logistic(float x) { return 1.0f / (1.0f + expf(
 
 // composite_kernel_nerf (Shade mode, exponential density, logistic rgb) + compact_kernel_nerf + shade_kernel_nerf.
 // out_stride == 0: network output is 4 halves per sample (r, g, b, sigma); else out[i + c * out_stride] as the reference.
-__global__ void __launch_bounds__(128) nerf_composite_kernel(const RenderArgs a, RaySet rays, RaySet next, const uint32_t n_alive, const float* __restrict__ records,
-                                                             const uint32_t stride, const __half* __restrict__ net_out, const uint32_t out_stride, const uint32_t n_steps,
-                                                             const uint32_t current_step, uint32_t* __restrict__ n_next, float4* __restrict__ frame_rgba,
-                                                             float* __restrict__ frame_depth, const int linear_colors) {
+__global__ void __launch_bounds__(128) nerf_composite_kernel(const RenderArgs a, RaySet rays, RaySet next, const uint32_t n_alive_arg, const float* __restrict__ records,
+                                                             const uint32_t stride, const __half* __restrict__ net_out, const uint32_t out_stride, const uint32_t n_steps_arg,
+                                                             const uint32_t current_step_arg, uint32_t* __restrict__ n_next, float4* __restrict__ frame_rgba,
+                                                             float* __restrict__ frame_depth, const int linear_colors, const RenderSched* __restrict__ sched) {
+	const uint32_t n_alive = sched ? sched->n_alive : n_alive_arg, n_steps = sched ? sched->n_steps : n_steps_arg,
+	               current_step = sched ? sched->step : current_step_arg;
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool alive = false, finished = false;
 	float4 rgba = make_float4(0, 0, 0, 0), o_t = rgba, d_w = rgba;
@@ -304,6 +342,9 @@ struct Tracer {
 	uint32_t* d_counters = nullptr;  // [0] alive (current), [1] alive (next)
 	uint32_t* h_counters = nullptr;  // pinned
 	uint32_t n_alive = 0, n_init = 0, cur = 0, step = 1;
+	RenderSched* d_sched = nullptr;
+	RenderSched* h_sched = nullptr;  // pinned
+	uint32_t last_iterations = 0;    // of the previous frame: how many iterations render_frame enqueues before it first looks at the device's count
 	RenderArgs args{};
 };
 
@@ -321,6 +362,8 @@ void tracer_destroy(insta_ctx* ctx) {
 	if (t->d_zero_extra) cudaFree(t->d_zero_extra);
 	if (t->d_counters) cudaFree(t->d_counters);
 	if (t->h_counters) cudaFreeHost(t->h_counters);
+	if (t->d_sched) cudaFree(t->d_sched);
+	if (t->h_sched) cudaFreeHost(t->h_sched);
 	delete t;
 	ctx->tracer = nullptr;
 }
@@ -329,6 +372,8 @@ static int tracer_reserve(insta_ctx* ctx, Tracer* t, uint32_t n) {
 	if (!t->d_counters) {
 		INSTA_CUDA(cudaMalloc(&t->d_counters, 64));
 		INSTA_CUDA(cudaHostAlloc(&t->h_counters, 64, cudaHostAllocDefault));
+		INSTA_CUDA(cudaMalloc(&t->d_sched, sizeof(RenderSched)));
+		INSTA_CUDA(cudaHostAlloc(&t->h_sched, sizeof(RenderSched), cudaHostAllocDefault));
 	}
 	if (n <= t->cap) return INSTA_OK;
 	INSTA_CUDA(cudaDeviceSynchronize());
@@ -376,10 +421,11 @@ int tracer_init_rays(insta_ctx* ctx, const insta_camera* cam, const insta_render
 	nerf_init_rays_kernel<<<grid, 128, 0, s>>>(t->args, t->set[0], t->d_counters, (float4*)d_frame_rgba, d_frame_depth, (float4*)d_dbg_origin_t, (float4*)d_dbg_dir_alive);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
+	if (!h_n_alive) return INSTA_OK;  // insta_render_frame: the count stays on the device
 	INSTA_CUDA(cudaMemcpyAsync(t->h_counters, t->d_counters, 4, cudaMemcpyDeviceToHost, s));
 	INSTA_CUDA(cudaStreamSynchronize(s));
 	t->n_alive = t->h_counters[0];
-	if (h_n_alive) *h_n_alive = t->n_alive;
+	*h_n_alive = t->n_alive;
 	return INSTA_OK;
 }
 
@@ -399,7 +445,7 @@ int tracer_generate(insta_ctx* ctx, float* d_records, uint32_t stride, uint32_t 
 	const size_t march_smem = (size_t)4 * 32 * stride * sizeof(float) + (size_t)4 * kMarchChunk * 32 * sizeof(float4);
 	if (march_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(nerf_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem));
 	nerf_march_kernel<<<(t->n_alive + 127) / 128, 128, march_smem, s>>>(t->args, t->set[t->cur], t->n_alive, d_records, stride, n_steps, (float)frame_id,
-	                                                                    d_extra_dims, stride - 11);
+	                                                                    d_extra_dims, stride - 11, nullptr);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
@@ -415,7 +461,7 @@ int tracer_composite(insta_ctx* ctx, const float* d_records, uint32_t stride, co
 	uint32_t* cnt_next = t->d_counters + 1 + (t->cur ^ 1u);  // [1] / [2], alternating
 	INSTA_CUDA(cudaMemsetAsync(cnt_next, 0, 4, s));
 	nerf_composite_kernel<<<(t->n_alive + 127) / 128, 128, 0, s>>>(t->args, t->set[t->cur], t->set[t->cur ^ 1u], t->n_alive, d_records, stride, (const __half*)d_net_out,
-	                                                               out_stride, n_steps, t->step, cnt_next, (float4*)d_frame_rgba, d_frame_depth, linear_colors);
+	                                                               out_stride, n_steps, t->step, cnt_next, (float4*)d_frame_rgba, d_frame_depth, linear_colors, nullptr);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	INSTA_CUDA(cudaMemcpyAsync(t->h_counters, cnt_next, 4, cudaMemcpyDeviceToHost, s));
@@ -464,32 +510,55 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 		INSTA_CUDA(cudaMemset(t->d_zero_extra, 0, 64 * 4));
 	}
 	INSTA_CUDA(cudaMemsetAsync(d_frame_rgba, 0, (size_t)n_pix * 16, s));
-	uint32_t n_alive = 0;
-	int rc = tracer_init_rays(ctx, cam, opts, d_frame_rgba, d_frame_depth, nullptr, nullptr, &n_alive, s);
+	int rc = tracer_init_rays(ctx, cam, opts, d_frame_rgba, d_frame_depth, nullptr, nullptr, nullptr, s);
 	if (rc) return rc;
-	uint32_t iterations = 0;
-	uint64_t samples = 0;
 	const bool deform = frame_id >= 0 && !ctx->frames.empty();
 	if (deform) {
 		rc = sync_frame_table(ctx, s);
 		if (rc) return rc;
 	}
-	while (n_alive > 0) {
-		const uint32_t ns = std::min(std::max(budget / n_alive, 1u), max_steps);  // max_steps == 8: tracer_n_steps(ctx), the reference's
-		uint32_t n_rec = 0;
-		rc = tracer_generate(ctx, t->d_records, stride, ns, frame_id, d_extra_dims ? d_extra_dims : t->d_zero_extra, &n_rec, s);
-		if (rc) return rc;
-		if (deform) {
-			rc = launch_deform(ctx, t->d_records, n_rec, stride, frame_id, nullptr, false, nullptr, s, nullptr, /*coherent_hint=*/true, compact);
+	// The iterations are enqueued WITHOUT reading the live-ray count back (NerfTracer::trace synchronises once per iteration, testbed_nerf.cu:2156-2165):
+	// render_schedule_kernel turns the survivor count of iteration k - 1 into the sizes of iteration k on the device, the kernels of an iteration are
+	// launched for the upper bounds and take their sizes from that block.  The host looks at the count after as many iterations as the previous frame
+	// needed (an iteration without rays costs five empty launches), then every two.
+	const float* extra = d_extra_dims ? d_extra_dims : t->d_zero_extra;
+	const size_t march_smem = (size_t)4 * 32 * stride * sizeof(float) + (size_t)4 * kMarchChunk * 32 * sizeof(float4);
+	if (march_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(nerf_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem));
+	const uint32_t ray_blocks = (n_pix + 127) / 128;
+	uint32_t cur = 0, enqueued = 0;
+	bool first = true;
+	uint32_t group = std::min(std::max(t->last_iterations, 4u), 16u);
+	while (true) {
+		for (uint32_t g = 0; g < group; ++g, ++enqueued) {
+			uint32_t* cnt_next = t->d_counters + 1 + (cur ^ 1u);
+			render_schedule_kernel<<<1, 1, 0, s>>>(t->d_sched, first ? t->d_counters : t->d_counters + 1 + cur, cnt_next, budget, max_steps, first ? 1 : 0);
+			nerf_march_kernel<<<ray_blocks, 128, march_smem, s>>>(t->args, t->set[cur], 0, t->d_records, stride, 0, (float)frame_id, extra, stride - 11, t->d_sched);
+			ctx->launches += 2;
+			INSTA_CUDA(cudaGetLastError());
+			if (deform) {
+				rc = launch_deform(ctx, t->d_records, budget, stride, frame_id, nullptr, false, nullptr, s, &t->d_sched->n_records, /*coherent_hint=*/true, compact);
+				if (rc) return rc;
+			}
+			rc = launch_network_fwd(ctx, t->d_records, stride, budget, d_params, t->d_net_out, 0, s, &t->d_sched->n_records, compact ? extra : nullptr);
 			if (rc) return rc;
+			nerf_composite_kernel<<<ray_blocks, 128, 0, s>>>(t->args, t->set[cur], t->set[cur ^ 1u], 0, t->d_records, stride, (const __half*)t->d_net_out, 0, 0, 0, cnt_next,
+			                                                (float4*)d_frame_rgba, d_frame_depth, opts ? (int)opts->linear_colors : 0, t->d_sched);
+			ctx->launches++;
+			INSTA_CUDA(cudaGetLastError());
+			cur ^= 1u;
+			first = false;
 		}
-		rc = launch_network_fwd(ctx, t->d_records, stride, n_rec, d_params, t->d_net_out, 0, s, nullptr, compact ? (d_extra_dims ? d_extra_dims : t->d_zero_extra) : nullptr);
-		if (rc) return rc;
-		rc = tracer_composite(ctx, t->d_records, stride, t->d_net_out, 0, ns, d_frame_rgba, d_frame_depth, opts ? (int)opts->linear_colors : 0, &n_alive, s);
-		if (rc) return rc;
-		++iterations;
-		samples += n_rec;
+		INSTA_CUDA(cudaMemcpyAsync(t->h_sched, t->d_sched, sizeof(RenderSched), cudaMemcpyDeviceToHost, s));
+		INSTA_CUDA(cudaMemcpyAsync(t->h_counters, t->d_counters + 1 + cur, 4, cudaMemcpyDeviceToHost, s));
+		INSTA_CUDA(cudaStreamSynchronize(s));
+		if (t->h_counters[0] == 0 || enqueued >= 4096u) break;
+		group = 2;
 	}
+	const uint32_t iterations = t->h_sched->iterations;
+	const uint64_t samples = t->h_sched->samples;
+	t->last_iterations = iterations;
+	t->n_alive = 0;
+	t->cur = cur;
 	if (stats) {
 		stats->iterations = iterations;
 		stats->samples = samples;
