@@ -228,6 +228,18 @@ def run_ours(args):
     ctx.add_frames(fv)  # Core::load_meshes: host BVH builds on a thread pool (the reference's nth_element order) + upload + per-triangle transform tables
     t_ing = time.perf_counter() - t_ing
     n_local = ctx.n_frames
+    # frame-cache turnover (rta::Core::reload_training_data, core.cu:663-706): 256 resident frames get the meshes of other frames, then their own back
+    turn = None
+    if n_local >= 512:
+        idx = np.arange(0, 256, dtype=np.int32)
+        t0r = time.perf_counter()
+        ctx.replace_frames(idx, fv[256:512])
+        t1r = time.perf_counter()
+        ctx.refit_frames(idx, fv[256:512])
+        torch.cuda.synchronize()
+        t2r = time.perf_counter()
+        ctx.replace_frames(idx, fv[:256])  # the timed batches below see the original scene
+        turn = {"frames": 256, "replace_frames_per_s (host builds, parity)": 256 / (t1r - t0r), "refit_frames_per_s (GPU refit, non-parity)": 256 / (t2r - t1r)}
     layout = ctx.grid_layout()
     n_entries = int(layout[0][-1])
     table = torch.from_numpy(synth.make_grid_table(n_entries)).cuda()
@@ -406,7 +418,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_SAMPLES * STRIDE * 4,
                     "d2h_bytes_per_step": N_SAMPLES * STRIDE * 4 + N_SAMPLES * 128 * 2, "steps": len(e2e_t)},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t1 - t0,
-            "ingest": {"frames": int(n_local), "seconds": t_ing, "frames_per_s": n_local / max(t_ing, 1e-9), "host_threads": os.cpu_count(),
+            "ingest": {"frames": int(n_local), "seconds": t_ing, "frames_per_s": n_local / max(t_ing, 1e-9), "host_threads": os.cpu_count(), "turnover": turn,
                        "note": "insta_add_frames (rta::Core::load_meshes, core.cu:294-334): per-frame host BVH build + H2D + transform table; outside the timed region"},
         }
         if world == 1 and not args.no_cpu_baseline:

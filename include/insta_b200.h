@@ -95,6 +95,17 @@ INSTA_API int insta_add_frame(insta_ctx* ctx, const float* h_verts, int32_t* fra
 INSTA_API int insta_add_frames(insta_ctx* ctx, const float* h_verts, uint32_t n, uint32_t n_threads);
 INSTA_API int insta_add_frame_obj(insta_ctx* ctx, const char* obj_path, int32_t* frame_index);
 INSTA_API int insta_clear_frames(insta_ctx* ctx);
+/* Frame-cache turnover = rta::Core::reload_training_data (src/core.cu:663-706: every 1,500 training steps the reference synchronises the device, drops the
+ * dataset and loads another subset of images + meshes, load_meshes core.cu:294-334).  Replaces the meshes of n resident frames in place: host BVH builds on
+ * n_threads threads (the reference's build order, so the winners among tied triangles stay the reference's), uploads into the frames' existing device
+ * storage (no allocation, pointers in the frame table unchanged).  Synchronises the device at entry like the reference.  h_verts: n vertex sets in the
+ * canonical topology; h_frame_indices: which resident frame each one replaces (distinct). */
+INSTA_API int insta_replace_frames(insta_ctx* ctx, const int32_t* h_frame_indices, const float* h_verts, uint32_t n, uint32_t n_threads);
+/* The same turnover WITHOUT the host build (not in the reference, non-parity): the frames keep the tree they have and its boxes are refitted
+ * on the GPU to the new vertices.  The nearest triangle of a query is still found (same distance), but where several triangles are exactly equidistant the
+ * winner may differ from the reference's, because the visit order follows the old frame's median splits (tests/test_gpu_frames.py reports the rate).
+ * Does not synchronise: copies and kernels are ordered on `stream`. */
+INSTA_API int insta_refit_frames(insta_ctx* ctx, const int32_t* h_frame_indices, const float* h_verts, uint32_t n, insta_stream stream);
 INSTA_API uint32_t insta_n_frames(const insta_ctx* ctx);
 /* TinyMesh::m_aabb of the canonical mesh (tiny_mesh.cu:157-162) -> Testbed::m_render_aabb (core.cu:289) */
 INSTA_API int insta_get_render_aabb(const insta_ctx* ctx, float* h_aabb6);

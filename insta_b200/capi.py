@@ -134,6 +134,7 @@ EXPORTS = [
     "insta_optimizer_step",
     "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
     "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
+    "insta_replace_frames", "insta_refit_frames",
     "insta_microbench_gather", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
     "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
@@ -249,6 +250,20 @@ class Context:
     def add_frames(self, verts_all, n_threads=0):
         verts_all = _np(verts_all, np.float32)
         self._check(self.lib.insta_add_frames(self.h, _vp(verts_all), C.c_uint32(verts_all.shape[0]), C.c_uint32(n_threads)))
+
+    def replace_frames(self, indices, verts_all, n_threads=0):
+        """rta::Core::reload_training_data for the meshes: new vertex sets for resident frames, host builds (the reference's order), storage reused"""
+        idx = _np(indices, np.int32)
+        verts_all = _np(verts_all, np.float32)
+        assert len(idx) == verts_all.shape[0]
+        self._check(self.lib.insta_replace_frames(self.h, _vp(idx), _vp(verts_all), C.c_uint32(len(idx)), C.c_uint32(n_threads)))
+
+    def refit_frames(self, indices, verts_all, stream=None):
+        """non-parity turnover: the frames keep their trees, boxes refitted on the GPU"""
+        idx = _np(indices, np.int32)
+        verts_all = _np(verts_all, np.float32)
+        assert len(idx) == verts_all.shape[0]
+        self._check(self.lib.insta_refit_frames(self.h, _vp(idx), _vp(verts_all), C.c_uint32(len(idx)), _stream(stream)))
 
     def clear_frames(self):
         self._check(self.lib.insta_clear_frames(self.h))

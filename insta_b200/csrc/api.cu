@@ -77,6 +77,7 @@ static int upload_frame(insta_ctx* ctx, const float* h_verts, const HostBvh& bvh
 	fr.dev.quads = d_quads;
 	fr.dev.tris = d_tris;
 	fr.dev.xf = d_xf;
+	fr.d_verts = d_verts;
 	fr.n_nodes = (uint32_t)bvh.nodes.size();
 	fr.n_quads = (uint32_t)bvh.quads.size();
 	fr.bvh_order_ids.resize(bvh.tris.size());
@@ -117,6 +118,7 @@ static int upload_frames(insta_ctx* ctx, const float* h_verts, const std::vector
 		fr.dev.quads = d_quads;
 		fr.dev.tris = d_tris;
 		fr.dev.xf = d_xf;
+		fr.d_verts = d_verts;
 		fr.n_nodes = (uint32_t)bvh.nodes.size();
 		fr.n_quads = (uint32_t)bvh.quads.size();
 		fr.bvh_order_ids.resize(bvh.tris.size());
@@ -303,8 +305,10 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	for (auto& f : ctx->frames)
+	for (auto& f : ctx->frames) {
 		if (f.slab) cudaFree(f.slab);
+		if (f.d_order) cudaFree(f.d_order);
+	}
 	if (ctx->d_frame_table) cudaFree(ctx->d_frame_table);
 	if (ctx->d_faces) cudaFree(ctx->d_faces);
 	if (ctx->d_mask_ids) cudaFree(ctx->d_mask_ids);
@@ -488,11 +492,126 @@ int insta_clear_frames(insta_ctx* ctx) {
 	INSTA_CUDA(cudaSetDevice(ctx->device));
 	INSTA_CUDA(cudaDeviceSynchronize());
 	std::lock_guard<std::mutex> lock(ctx->mu);
-	for (auto& f : ctx->frames)
+	for (auto& f : ctx->frames) {
 		if (f.slab) cudaFree(f.slab);
+		if (f.d_order) cudaFree(f.d_order);
+	}
 	ctx->frames.clear();
 	ctx->frame_table_dirty = true;
 	return upload_frame_table(ctx);
+}
+
+static int check_frame_indices(const insta_ctx* ctx, const int32_t* idx, uint32_t n, const char* who) {
+	std::vector<char> seen(ctx->frames.size(), 0);
+	for (uint32_t i = 0; i < n; ++i) {
+		if (idx[i] < 0 || (size_t)idx[i] >= ctx->frames.size()) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": frame index out of range");
+		if (seen[idx[i]]) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": frame index given twice");
+		seen[idx[i]] = 1;
+	}
+	return INSTA_OK;
+}
+
+int insta_replace_frames(insta_ctx* ctx, const int32_t* h_frame_indices, const float* h_verts, uint32_t n, uint32_t n_threads) {
+	if (!ctx || !h_frame_indices || !h_verts) INSTA_FAIL(INSTA_ERR_INVALID, "insta_replace_frames: bad arguments");
+	if (n == 0) return INSTA_OK;
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	int rc = check_frame_indices(ctx, h_frame_indices, n, "insta_replace_frames");
+	if (rc) return rc;
+	if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
+	n_threads = std::min(n_threads, n);
+	const size_t per = (size_t)ctx->n_verts * 3;
+	// host builds on the pool (batches of 64 frames, the upload of a batch overlaps the build of the next one)
+	const uint32_t batch = std::max(32u, n_threads * 4);
+	std::atomic<bool> build_failed{false};
+	auto build_batch = [&](uint32_t b0, uint32_t b1, std::vector<HostBvh>& out) {
+		try {
+			out.clear();
+			out.resize(b1 - b0);
+		} catch (...) {
+			build_failed = true;
+			return;
+		}
+		std::atomic<uint32_t> next{b0};
+		std::vector<std::thread> pool;
+		auto work = [&]() {
+			try {
+				for (uint32_t i; (i = next.fetch_add(1)) < b1;) prepare_frame(ctx, h_verts + per * i, out[i - b0]);
+			} catch (...) {
+				build_failed = true;
+			}
+		};
+		try {
+			for (uint32_t t = 1; t < std::min(n_threads, b1 - b0); ++t) pool.emplace_back(work);
+		} catch (...) {
+		}
+		work();
+		for (auto& t : pool) t.join();
+	};
+	std::vector<HostBvh> cur, nxt;
+	build_batch(0, std::min(n, batch), cur);
+	INSTA_CUDA(cudaDeviceSynchronize());  // nothing may still read the frames that are about to change (reload_training_data does the same, core.cu:696)
+	cudaStream_t s = ctx->streams[0];
+	for (uint32_t b0 = 0; b0 < n && !rc; b0 += batch) {
+		const uint32_t b1 = std::min(n, b0 + batch), b2 = std::min(n, b1 + batch);
+		std::thread builder;
+		if (b1 < n) builder = std::thread([&]() { build_batch(b1, b2, nxt); });
+		for (uint32_t i = b0; i < b1 && !rc && !build_failed; ++i) {
+			insta_ctx::Frame& fr = ctx->frames[h_frame_indices[i]];
+			const HostBvh& bvh = cur[i - b0];
+			if (bvh.quads.size() != fr.n_quads || bvh.tris.size() != (size_t)ctx->n_faces) {
+				set_error("insta_replace_frames: the new tree does not fit the frame's storage");
+				rc = INSTA_ERR_INVALID;
+				break;
+			}
+			cudaError_t e = cudaMemcpyAsync(const_cast<Quad*>(fr.dev.quads), bvh.quads.data(), bvh.quads.size() * sizeof(Quad), cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(const_cast<Tri*>(fr.dev.tris), bvh.tris.data(), bvh.tris.size() * sizeof(Tri), cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(fr.d_verts, h_verts + per * i, per * 4, cudaMemcpyHostToDevice, s);
+			if (e != cudaSuccess) {
+				set_error(std::string("insta_replace_frames: upload failed: ") + cudaGetErrorString(e));
+				rc = INSTA_ERR_CUDA;
+				break;
+			}
+			rc = launch_build_xf(ctx, fr.d_verts, const_cast<TriXf*>(fr.dev.xf), ctx->d_canon_area, nullptr, s);
+			for (size_t k = 0; k < bvh.tris.size(); ++k) fr.bvh_order_ids[k] = bvh.tris[k].id;
+			if (fr.d_order) {  // a refit would now follow a stale order
+				cudaFree(fr.d_order);
+				fr.d_order = nullptr;
+			}
+		}
+		const cudaError_t es = cudaStreamSynchronize(s);  // `cur` is pageable and is reused by the next build
+		if (builder.joinable()) builder.join();
+		if (!rc && es != cudaSuccess) INSTA_CUDA(es);
+		if (build_failed && !rc) {
+			set_error("insta_replace_frames: a host BVH build failed (out of memory?)");
+			rc = INSTA_ERR_INVALID;
+		}
+		cur.swap(nxt);
+	}
+	return rc;
+}
+
+int insta_refit_frames(insta_ctx* ctx, const int32_t* h_frame_indices, const float* h_verts, uint32_t n, insta_stream stream) {
+	if (!ctx || !h_frame_indices || !h_verts) INSTA_FAIL(INSTA_ERR_INVALID, "insta_refit_frames: bad arguments");
+	if (n == 0) return INSTA_OK;
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	int rc = check_frame_indices(ctx, h_frame_indices, n, "insta_refit_frames");
+	if (rc) return rc;
+	cudaStream_t s = (cudaStream_t)stream;
+	const size_t per = (size_t)ctx->n_verts * 3;
+	for (uint32_t i = 0; i < n; ++i) {
+		insta_ctx::Frame& fr = ctx->frames[h_frame_indices[i]];
+		if (!fr.d_order) {
+			INSTA_CUDA(cudaMalloc(&fr.d_order, fr.bvh_order_ids.size() * 4));
+			INSTA_CUDA(cudaMemcpy(fr.d_order, fr.bvh_order_ids.data(), fr.bvh_order_ids.size() * 4, cudaMemcpyHostToDevice));
+		}
+		INSTA_CUDA(cudaMemcpyAsync(fr.d_verts, h_verts + per * i, per * 4, cudaMemcpyHostToDevice, s));
+		rc = launch_build_xf(ctx, fr.d_verts, const_cast<TriXf*>(fr.dev.xf), ctx->d_canon_area, nullptr, s);
+		if (!rc) rc = launch_refit(ctx, fr.dev, fr.n_quads, fr.d_verts, fr.d_order, s);
+		if (rc) return rc;
+	}
+	return INSTA_OK;
 }
 
 uint32_t insta_n_frames(const insta_ctx* ctx) { return ctx ? (uint32_t)ctx->frames.size() : 0; }

@@ -140,6 +140,8 @@ struct insta_ctx {
 		insta::FrameDev dev{};
 		uint32_t n_nodes = 0, n_quads = 0;
 		std::vector<uint32_t> bvh_order_ids;
+		float* d_verts = nullptr;          // inside the frame's slab (insta_replace_frames / insta_refit_frames write it again)
+		uint32_t* d_order = nullptr;       // refit only: topology id of every BVH-order triangle (allocated on first refit)
 	};
 	std::vector<Frame> frames;
 	insta::FrameDev* d_frame_table = nullptr;
@@ -188,6 +190,7 @@ namespace insta {
 // deform.cu
 int launch_build_xf(insta_ctx* ctx, const float* d_verts, TriXf* d_xf, const float* d_canon_area, float* d_area_out, cudaStream_t s);
 int launch_build_seed_grid(insta_ctx* ctx, cudaStream_t s);
+int launch_refit(insta_ctx* ctx, const FrameDev& fr, uint32_t n_quads, const float* d_verts, const uint32_t* d_order, cudaStream_t s);
 // recorder.cu
 int recorder_readback(insta_ctx* ctx, const float* d_rgba, const float* d_depth, uint32_t w, uint32_t h, int srgb_to_linear, uint8_t* h_rgba8, uint32_t* h_depth_mm,
                       cudaStream_t s);
