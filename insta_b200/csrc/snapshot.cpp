@@ -180,29 +180,45 @@ struct SnapshotFile {
 int snapshot_save(const char* path, const insta_params* p, const insta_snapshot* s) {
 	Writer w;
 	w.out.reserve((size_t)s->n_params * 2 + (size_t)s->n_density_grid * 2 + (s->has_optimizer ? (size_t)s->n_params * 14 : 0) + 4096);
-	// the network config the reference would have loaded (configs/nerf/main.json), keys in nlohmann's (sorted) order
-	w.map(8);
+	// The network config the reference would have loaded -- EVERY key of configs/nerf/main.json, in nlohmann's (sorted) order: Testbed::reset_network reads
+	// "nerf_network" as a string without a guard (testbed.cu:2285), rta::Core reads seg_weight / penalize_density_alpha / beta_loss / depth_weight /
+	// geo_params / exp_params / use_eyes (src/core.cu:187-213) and the recorder max_steps (src/recorder.cu:63); a file without them makes the reference's
+	// loader throw a json type_error.  Values: insta_params where it carries the key, main.json's otherwise.
+	w.map(24);
+	w.kv_uint("beta_loss", 0);
+	w.kv_real("depth_weight", 1.25);
 	w.str("dir_encoding"); w.map(2);
 	w.str("nested"); w.array(2);
 	w.map(3); w.kv_uint("degree", 4); w.kv_uint("n_dims_to_encode", 3); w.kv_str("otype", "SphericalHarmonics");
 	w.map(3); w.kv_uint("degree", 4); w.kv_uint("n_bins", 4); w.kv_str("otype", "Identity");
 	w.kv_str("otype", "Composite");
+	w.kv_bool("disable_interp", p->disable_interp != 0);
 	w.str("encoding"); w.map(5);
 	w.kv_uint("base_resolution", p->base_resolution); w.kv_uint("log2_hashmap_size", p->log2_hashmap_size); w.kv_uint("n_features_per_level", p->n_features_per_level);
 	w.kv_uint("n_levels", p->n_levels); w.kv_str("otype", "HashGrid");
 	w.kv_uint("exp_params", p->exp_params);
+	w.kv_uint("geo_params", p->geo_params);
 	w.str("loss"); w.map(1); w.kv_str("otype", "Huber");
+	w.kv_uint("max_cached_bvh", p->max_cached_bvh);
+	w.kv_uint("max_images_gpu", 1700);
+	w.kv_uint("max_steps", 33000);
+	w.kv_str("nerf_network", "concatenation");
 	w.str("network"); w.map(6);
 	w.kv_str("activation", "ReLU"); w.kv_uint("n_hidden_layers", 2); w.kv_uint("n_neurons", 64); w.kv_uint("n_output_dims", 16); w.kv_str("otype", "FullyFusedMLP");
 	w.kv_str("output_activation", "None");
+	w.kv_bool("optimize_latent_code", false);
 	w.str("optimizer"); w.map(3);
 	w.kv_real("decay", (double)s->ema_decay);
 	w.str("nested"); w.map(6);
 	w.kv_real("beta1", (double)s->beta1); w.kv_real("beta2", (double)s->beta2); w.kv_real("epsilon", (double)s->epsilon); w.kv_real("l2_reg", (double)s->l2_reg);
 	w.kv_real("learning_rate", (double)s->opt_base_learning_rate); w.kv_str("otype", "Adam");
 	w.kv_str("otype", "Ema");
+	w.kv_bool("penalize_density_alpha", false);
+	w.kv_bool("render_from_snapshot", false);
+	w.kv_bool("render_novel_trajectory", false);
 	w.str("rgb_network"); w.map(5);
 	w.kv_str("activation", "ReLU"); w.kv_uint("n_hidden_layers", 3); w.kv_uint("n_neurons", 64); w.kv_str("otype", "FullyFusedMLP"); w.kv_str("output_activation", "None");
+	w.kv_uint("seg_weight", 40);
 	// ---- "snapshot" ----
 	w.str("snapshot");
 	w.map(11 + (s->has_optimizer ? 1 : 0));
@@ -231,6 +247,9 @@ int snapshot_save(const char* path, const insta_params* p, const insta_snapshot*
 	w.box("render_aabb", s->render_aabb);
 	w.kv_uint("training_step", s->training_step);
 	w.kv_uint("version", 1);
+	w.kv_bool("use_dataset_cache", true);
+	w.kv_bool("use_eyes", false);
+	w.kv_bool("use_ngp", false);
 	FILE* f = std::fopen(path, "wb");
 	if (!f) INSTA_FAIL(INSTA_ERR_IO, std::string("insta_snapshot_save: cannot open ") + path);
 	const size_t written = std::fwrite(w.out.data(), 1, w.out.size(), f);
