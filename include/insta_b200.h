@@ -363,6 +363,10 @@ typedef struct insta_trainer_config {
 	float    loss_scale;             /* LOSS_SCALE = 128 (ngp testbed.h:256) */
 	float    background_color[3];
 	float    depth_weight, seg_weight, near_distance, beta_loss; /* core.cu:189-208 */
+	/* measurement controls (not in the reference): a fixed workload per step */
+	uint32_t fixed_rays_per_batch;   /* 0 = Counters::update_after_training adapts rays_per_batch (reference behaviour); else every step shoots this many rays */
+	uint32_t freeze_parameters;      /* 1 = the step does everything except Trainer::optimizer_step (gradients and their allreduce included): the model, hence the
+	                                    samples per ray and the compacted batch, stay what they are */
 } insta_trainer_config;
 typedef struct insta_train_stats {
 	uint32_t training_step;          /* steps finished */

@@ -71,7 +71,7 @@ class TrainerConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("target_batch_size", C.c_uint32), ("rays_per_batch", C.c_uint32), ("snap_to_pixel_centers", C.c_uint32),
                 ("random_bg_color", C.c_uint32), ("penalize_density_alpha", C.c_uint32), ("rng_seed", C.c_uint64), ("cone_angle_constant", C.c_float),
                 ("loss_scale", C.c_float), ("background_color", C.c_float * 3), ("depth_weight", C.c_float), ("seg_weight", C.c_float),
-                ("near_distance", C.c_float), ("beta_loss", C.c_float)]
+                ("near_distance", C.c_float), ("beta_loss", C.c_float), ("fixed_rays_per_batch", C.c_uint32), ("freeze_parameters", C.c_uint32)]
 
 
 class TrainStats(C.Structure):

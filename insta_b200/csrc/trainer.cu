@@ -249,7 +249,7 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	if (!t) INSTA_FAIL(INSTA_ERR_INVALID, "insta_train_nerf: no trainer (insta_trainer_create)");
 	const insta_trainer_config& c = t->cfg;
 	const uint32_t target = c.target_batch_size;
-	const uint32_t n_rays = t->rays_per_batch;
+	const uint32_t n_rays = c.fixed_rays_per_batch ? std::min(c.fixed_rays_per_batch, kMaxRays) : t->rays_per_batch;
 	const uint32_t world = (uint32_t)comm_world(ctx);
 	const uint32_t stride = 11 + ctx->p.exp_params + ctx->p.geo_params;
 
@@ -329,10 +329,12 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	rc = grad_allreduce(ctx, (void*)opt->d_gradients_f16, network_n_params(ctx), s);
 	if (rc) return rc;
 	// Trainer::optimizer_step(stream, LOSS_SCALE) (testbed_nerf.cu:2974)
-	insta_optimizer o = *opt;
-	o.loss_scale = c.loss_scale;
-	rc = optimizer_step(ctx, &o, network_n_params(ctx), 25600u, s);
-	if (rc) return rc;
+	if (!c.freeze_parameters) {
+		insta_optimizer o = *opt;
+		o.loss_scale = c.loss_scale;
+		rc = optimizer_step(ctx, &o, network_n_params(ctx), 25600u, s);
+		if (rc) return rc;
+	}
 	t->training_step += 1;
 
 	// Counters::update_after_training (testbed_nerf.cu:2889-2914): one read-back per step, as in the reference
@@ -355,9 +357,11 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 			std::memcpy(&sum, t->h_counters + 3, sizeof(float));
 			loss_scalar = sum * (float)compacted / (float)target;
 		}
-		uint32_t r = (uint32_t)((float)t->rays_per_batch * (float)target / (float)compacted);
-		r = (r + kGranularity - 1) / kGranularity * kGranularity;
-		t->rays_per_batch = std::min(r, kMaxRays);
+		if (!c.fixed_rays_per_batch) {
+			uint32_t r = (uint32_t)((float)t->rays_per_batch * (float)target / (float)compacted);
+			r = (r + kGranularity - 1) / kGranularity * kGranularity;
+			t->rays_per_batch = std::min(r, kMaxRays);
+		}
 	}
 	if (h_stats) {
 		trainer_state(ctx, h_stats);

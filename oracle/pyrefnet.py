@@ -68,3 +68,13 @@ class RefNet:
 
     def optimizer_step(self, loss_scale=128.0):
         self._check(self.lib.refnet_optimizer_step(C.c_float(loss_scale), self._s()), "optimizer_step")
+
+    def set_grads(self, grads16):
+        assert grads16.numel() == self.n_params
+        self._check(self.lib.refnet_set_grads(C.c_void_p(grads16.data_ptr()), self._s()), "set_grads")
+
+    def optimizer_state(self, master32, params16, ema16):
+        self._check(self.lib.refnet_get_optimizer_state(C.c_void_p(master32.data_ptr()), C.c_void_p(params16.data_ptr()), C.c_void_p(ema16.data_ptr()), self._s()), "optimizer_state")
+
+    def reset_optimizer(self):
+        self.lib.refnet_reset_optimizer()

@@ -146,4 +146,25 @@ int refnet_optimizer_step(float loss_scale, cudaStream_t stream) {
 	}
 }
 
+// For the optimizer parity test: feed a gradient vector, read back what Ema{Adam} made of it
+int refnet_set_grads(const void* d_grads_f16, cudaStream_t stream) {
+	cudaMemcpyAsync(g_grads.data(), d_grads_f16, g_grads.get_bytes(), cudaMemcpyDeviceToDevice, stream);
+	return 0;
+}
+int refnet_get_optimizer_state(float* d_params_fp32, void* d_params_f16, void* d_ema_f16, cudaStream_t stream) {
+	if (!g_opt) {
+		g_err = "no optimizer step has run yet";
+		return -1;
+	}
+	if (d_params_fp32) cudaMemcpyAsync(d_params_fp32, g_params_fp32.data(), g_params_fp32.get_bytes(), cudaMemcpyDeviceToDevice, stream);
+	if (d_params_f16) cudaMemcpyAsync(d_params_f16, g_params.data(), g_params.get_bytes(), cudaMemcpyDeviceToDevice, stream);
+	if (d_ema_f16) cudaMemcpyAsync(d_ema_f16, g_opt->custom_weights(), g_params.get_bytes(), cudaMemcpyDeviceToDevice, stream);
+	return 0;
+}
+// forget the optimizer (its moments, step count and fp32 master copy): the next refnet_optimizer_step starts from the current fp16 parameters
+int refnet_reset_optimizer() {
+	g_opt.reset();
+	return 0;
+}
+
 }  // extern "C"

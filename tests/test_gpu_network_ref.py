@@ -91,3 +91,37 @@ def test_forward_backward_vs_reference_network(gpu_ctx, scene, refnet):
     assert float(wg.abs().max()) > 0 and float(cos(wg, gg, dim=0)) > 0.995, float(cos(wg, gg, dim=0))
     # the same entries are touched
     assert float(((wg != 0) != (gg != 0)).float().mean()) < 2e-3
+
+
+def test_adam_ema_steps_vs_tcnn_optimizer(gpu_ctx, refnet):
+    """insta_optimizer_step against tiny-cuda-nn's own EmaOptimizer{AdamOptimizer} (optimizers/ema.h:64-130, adam.h:48-114; the optimizer of
+    configs/nerf/main.json:21-32, compiled into libref_net.so): four steps on identical parameters and gradient vectors -- fp32 master weights, fp16 weights
+    and EMA weights after every step.  Gradients as in training: dense for the 25,600 MLP weights, ~10 % of the hash-grid entries touched per step, so the
+    per-parameter step counts and the skip rule for untouched grid entries (adam.h:79-82) are exercised too."""
+    import torch
+
+    n = gpu_ctx.network_n_params
+    g = torch.Generator(device="cuda").manual_seed(17)
+    params16 = (torch.randn(n, device="cuda", generator=g) * 0.05).half()
+    refnet.set_params(params16)
+    refnet.reset_optimizer()
+    master, w16 = params16.float(), params16.clone()
+    m1, m2 = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    steps = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ema = torch.zeros(n, dtype=torch.float16, device="cuda")
+    r_master, r_w16, r_ema = torch.empty(n, device="cuda"), torch.empty(n, dtype=torch.float16, device="cuda"), torch.empty(n, dtype=torch.float16, device="cuda")
+    for k in range(4):
+        grads = (torch.randn(n, device="cuda", generator=g) * 2.0).half()
+        grads[25600:][torch.rand(n - 25600, device="cuda", generator=g) < 0.9] = 0
+        refnet.set_grads(grads)
+        refnet.optimizer_step(128.0)
+        refnet.optimizer_state(r_master, r_w16, r_ema)
+        gpu_ctx.optimizer_step(k, master, w16, grads, m1, m2, steps, ema)
+        torch.cuda.synchronize()
+        assert torch.allclose(master, r_master, rtol=3e-5, atol=1e-7), "fp32 master weights differ at step %d: %g" % (k, float((master - r_master).abs().max()))
+        # fp16 copies: the same fp32 value rounded -- allow the rare last-bit difference of the fp32 input
+        dw = (w16.float() - r_w16.float()).abs()
+        assert float(dw.max()) <= 1e-3 * float(r_w16.float().abs().max()) and float((dw > 0).float().mean()) < 1e-3, "fp16 weights differ at step %d" % k
+        de = (ema.float() - r_ema.float()).abs()
+        assert float(de.max()) <= 2e-3 * float(r_ema.float().abs().max() + 1e-6), "EMA weights differ at step %d: %g" % (k, float(de.max()))
+    assert int(steps[:25600].min()) == 4 and int(steps[25600:].max()) <= 4 and int(steps[25600:].min()) == 0

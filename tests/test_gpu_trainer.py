@@ -237,3 +237,92 @@ def test_lazy_rounds_equal_full_evaluation(scene, train_ctx, dataset, monkeypatc
     assert float((touched != (ga[25600:] != 0)).float().mean()) < 2e-3
     assert float(cos(ga[25600:], gb[25600:], dim=0)) > 0.98
     assert float((A.p32 - B.p32).abs().mean()) < 1e-5
+
+
+def test_k_steps_vs_the_step_composed_from_reference_code(train_ctx, dataset, scene, oracle):
+    """K consecutive insta_train_nerf steps against Testbed::train_nerf_step composed from the REFERENCE's own CUDA code (oracle/_ref: generate_training_samples_nerf,
+    `warp`, NerfNetwork inference, compute_loss_kernel_train_nerf + roll-over, NerfNetwork forward + backward, tcnn Ema{Adam}; testbed_nerf.cu:3170-3426, 2889-2914), both
+    starting from the same parameters and each side updating its OWN parameters with its own optimizer: rays accepted and samples generated are equal at every
+    step (they depend on the RNG stream, the occupancy grid and the ray count only), compacted samples and loss within the tolerance two fp16 networks that
+    differ in accumulation width (fp16 wmma vs fp32 tensor memory) allow.  The ray count is FIXED (insta_trainer_config.fixed_rays_per_batch) and small enough
+    that the compacted batch stays below the target: beyond the target the reference's loss kernel drops whichever rays lose the race for the last slots
+    (testbed_nerf.cu:1379-1401, before it writes their loss), so neither side is deterministic there.  The adaptation rule itself (Counters::
+    update_after_training) is compared on the first step of an adaptive run."""
+    import torch
+
+    from oracle import pyrefcuda, pyrefnerf, pyrefnet
+
+    if not (pyrefcuda.available() and pyrefnerf.available() and pyrefnet.available()):
+        pytest.skip("oracle/_ref libraries (refcuda, refnerf, refnet) not all built")
+    ctx = train_ctx
+    dev, bf, extra = dataset
+    K, target, n0 = 5, TARGET, 256
+    unit = [0, 0, 0, 1, 1, 1]
+    # ---- the reference side ----
+    oracle.set_arith("device")
+    canon = oracle.build_triangles(scene.verts, scene.faces, scene.masks)
+    adj = oracle.adjacency(scene.faces, len(scene.verts))
+    nodes, tbvh, ttopo = [], [], []
+    for v in ctx._frame_verts:
+        t = oracle.build_triangles(v, scene.faces, scene.masks, canon)
+        nn, tb = oracle.bvh_build(t)
+        nodes.append(nn); tbvh.append(tb); ttopo.append(t)
+    oracle.set_arith("host")
+    R = pyrefcuda.RefCuda()
+    R.upload_scene(nodes, tbvh, ttopo, canon, adj)
+    G = pyrefnerf.RefNerf()
+    G.train_set_images(dev)
+    N = pyrefnet.RefNet()
+    A, B = State(ctx, seed=23), State(ctx, seed=23)
+    N.set_params(B.p16)
+    N.reset_optimizer()
+    max_samples = 16 * target
+    coords = torch.zeros((max_samples, STRIDE), device="cuda")
+    counters = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ray_indices = torch.zeros(1 << 18, dtype=torch.int32, device="cuda")
+    rays = torch.zeros((1 << 18, 6), device="cuda")
+    numsteps = torch.zeros((1 << 18, 2), dtype=torch.int32, device="cuda")
+    out_cm = torch.zeros((max_samples, 16), dtype=torch.float16, device="cuda")
+    cc = torch.zeros((target, STRIDE), device="cuda")
+    dl = torch.zeros((target, 16), dtype=torch.float16, device="cuda")
+    out_cc = torch.zeros((target, 16), dtype=torch.float16, device="cuda")
+    loss = torch.zeros(1 << 18, device="cuda")
+    grads = torch.zeros(N.n_params, dtype=torch.float16, device="cuda")
+    mean_density = torch.tensor([0.02], device="cuda")
+    ref_hist, n_rays, n_total, max_inference = [], n0, 0, max_samples
+    for it in range(K):
+        loss.zero_()
+        c = coords[:max_inference]
+        G.train_generate(n_rays, n_total, c, counters, ray_indices, rays, numsteps, bf, unit, extra, rng_advances=it)
+        R.warp(c, STRIDE, -1)
+        N.inference_cm(c, out_cm)
+        G.train_loss(n_rays, n_total, target, c, counters, ray_indices, rays, numsteps, out_cm, 16, cc, dl, loss, mean_density, unit, rng_advances=it)
+        N.forward_backward(cc, dl, out_cc, grads)
+        N.optimizer_step(128.0)
+        cnt = counters.cpu().numpy()
+        n_total += n_rays
+        gen, comp = int(cnt[1]), int(cnt[2])
+        assert gen > 0 and comp > 0
+        # Counters::update_after_training (testbed_nerf.cu:2889-2914)
+        lsum = float(loss[:n_rays].sum())
+        nxt = min((int(np.float32(n_rays) * np.float32(target) / np.float32(comp)) + 127) // 128 * 128, 1 << 18)
+        ref_hist.append(dict(n_rays=n_rays, accepted=int(cnt[0]), generated=gen, compacted=comp, next_rays=nxt, loss=lsum * comp / target))
+        max_inference = min((min(gen, max_samples) + 127) // 128 * 128, max_samples)
+        assert comp < target, "pick fewer rays: the compacted batch must stay below the target for a deterministic comparison"
+    # ---- ours ----
+    ctx.trainer_create(target_batch_size=target, rays_per_batch=n0, depth_weight=1.25, seg_weight=40.0)
+    first = ctx.train_nerf(State(ctx, seed=23).optimizer(ctx), bf, extra, mean_density)
+    assert first["rays_per_batch"] == ref_hist[0]["next_rays"]  # adaptive mode: the next step's ray count follows the reference's rule
+    ctx.trainer_destroy()
+    ctx.trainer_create(target_batch_size=target, rays_per_batch=n0, fixed_rays_per_batch=n0, depth_weight=1.25, seg_weight=40.0)
+    ours = []
+    for it in range(K):
+        ours.append(ctx.train_nerf(A.optimizer(ctx, current_step=it), bf, extra, mean_density, get_loss_scalar=True))
+    ctx.trainer_destroy()
+    for it, (o, r) in enumerate(zip(ours, ref_hist)):
+        print("step %d ours %s | reference %s" % (it, {k: o[k] for k in ("n_rays", "n_rays_accepted", "measured_batch_size_before_compaction", "measured_batch_size", "rays_per_batch", "loss")}, r))
+        assert o["n_rays"] == r["n_rays"], it
+        assert o["n_rays_accepted"] == r["accepted"], it
+        assert o["measured_batch_size_before_compaction"] == r["generated"], it
+        assert abs(o["measured_batch_size"] - r["compacted"]) <= max(8, 0.01 * r["compacted"]), it
+        assert abs(o["loss"] - r["loss"]) <= 0.02 * abs(r["loss"]) + 1e-5, it
