@@ -574,9 +574,40 @@ def train_leg(ctx, verts, fv, args, rank, world, ref_hook=None):
         e1.record()
         torch.cuda.synchronize()
         tg.append(e0.elapsed_time(e1))
-    # tests/bench_ref_cuda.py passes a hook that runs the reference's own CUDA code on exactly this workload; bench.py itself never does
+    # the reference's own CUDA code on exactly this workload (oracle/ref_legs.py), after our timed region
     ref = ref_hook(verts, fv[:n_img], dev, bf0, extra, p16, hist[-1]["n_rays"], mean_density, args) if ref_hook else None
     ctx.trainer_destroy()
+    # ---- configs[3] as a controlled experiment: exactly 262,144 rays per rank and step, parameters frozen at the trained state reached above, so every
+    # step and every rank count does the same work (rays beyond the 16 x 2^18-sample workspace are dropped by the generator, as in the reference) ----
+    fixed = {}
+    modes = ("overlap", "serial", "none") if world > 1 else ("none",)
+    for mode in modes:
+        os.environ["INSTA_GRAD_EXCHANGE"] = mode
+        ctx.trainer_create(target_batch_size=1 << 18, rays_per_batch=1 << 18, fixed_rays_per_batch=1 << 18, freeze_parameters=1, depth_weight=1.25, seg_weight=40.0)
+        for k in range(5):
+            ctx.train_nerf(opt, bf0, extra, mean_density)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tf = []
+        for k in range(args.train_steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            stf = ctx.train_nerf(opt, bf0, extra, mean_density)
+            e1.record()
+            torch.cuda.synchronize()
+            tf.append(e0.elapsed_time(e1))
+        ctx.trainer_destroy()
+        msf = float(np.mean(tf))
+        if world > 1:
+            tt = torch.tensor([msf], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            msf = float(tt.item())
+        fixed[mode] = {"ms_per_step": msf, "ms_per_step_min": float(np.min(tf)), "rays_per_step": int(stf["n_rays"]), "rays_accepted": int(stf["n_rays_accepted"]),
+                       "samples_generated": int(stf["measured_batch_size_before_compaction"]), "samples_compacted": int(stf["measured_batch_size"])}
+    os.environ.pop("INSTA_GRAD_EXCHANGE", None)
+    fixed["note"] = ("insta_trainer_config.fixed_rays_per_batch = 2^18, freeze_parameters = 1; modes: overlap = NCCL sum of the grid gradients on a side stream under the MLP "
+                     "weight-gradient kernels (default), serial = one ncclAllReduce after the backward pass, none = no collective (compute only)")
     ar_ms = None
     if world > 1:
         # the exchange step alone: in-place fp16 sum of the gradient buffer over NCCL
@@ -603,6 +634,7 @@ def train_leg(ctx, verts, fv, args, rank, world, ref_hook=None):
             "aggregate_rays_per_s": world * last["n_rays"] / (ms * 1e-3), "loss": last["loss"], "images_per_gpu": n_img, "launches_per_step": launches / max(1, len(ts)),
             "grad_allreduce": ("NCCL fp16 sum of %d halves per step" % n) if world > 1 else "none (1 GPU)", "grad_allreduce_ms": ar_ms,
             "grad_allreduce_busbw_gbs": (2.0 * (world - 1) / world * n * 2 / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
+            "fixed_262144_rays": fixed,
             "grid_update_ms": {"first_256_steps (2^21 uniform points)": float(np.mean(tg_full[1:])), "later (2^19 + 2^19 points)": float(np.mean(tg[1:]))},
             "ref_cuda": ref,
             "note": "insta_train_nerf: generate + deform + fused inference + loss/compaction + fused forward/backward (tcgen05) + Adam/EMA; one stream sync per step"}

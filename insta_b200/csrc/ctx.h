@@ -215,8 +215,12 @@ int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, 
                        const float* d_uniform_extra = nullptr, const uint32_t* d_index = nullptr);
 // mlp_bwd.cu
 void network_bwd_destroy(insta_ctx* ctx);
+struct GradExchange {  // trainer.cu: side stream + events of the overlapped gradient sum (world > 1)
+	cudaStream_t side;
+	cudaEvent_t ev_grid_ready, ev_grid_summed;
+};
 int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,
-                           void* d_grads, void* d_out, cudaStream_t s);
+                           void* d_grads, void* d_out, cudaStream_t s, const GradExchange* ex = nullptr);
 // train.cu
 void pcg_seed(uint64_t seed, uint64_t advance_steps, uint64_t& state, uint64_t& inc);  // pcg32{seed} advanced `advance_steps` x advance()
 int training_set_images(insta_ctx* ctx, const insta_train_image* h, uint32_t n);

@@ -535,8 +535,10 @@ void network_bwd_destroy(insta_ctx* ctx) {
 }
 
 // NerfNetwork::forward + backward on the compacted batch: fills the fp16 gradient buffer (MLP weights, then grid) in parameter order.
+// `ex` (training with more than one rank): the grid gradients -- 99.9 % of the gradient vector, all produced by the scatter kernel -- are computed FIRST and
+// their NCCL sum runs on ex->side while this stream computes the MLP weight gradients; the caller's optimizer step waits for ex->ev_grid_summed.
 int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,
-                           void* d_grads, void* d_out, cudaStream_t s) {
+                           void* d_grads, void* d_out, cudaStream_t s, const GradExchange* ex) {
 	if (n == 0) return INSTA_OK;
 	if (!ctx->bwd_scratch) ctx->bwd_scratch = new BwdScratch();
 	BwdScratch* sc = (BwdScratch*)ctx->bwd_scratch;
@@ -576,6 +578,17 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 	net_fwd_bwd_kernel<<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), kNetThreads, kSmTotal, s>>>(a);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
+	const uint64_t n_grid = (uint64_t)ctx->levels.offset[ctx->levels.n_levels] * 8u;
+	if (ex) {
+		// grid gradients (kernel_grid_backward on the SoA dL/d(features)), then their sum across ranks on the side stream
+		int rc = launch_hash_bwd_pitched(ctx, d_records, stride, n, sc->dfeat, n_pad, (__half*)d_grads + kOffGrid, 1, s);
+		if (rc) return rc;
+		INSTA_CUDA(cudaEventRecord(ex->ev_grid_ready, s));
+		INSTA_CUDA(cudaStreamWaitEvent(ex->side, ex->ev_grid_ready, 0));
+		rc = grad_allreduce(ctx, (__half*)d_grads + kOffGrid, n_grid, ex->side);
+		if (rc) return rc;
+		INSTA_CUDA(cudaEventRecord(ex->ev_grid_summed, ex->side));
+	}
 	WgArgs w{sc->xs, sc->dys, n_pad, sc->dw32};
 	INSTA_CUDA(cudaFuncSetAttribute(net_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmTotal));
 	net_wgrad_kernel<<<std::min<uint32_t>(n_pad / kWgK, (uint32_t)ctx->sm_count), kWgThreads, kWgSmTotal, s>>>(w);
@@ -583,6 +596,13 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 	wgrad_finish_kernel<<<(kOffGrid + 255) / 256, 256, 0, s>>>(kOffGrid, sc->dw32, (__half*)d_grads);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
+	if (ex) {
+		// the 25,600 MLP gradients: NCCL runs the two sums in the order they were issued (the same on every rank)
+		int rc = grad_allreduce(ctx, d_grads, kOffGrid, s);
+		if (rc) return rc;
+		INSTA_CUDA(cudaStreamWaitEvent(s, ex->ev_grid_summed, 0));
+		return INSTA_OK;
+	}
 	// grid gradients: kernel_grid_backward on the SoA dL/d(features)
 	return launch_hash_bwd_pitched(ctx, d_records, stride, n, sc->dfeat, n_pad, (__half*)d_grads + kOffGrid, 1, s);
 }

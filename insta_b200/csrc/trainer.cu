@@ -94,6 +94,10 @@ struct Trainer {
 	uint32_t measured_batch_size = 0, measured_batch_size_before_compaction = 0;
 	uint64_t rng_advances = 0;
 	uint32_t training_step = 0;
+	// gradient exchange (world > 1)
+	GradExchange ex{};
+	bool serial_exchange = false;  // INSTA_GRAD_EXCHANGE=serial
+	bool no_exchange = false;      // INSTA_GRAD_EXCHANGE=none: the step without its collective (measurement only: the ranks' parameters diverge)
 };
 
 namespace {
@@ -121,6 +125,9 @@ void free_trainer(Trainer* t) {
 	cudaFree(t->coords_compacted); cudaFree(t->counters); cudaFree(t->loss); cudaFree(t->loss_sum);
 	cudaFree(t->ray_T); cudaFree(t->round_index); cudaFree(t->round_count);
 	if (t->h_counters) cudaFreeHost(t->h_counters);
+	if (t->ex.side) cudaStreamDestroy(t->ex.side);
+	if (t->ex.ev_grid_ready) cudaEventDestroy(t->ex.ev_grid_ready);
+	if (t->ex.ev_grid_summed) cudaEventDestroy(t->ex.ev_grid_summed);
 	delete t;
 }
 }  // namespace
@@ -193,6 +200,10 @@ int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
 	trainer_destroy(ctx);
 	Trainer* t = new Trainer();
 	t->cfg = *cfg;
+	if (const char* e = getenv("INSTA_GRAD_EXCHANGE")) {
+		t->serial_exchange = std::string(e) == "serial";
+		t->no_exchange = std::string(e) == "none";
+	}
 	const uint32_t target = cfg->target_batch_size;
 	const uint32_t max_samples = target * 16;  // "somewhat of a worst case" (testbed_nerf.cu:3172)
 	const uint32_t stride = 11 + ctx->p.exp_params + ctx->p.geo_params;
@@ -322,12 +333,21 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	rc = train_loss(ctx, &st, t->mlp_out, kOutWidth, t->coords_compacted, t->dloss, t->loss, d_mean_density, s);
 	if (rc) return rc;
 	// forward + backward on the compacted, rolled-over batch (testbed_nerf.cu:3366-3371)
-	rc = launch_network_fwd_bwd(ctx, t->coords_compacted, stride, target, opt->d_params_f16, t->dloss, kOutWidth, (void*)opt->d_gradients_f16, nullptr, s);
+	// data-parallel exchange step (world > 1): the sum of the grid gradients overlaps the MLP weight-gradient kernels (launch_network_fwd_bwd); with
+	// INSTA_GRAD_EXCHANGE=serial one ncclAllReduce over the whole vector follows the backward pass (round-1 behaviour, A/B)
+	const bool overlap = world > 1 && !t->serial_exchange && !t->no_exchange;
+	if (overlap && !t->ex.side) {
+		INSTA_CUDA(cudaStreamCreateWithFlags(&t->ex.side, cudaStreamNonBlocking));
+		INSTA_CUDA(cudaEventCreateWithFlags(&t->ex.ev_grid_ready, cudaEventDisableTiming));
+		INSTA_CUDA(cudaEventCreateWithFlags(&t->ex.ev_grid_summed, cudaEventDisableTiming));
+	}
+	rc = launch_network_fwd_bwd(ctx, t->coords_compacted, stride, target, opt->d_params_f16, t->dloss, kOutWidth, (void*)opt->d_gradients_f16, nullptr, s, overlap ? &t->ex : nullptr);
 	if (rc) return rc;
 	t->rng_advances += 1;  // m_rng.advance() (testbed_nerf.cu:3419)
-	// data-parallel exchange step
-	rc = grad_allreduce(ctx, (void*)opt->d_gradients_f16, network_n_params(ctx), s);
-	if (rc) return rc;
+	if (!overlap && !t->no_exchange) {
+		rc = grad_allreduce(ctx, (void*)opt->d_gradients_f16, network_n_params(ctx), s);
+		if (rc) return rc;
+	}
 	// Trainer::optimizer_step(stream, LOSS_SCALE) (testbed_nerf.cu:2974)
 	if (!c.freeze_parameters) {
 		insta_optimizer o = *opt;
