@@ -206,6 +206,8 @@ int init_grid_levels(insta_ctx* ctx);
 int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* table, void* out, cudaStream_t s);
 int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, void* grad, int zero_first, cudaStream_t s);
 int launch_hash_bwd_pitched(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, uint32_t pitch, void* grad, int zero_first, cudaStream_t s);
+int launch_hash_bwd_levels(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, uint32_t pitch, void* grad, int zero_first, uint32_t level_begin,
+                           uint32_t level_end, cudaStream_t s);
 int launch_hash_slots(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, uint32_t* slots, cudaStream_t s);
 int sync_frame_table(insta_ctx* ctx, cudaStream_t s);
 // mlp.cu
@@ -217,7 +219,7 @@ int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, 
 void network_bwd_destroy(insta_ctx* ctx);
 struct GradExchange {  // trainer.cu: side stream + events of the overlapped gradient sum (world > 1)
 	cudaStream_t side;
-	cudaEvent_t ev_grid_ready, ev_grid_summed;
+	cudaEvent_t ev_grid_ready[4], ev_grid_summed;
 };
 int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stride, uint32_t n, const void* d_params, const void* d_dloss, uint32_t dloss_width,
                            void* d_grads, void* d_out, cudaStream_t s, const GradExchange* ex = nullptr);

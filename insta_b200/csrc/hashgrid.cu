@@ -15,6 +15,7 @@
 // interpolation reproduces `result[f] += (half)(w * (float)table[f])` in corner order with fp16 accumulation.
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <string>
@@ -236,15 +237,17 @@ __device__ __forceinline__ void bwd_level(const GridLevels& L, uint32_t level, u
 	if (two && any1) bwd_sample<HASHED>(grad, pos_fract3(sp[3], sp[4], sp[5], scale), g1, size, mul1, mul2);
 }
 
+// levels [level_begin, level_end): one warp per level (the block has that many warps, at most kFwdWarps)
 __global__ void __launch_bounds__(kBwdThreads) hash_bwd_kernel(const __grid_constant__ GridLevels L, uint32_t n, uint32_t pitch, const float* __restrict__ pos,
-                                                               uint32_t stride, const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
+                                                               uint32_t stride, const __half* __restrict__ dLdy, uint4* __restrict__ grad, uint32_t level_begin,
+                                                               uint32_t level_end) {
 	__shared__ float s_pos[kTile * 3];
 	const uint32_t tile_first = blockIdx.x * kTile;
 	stage_positions(s_pos, pos, stride, n, tile_first);
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
 	const uint32_t i0 = tile_first + 2u * lane;
 	const bool one = i0 < n, two = i0 + 1 < n;
-	for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
+	for (uint32_t level = level_begin + warp; level < level_end; level += n_warps) {
 		if (L.hashed[level]) bwd_level<true>(L, level, pitch, i0, one, two, s_pos + 6 * lane, dLdy, grad);
 		else bwd_level<false>(L, level, pitch, i0, one, two, s_pos + 6 * lane, dLdy, grad);
 	}
@@ -321,10 +324,19 @@ int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_
 
 // dLdy rows are `pitch` samples apart (pitch >= n)
 int launch_hash_bwd_pitched(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, uint32_t pitch, void* grad, int zero_first, cudaStream_t s) {
-	if (zero_first) INSTA_CUDA(cudaMemsetAsync(grad, 0, (size_t)ctx->levels.offset[ctx->levels.n_levels] * 16, s));
+	return launch_hash_bwd_levels(ctx, d_pos, stride, n, dLdy, pitch, grad, zero_first, 0, ctx->levels.n_levels, s);
+}
+
+// the same for the levels [level_begin, level_end) only (zero_first clears just their part of the gradient table): the trainer's pipelined exchange
+int launch_hash_bwd_levels(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, uint32_t pitch, void* grad, int zero_first, uint32_t level_begin,
+                           uint32_t level_end, cudaStream_t s) {
+	const GridLevels& L = ctx->levels;
+	if (level_end > L.n_levels || level_begin >= level_end) INSTA_FAIL(INSTA_ERR_INVALID, "launch_hash_bwd_levels: bad level range");
+	if (zero_first) INSTA_CUDA(cudaMemsetAsync((unsigned char*)grad + (size_t)L.offset[level_begin] * 16, 0, (size_t)(L.offset[level_end] - L.offset[level_begin]) * 16, s));
 	if (n == 0) return INSTA_OK;
 	const dim3 grid((n + kTile - 1) / kTile);
-	hash_bwd_kernel<<<grid, kBwdThreads, 0, s>>>(ctx->levels, n, pitch, d_pos, stride, (const __half*)dLdy, (uint4*)grad);
+	const uint32_t warps = std::min<uint32_t>(level_end - level_begin, (uint32_t)kFwdWarps);
+	hash_bwd_kernel<<<grid, warps * 32, 0, s>>>(L, n, pitch, d_pos, stride, (const __half*)dLdy, (uint4*)grad, level_begin, level_end);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;

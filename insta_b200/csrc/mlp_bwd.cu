@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "ctx.h"
 #include "grid_device.cuh"
@@ -580,18 +581,36 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 	INSTA_CUDA(cudaGetLastError());
 	const uint64_t n_grid = (uint64_t)ctx->levels.offset[ctx->levels.n_levels] * 8u;
 	if (ex) {
-		// grid gradients (kernel_grid_backward on the SoA dL/d(features)), then their sum across ranks on the side stream
-		int rc = launch_hash_bwd_pitched(ctx, d_records, stride, n, sc->dfeat, n_pad, (__half*)d_grads + kOffGrid, 1, s);
-		if (rc) return rc;
-		INSTA_CUDA(cudaEventRecord(ex->ev_grid_ready, s));
-		INSTA_CUDA(cudaStreamWaitEvent(ex->side, ex->ev_grid_ready, 0));
-		rc = grad_allreduce(ctx, (__half*)d_grads + kOffGrid, n_grid, ex->side);
-		if (rc) return rc;
+		// Grid gradients (kernel_grid_backward on the SoA dL/d(features)) in groups of levels of about equal size, each group's sum across ranks on the side
+		// stream while the next group is scattered: the scatter kernel's CTAs are small, so NCCL's kernel gets SMs next to it (it does not next to the
+		// persistent weight-gradient kernel), and only the last group's sum is left when the scatter ends.
+		const GridLevels& L = ctx->levels;
+		const uint32_t n_groups = std::min<uint32_t>(4u, L.n_levels);
+		uint32_t lb = 0;
+		for (uint32_t g = 0; g < n_groups; ++g) {
+			// group g ends at the level where the running entry count passes (g + 1) / n_groups of the table
+			uint32_t le = lb + 1;
+			while (le < L.n_levels && (g + 1 == n_groups || (uint64_t)L.offset[le] * n_groups < (uint64_t)L.offset[L.n_levels] * (g + 1))) ++le;
+			if (g + 1 == n_groups) le = L.n_levels;
+			int rc = launch_hash_bwd_levels(ctx, d_records, stride, n, sc->dfeat, n_pad, (__half*)d_grads + kOffGrid, 1, lb, le, s);
+			if (rc) return rc;
+			INSTA_CUDA(cudaEventRecord(ex->ev_grid_ready[g], s));
+			INSTA_CUDA(cudaStreamWaitEvent(ex->side, ex->ev_grid_ready[g], 0));
+			rc = grad_allreduce(ctx, (__half*)d_grads + kOffGrid + (size_t)L.offset[lb] * 8u, (uint64_t)(L.offset[le] - L.offset[lb]) * 8u, ex->side);
+			if (rc) return rc;
+			lb = le;
+			if (lb >= L.n_levels) break;
+		}
+		(void)n_grid;
 		INSTA_CUDA(cudaEventRecord(ex->ev_grid_summed, ex->side));
 	}
 	WgArgs w{sc->xs, sc->dys, n_pad, sc->dw32};
 	INSTA_CUDA(cudaFuncSetAttribute(net_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmTotal));
-	net_wgrad_kernel<<<std::min<uint32_t>(n_pad / kWgK, (uint32_t)ctx->sm_count), kWgThreads, kWgSmTotal, s>>>(w);
+	// With the collective in flight on the side stream, leave a few SMs to NCCL's kernel: the weight-gradient kernel is persistent (one CTA per SM with
+	// most of its shared memory), and a collective that cannot get an SM simply runs after it
+	static const uint32_t reserve = [] { const char* e = getenv("INSTA_WGRAD_SM_RESERVE"); return e ? (uint32_t)atoi(e) : 16u; }();
+	const uint32_t wg_sms = ex ? std::max<uint32_t>((uint32_t)ctx->sm_count > reserve ? (uint32_t)ctx->sm_count - reserve : 1u, 1u) : (uint32_t)ctx->sm_count;
+	net_wgrad_kernel<<<std::min<uint32_t>(n_pad / kWgK, wg_sms), kWgThreads, kWgSmTotal, s>>>(w);
 	ctx->launches++;
 	wgrad_finish_kernel<<<(kOffGrid + 255) / 256, 256, 0, s>>>(kOffGrid, sc->dw32, (__half*)d_grads);
 	ctx->launches++;

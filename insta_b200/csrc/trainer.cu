@@ -126,7 +126,8 @@ void free_trainer(Trainer* t) {
 	cudaFree(t->ray_T); cudaFree(t->round_index); cudaFree(t->round_count);
 	if (t->h_counters) cudaFreeHost(t->h_counters);
 	if (t->ex.side) cudaStreamDestroy(t->ex.side);
-	if (t->ex.ev_grid_ready) cudaEventDestroy(t->ex.ev_grid_ready);
+	for (int g = 0; g < 4; ++g)
+		if (t->ex.ev_grid_ready[g]) cudaEventDestroy(t->ex.ev_grid_ready[g]);
 	if (t->ex.ev_grid_summed) cudaEventDestroy(t->ex.ev_grid_summed);
 	delete t;
 }
@@ -200,8 +201,12 @@ int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
 	trainer_destroy(ctx);
 	Trainer* t = new Trainer();
 	t->cfg = *cfg;
+	// Default: one ncclAllReduce after the backward pass.  The pipelined form (INSTA_GRAD_EXCHANGE=overlap: scatter kernel per level group, each group's sum on
+	// a side stream) measured no better on 2 GPUs (3.17 vs 3.14 ms per step, 3.01 without the collective; profiles/r2_train_exchange.txt): four short scatter
+	// launches and four latency-bound collectives cost what the overlap gains, and next to the persistent weight-gradient kernel NCCL's kernel finds no SM.
+	t->serial_exchange = true;
 	if (const char* e = getenv("INSTA_GRAD_EXCHANGE")) {
-		t->serial_exchange = std::string(e) == "serial";
+		t->serial_exchange = std::string(e) != "overlap";
 		t->no_exchange = std::string(e) == "none";
 	}
 	const uint32_t target = cfg->target_batch_size;
@@ -333,12 +338,12 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	rc = train_loss(ctx, &st, t->mlp_out, kOutWidth, t->coords_compacted, t->dloss, t->loss, d_mean_density, s);
 	if (rc) return rc;
 	// forward + backward on the compacted, rolled-over batch (testbed_nerf.cu:3366-3371)
-	// data-parallel exchange step (world > 1): the sum of the grid gradients overlaps the MLP weight-gradient kernels (launch_network_fwd_bwd); with
-	// INSTA_GRAD_EXCHANGE=serial one ncclAllReduce over the whole vector follows the backward pass (round-1 behaviour, A/B)
+	// data-parallel exchange step (world > 1): one ncclAllReduce over the whole gradient vector after the backward pass, or (INSTA_GRAD_EXCHANGE=overlap)
+	// the grid gradients summed group of levels by group of levels on a side stream while the scatter kernel works on the next group
 	const bool overlap = world > 1 && !t->serial_exchange && !t->no_exchange;
 	if (overlap && !t->ex.side) {
 		INSTA_CUDA(cudaStreamCreateWithFlags(&t->ex.side, cudaStreamNonBlocking));
-		INSTA_CUDA(cudaEventCreateWithFlags(&t->ex.ev_grid_ready, cudaEventDisableTiming));
+		for (int g = 0; g < 4; ++g) INSTA_CUDA(cudaEventCreateWithFlags(&t->ex.ev_grid_ready[g], cudaEventDisableTiming));
 		INSTA_CUDA(cudaEventCreateWithFlags(&t->ex.ev_grid_summed, cudaEventDisableTiming));
 	}
 	rc = launch_network_fwd_bwd(ctx, t->coords_compacted, stride, target, opt->d_params_f16, t->dloss, kOutWidth, (void*)opt->d_gradients_f16, nullptr, s, overlap ? &t->ex : nullptr);
