@@ -110,6 +110,30 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process (and the pinned host buffers it allocates afterwards: first touch) to the NUMA node its GPU hangs off.  At N = 8 every rank moves 2 GB
+    per e2e step over its own PCIe link; with unbound processes half of that traffic also crosses the socket interconnect.  Returns a description or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]  # sysfs uses a 4-digit domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 def build_scene(n_frames, rank, world):
     """Canonical mesh + this rank's shard of the synthetic frames (rank r holds frames r, r+R, ...: SURVEY.md 8e)."""
     from insta_b200 import shard, synth
@@ -316,6 +340,7 @@ def run_ours(args):
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region) ----
     e2e_steps = max(1, min(K, args.e2e_steps))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None  # before the pinned buffers are allocated
     h_rec0 = torch.from_numpy(rec_np).pin_memory()
     h_rec = torch.empty_like(h_rec0).pin_memory()
     h_out = torch.empty((128, N_SAMPLES), dtype=torch.float16).pin_memory()
@@ -416,7 +441,9 @@ def run_ours(args):
                 "step_frac": ((2048 * N_SAMPLES / gather["l2_16B_gbs"] + (BYTES_DEFORM - 52) * N_SAMPLES / gather["l2_128B_gbs"]) / 1e9) / (float(step_ms.mean()) * 1e-3),
                 "note": "frac = algorithmic gathered bytes / s over the measured divergent-gather bandwidth (16-B entries for the hash grid, 128-B lines for BVH quads / leaves); step_frac = time the step's gathers would take at those bandwidths / measured step time"}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_SAMPLES * STRIDE * 4,
-                    "d2h_bytes_per_step": N_SAMPLES * STRIDE * 4 + N_SAMPLES * 128 * 2, "steps": len(e2e_t)},
+                    "d2h_bytes_per_step": N_SAMPLES * STRIDE * 4 + N_SAMPLES * 128 * 2, "steps": len(e2e_t), "numa_binding_rank0": numa,
+                    "note": "insta_deform_encode_host: pinned host records in, deformed records + fp16 encodings out (1.98 GB over PCIe per step and rank): the "
+                            "figure is the host link, not the kernels"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t1 - t0,
             "ingest": {"frames": int(n_local), "seconds": t_ing, "frames_per_s": n_local / max(t_ing, 1e-9), "host_threads": os.cpu_count(), "turnover": turn,
                        "note": "insta_add_frames (rta::Core::load_meshes, core.cu:294-334): per-frame host BVH build + H2D + transform table; outside the timed region"},

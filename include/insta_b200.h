@@ -250,6 +250,18 @@ INSTA_API int insta_recorder_readback(insta_ctx* ctx, const float* d_frame_rgba,
  * pixels are what agrees) and the depth .bin (raw little-endian uint32 millimetres, recorder.cu:88-103). */
 INSTA_API int insta_host_write_png(const char* path, uint32_t width, uint32_t height, const uint8_t* h_rgba8);
 INSTA_API int insta_host_write_depth_bin(const char* path, const uint32_t* h_depth_mm, uint64_t n_values);
+/* Host only.  The camera trajectory of a recording -- rta::Recorder::dump_cameras_json (src/recorder.cu:648-695) over the JsonFrame entries that
+ * dump_frame_buffer appends per recorded frame (recorder.cu:318-343): image size, focal lengths in pixels, principal point, and per frame the 4x4
+ * camera-to-world matrix (the 3x4 camera with 0.5 subtracted from its translation: INSTA's scene offset) plus the paths "flame/exp/<id>.txt",
+ * "flame/eyes/<id>.txt", "meshes/<id>.obj" with <id> = the 5-digit frame index + suffix.  Frames are sorted by mesh path, keys and the 4-space
+ * indentation are nlohmann::json's.  (Recorder::raycast_flame -- the shaded mesh overlay of the GUI, src/core.cu:350-402 -- is not part of this library.) */
+typedef struct insta_trajectory_frame {
+	float       camera_matrix[12]; /* 3x4, row-major: rta::Core::m_camera at the time the frame was recorded */
+	uint32_t    frame_index;       /* Recorder::m_index_frame */
+	const char* suffix;            /* dump_frame_buffer's suffix argument, NULL = "" */
+} insta_trajectory_frame;
+INSTA_API int insta_host_write_trajectory_json(const char* path, uint32_t width, uint32_t height, float fl_x, float fl_y, float cx, float cy,
+                                               const insta_trajectory_frame* h_frames, uint32_t n_frames);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Network -- ngp::NerfNetwork<__half> (ngp/include/neural-graphics-primitives/nerf_network.h) with the shipped

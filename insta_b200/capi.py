@@ -74,6 +74,10 @@ class TrainerConfig(C.Structure):
                 ("near_distance", C.c_float), ("beta_loss", C.c_float), ("fixed_rays_per_batch", C.c_uint32), ("freeze_parameters", C.c_uint32)]
 
 
+class TrajectoryFrame(C.Structure):
+    _fields_ = [("camera_matrix", C.c_float * 12), ("frame_index", C.c_uint32), ("suffix", C.c_char_p)]
+
+
 class TrainStats(C.Structure):
     _fields_ = [("training_step", C.c_uint32), ("n_rays", C.c_uint32), ("n_rays_accepted", C.c_uint32), ("rays_per_batch", C.c_uint32), ("n_rays_total", C.c_uint32),
                 ("measured_batch_size", C.c_uint32), ("measured_batch_size_before_compaction", C.c_uint32), ("loss", C.c_float)]
@@ -134,7 +138,7 @@ EXPORTS = [
     "insta_optimizer_step",
     "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
     "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
-    "insta_replace_frames", "insta_refit_frames",
+    "insta_replace_frames", "insta_refit_frames", "insta_host_write_trajectory_json",
     "insta_microbench_gather", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
     "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
@@ -622,6 +626,21 @@ def host_write_png(path, rgba8):
 def host_write_depth_bin(path, depth_mm):
     a = _np(depth_mm, np.uint32)
     _hcheck(load_library().insta_host_write_depth_bin(str(path).encode(), _vp(a), C.c_uint64(a.size)))
+
+
+def host_write_trajectory_json(path, width, height, fl, c, cameras, frame_indices, suffixes=None):
+    """rta::Recorder::dump_cameras_json: cameras [n, 3, 4] (Core::m_camera per recorded frame), frame_indices [n]"""
+    cams = _np(cameras, np.float32).reshape(-1, 12)
+    n = len(cams)
+    arr = (TrajectoryFrame * max(n, 1))()
+    for i in range(n):
+        for k in range(12):
+            arr[i].camera_matrix[k] = float(cams[i, k])
+        arr[i].frame_index = int(frame_indices[i])
+        arr[i].suffix = suffixes[i].encode() if suffixes and suffixes[i] else None
+    lib = load_library()
+    lib.insta_host_write_trajectory_json.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_uint32]
+    _hcheck(lib.insta_host_write_trajectory_json(str(path).encode(), width, height, fl[0], fl[1], c[0], c[1], C.cast(arr, C.c_void_p), n))
 
 
 def host_adjacency(faces, n_verts):

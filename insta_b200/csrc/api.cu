@@ -971,6 +971,12 @@ int insta_host_write_depth_bin(const char* path, const uint32_t* h_depth_mm, uin
 	return write_depth_bin(path, h_depth_mm, (size_t)n_values);
 }
 
+int insta_host_write_trajectory_json(const char* path, uint32_t width, uint32_t height, float fl_x, float fl_y, float cx, float cy, const insta_trajectory_frame* h_frames,
+                                     uint32_t n_frames) {
+	if (!path || (!h_frames && n_frames)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_write_trajectory_json: bad arguments");
+	return write_trajectory_json(path, width, height, fl_x, fl_y, cx, cy, h_frames, n_frames);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host-buffer path: chunks of the batch ping-pong between two streams so the H2D of chunk k+1 and the D2H of chunk
 // k-1 overlap the kernels of chunk k.  The SoA output is written per chunk with a 2-D copy (row pitch n).

@@ -197,6 +197,7 @@ int recorder_readback(insta_ctx* ctx, const float* d_rgba, const float* d_depth,
 void recorder_destroy(insta_ctx* ctx);
 int write_png_rgba8(const char* path, uint32_t w, uint32_t h, const uint8_t* rgba8);
 int write_depth_bin(const char* path, const uint32_t* depth_mm, size_t n);
+int write_trajectory_json(const char* path, uint32_t w, uint32_t h, float fl_x, float fl_y, float cx, float cy, const insta_trajectory_frame* frames, uint32_t n);
 int launch_deform(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride, int32_t frame_id, const int32_t* d_frame_ids,
                   bool random_frames, int32_t* d_tri_ids, cudaStream_t s, const uint32_t* d_n = nullptr, bool coherent_hint = false,
                   bool compact_extra = false, const uint32_t* d_index = nullptr);

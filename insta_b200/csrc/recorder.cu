@@ -6,6 +6,11 @@
 #include <cstring>
 #include <vector>
 
+#include <algorithm>
+#include <charconv>
+#include <string>
+#include <vector>
+
 #include "ctx.h"
 
 namespace insta {
@@ -140,6 +145,77 @@ int write_depth_bin(const char* path, const uint32_t* depth_mm, size_t n) {
 	FILE* f = fopen(path, "wb");
 	if (!f) INSTA_FAIL(INSTA_ERR_IO, std::string("cannot write ") + path);
 	const bool ok = fwrite(depth_mm, 4, n, f) == n;
+	fclose(f);
+	if (!ok) INSTA_FAIL(INSTA_ERR_IO, std::string("short write to ") + path);
+	return INSTA_OK;
+}
+
+// ---- camera trajectory (Recorder::dump_cameras_json, recorder.cu:648-695) ------------------------------------------------------------------------
+namespace {
+// nlohmann::json prints a float (stored as double) with the shortest digits that round-trip the DOUBLE, "x.0" for integral values
+std::string json_number(float v) {
+	char buf[64];
+	const auto r = std::to_chars(buf, buf + sizeof(buf), (double)v);
+	std::string s(buf, r.ptr);
+	if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
+	return s;
+}
+std::string json_string(const std::string& v) {
+	std::string s = "\"";
+	for (char c : v) {
+		if (c == '"' || c == '\\') s += '\\';
+		s += c;
+	}
+	return s + "\"";
+}
+}  // namespace
+
+int write_trajectory_json(const char* path, uint32_t w, uint32_t h, float fl_x, float fl_y, float cx, float cy, const insta_trajectory_frame* frames, uint32_t n) {
+	struct Row {
+		std::string id, mesh;
+		float m[16];
+	};
+	std::vector<Row> rows(n);
+	for (uint32_t i = 0; i < n; ++i) {
+		const std::string idx = std::to_string(frames[i].frame_index);
+		rows[i].id = std::string(5 - std::min<size_t>(5, idx.size()), '0') + idx + (frames[i].suffix ? frames[i].suffix : "");
+		rows[i].mesh = "meshes/" + rows[i].id + ".obj";
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 4; ++c) rows[i].m[4 * r + c] = frames[i].camera_matrix[4 * r + c] - (c == 3 ? 0.5f : 0.0f);
+		rows[i].m[12] = rows[i].m[13] = rows[i].m[14] = 0.0f;
+		rows[i].m[15] = 1.0f;
+	}
+	std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.mesh < b.mesh; });
+	std::string o = "{\n";
+	const std::string i1(4, ' '), i2(8, ' '), i3(12, ' '), i4(16, ' '), i5(20, ' ');
+	o += i1 + "\"cx\": " + json_number(cx) + ",\n" + i1 + "\"cy\": " + json_number(cy) + ",\n";
+	o += i1 + "\"fl_x\": " + json_number(fl_x) + ",\n" + i1 + "\"fl_y\": " + json_number(fl_y) + ",\n";
+	o += i1 + "\"frames\": [";
+	for (uint32_t i = 0; i < n; ++i) {
+		const Row& R = rows[i];
+		o += (i ? ",\n" : "\n") + i2 + "{\n";
+		o += i3 + "\"depth_path\": \"\",\n";
+		o += i3 + "\"exp_path\": " + json_string("flame/exp/" + R.id + ".txt") + ",\n";
+		o += i3 + "\"eyes_path\": " + json_string("flame/eyes/" + R.id + ".txt") + ",\n";
+		o += i3 + "\"file_path\": \"\",\n";
+		o += i3 + "\"mesh_path\": " + json_string(R.mesh) + ",\n";
+		o += i3 + "\"seg_mask_path\": \"\",\n";
+		o += i3 + "\"transform_matrix\": [\n";
+		for (int r = 0; r < 4; ++r) {
+			o += i4 + "[\n";
+			for (int c = 0; c < 4; ++c) o += i5 + json_number(R.m[4 * r + c]) + (c < 3 ? ",\n" : "\n");
+			o += i4 + (r < 3 ? "],\n" : "]\n");
+		}
+		o += i3 + "]\n" + i2 + "}";
+	}
+	o += n ? "\n" + i1 + "],\n" : "],\n";
+	o += i1 + "\"h\": " + std::to_string(h) + ",\n";
+	o += i1 + "\"integer_depth_scale\": " + json_number(0.001f) + ",\n";
+	o += i1 + "\"synthetic\": true,\n";
+	o += i1 + "\"w\": " + std::to_string(w) + "\n}\n";
+	FILE* f = fopen(path, "wb");
+	if (!f) INSTA_FAIL(INSTA_ERR_IO, std::string("cannot write ") + path);
+	const bool ok = fwrite(o.data(), 1, o.size(), f) == o.size();
 	fclose(f);
 	if (!ok) INSTA_FAIL(INSTA_ERR_IO, std::string("short write to ") + path);
 	return INSTA_OK;

@@ -44,3 +44,14 @@ class RefJson:
                                                   C.c_uint32(measured_before), *args)
         if rc:
             raise RuntimeError(self.lib.refjson_last_message().decode())
+
+    def dump_cameras(self, w, h, fl, c, cams, ids):
+        """the text Recorder::dump_cameras_json writes for these cameras (n x 12 floats, 3x4 row-major) and frame indices"""
+        cams = np.ascontiguousarray(cams, np.float32).reshape(-1, 12)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        rc = self.lib.refjson_dump_cameras(C.c_int(w), C.c_int(h), C.c_float(fl[0]), C.c_float(fl[1]), C.c_float(c[0]), C.c_float(c[1]), cams.ctypes.data_as(C.c_void_p),
+                                           ids.ctypes.data_as(C.c_void_p), C.c_int(len(ids)))
+        msg = self.lib.refjson_last_message().decode()
+        if rc:
+            raise RuntimeError(msg)
+        return msg

@@ -10,7 +10,9 @@
 // Built by oracle/Makefile (target refjson) into oracle/_ref/libref_json.so; used by tests/test_snapshot_ref.py and tests/golden/make_golden_snapshot.py.
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <fstream>
+#include <iomanip>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -144,6 +146,63 @@ int refjson_load_like_reference(const char* path, uint64_t* out8) {
 		}
 		out8[0] = n_params; out8[1] = n_grid; out8[2] = training_step; out8[3] = rays_per_batch; out8[4] = has_opt; out8[5] = current_step; out8[6] = exp_params;
 		out8[7] = geo_params;
+		return 0;
+	} catch (const std::exception& e) {
+		g_msg = e.what();
+		return 1;
+	}
+}
+
+// Recorder::dump_cameras_json (src/recorder.cu:648-695) over JsonFrame entries built as dump_frame_buffer builds them (recorder.cu:318-343).
+// cams: n x 12 floats (3x4 row-major m_camera); ids: n frame indices; the text the reference would write comes back in g_msg (refjson_last_message).
+int refjson_dump_cameras(int w, int h, float fl_x, float fl_y, float cx, float cy, const float* cams, const uint32_t* ids, int n) {
+	try {
+		struct Frame { std::string depth_path, exp_path, eyes_path, file_path, mesh_path, seg_mask_path; float m[4][4]; };
+		std::vector<Frame> frames;
+		for (int i = 0; i < n; ++i) {
+			Frame f{};
+			std::string str = std::to_string(ids[i]);
+			auto id = std::string(5 - std::min(5, int(str.length())), '0') + str;
+			for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) f.m[r][c] = r == c ? 1.0f : 0.0f;
+			for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) f.m[r][c] = cams[12 * i + 4 * r + c];
+			for (int r = 0; r < 3; ++r) f.m[r][3] -= 0.5f;
+			f.exp_path = "flame/exp/" + id + ".txt";
+			f.eyes_path = "flame/eyes/" + id + ".txt";
+			f.mesh_path = "meshes/" + id + ".obj";
+			frames.push_back(f);
+		}
+		nlohmann::json main;
+		main["synthetic"] = true;
+		main["h"] = h;
+		main["w"] = w;
+		main["fl_x"] = fl_x;
+		main["fl_y"] = fl_y;
+		main["cx"] = cx;
+		main["cy"] = cy;
+		main["integer_depth_scale"] = 0.001f;
+		auto data_array = nlohmann::json::array();
+		for (auto& frame : frames) {
+			nlohmann::json data;
+			data["depth_path"] = frame.depth_path;
+			data["exp_path"] = frame.exp_path;
+			data["eyes_path"] = frame.eyes_path;
+			data["file_path"] = frame.file_path;
+			data["mesh_path"] = frame.mesh_path;
+			data["seg_mask_path"] = frame.seg_mask_path;
+			auto camera = nlohmann::json::array();
+			for (int m = 0; m < 4; ++m) {
+				auto row = nlohmann::json::array();
+				for (int k = 0; k < 4; ++k) row.push_back(frame.m[m][k]);
+				camera.push_back(row);
+			}
+			data["transform_matrix"] = camera;
+			data_array.push_back(data);
+		}
+		std::sort(data_array.begin(), data_array.end(), [](const json& a, const json& b) { return a["mesh_path"] < b["mesh_path"]; });
+		main["frames"] = data_array;
+		std::ostringstream o;
+		o << std::setw(4) << main << std::endl;
+		g_msg = o.str();
 		return 0;
 	} catch (const std::exception& e) {
 		g_msg = e.what();

@@ -106,3 +106,38 @@ def test_rendered_frame_to_png(gpu_ctx, scene, tmp_path):
     assert np.array_equal(img.reshape(-1, 4), pyoracle.recorder_rgba8(fr.cpu().numpy()))
     assert int((img[..., 3] > 50).sum()) > 500
     assert np.array_equal(np.fromfile(tmp_path / "00000.bin", "<u4"), pyoracle.recorder_depth_mm(fd.cpu().numpy(), RES[0], RES[1]))
+
+
+def test_trajectory_json_equals_the_reference_writer(tmp_path):
+    """insta_host_write_trajectory_json against Recorder::dump_cameras_json restated over the reference's vendored nlohmann::json (oracle/ref_json.cpp):
+    the same text, byte for byte -- key order, 4-space indentation, shortest round-trip floats, frames sorted by mesh path."""
+    import json
+
+    from insta_b200 import capi
+    from oracle import pyrefjson
+
+    r = np.random.default_rng(4)
+    n = 7
+    cams = r.standard_normal((n, 3, 4)).astype(np.float32)
+    cams[0] = np.array([[1, 0, 0, 0.5], [0, 1, 0, 0.75], [0, 0, 1, 2.0]], np.float32)  # exactly representable values print as x.0 / 0.25
+    cams[1, 0, 0] = np.float32(1e-7)   # exponent notation
+    cams[1, 0, 1] = np.float32(123456789.0)
+    ids = np.array([12, 3, 100000, 7, 0, 99999, 41], np.uint32)  # sorted by mesh path on output, not by recording order
+    path = tmp_path / "transforms_test.json"
+    capi.host_write_trajectory_json(path, 512, 512, (1200.0, 1199.5), (256.0, 255.25), cams, ids)
+    text = path.read_text()
+    doc = json.loads(text)
+    assert doc["w"] == 512 and doc["h"] == 512 and doc["synthetic"] is True and doc["fl_y"] == 1199.5 and abs(doc["integer_depth_scale"] - 0.001) < 1e-9
+    assert [f["mesh_path"] for f in doc["frames"]] == sorted("meshes/%05d.obj" % i for i in ids)
+    f0 = next(f for f in doc["frames"] if f["mesh_path"] == "meshes/00012.obj")
+    assert f0["transform_matrix"] == [[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.25], [0.0, 0.0, 1.0, 1.5], [0.0, 0.0, 0.0, 1.0]]
+    assert f0["exp_path"] == "flame/exp/00012.txt" and f0["eyes_path"] == "flame/eyes/00012.txt" and f0["depth_path"] == ""
+    if not pyrefjson.available():
+        pytest.skip("oracle/_ref/libref_json.so not built (make -C oracle refjson; needs /root/reference)")
+    want = pyrefjson.RefJson().dump_cameras(512, 512, (1200.0, 1199.5), (256.0, 255.25), cams, ids)
+    if text != want:
+        k = next(i for i in range(min(len(text), len(want))) if text[i] != want[i])
+        pytest.fail("trajectory text differs from the reference writer at offset %d: %r vs %r" % (k, text[max(0, k - 60):k + 30], want[max(0, k - 60):k + 30]))
+    # no frames at all
+    capi.host_write_trajectory_json(path, 64, 48, (10.0, 10.0), (32.0, 24.0), np.zeros((0, 3, 4), np.float32), [])
+    assert path.read_text() == pyrefjson.RefJson().dump_cameras(64, 48, (10.0, 10.0), (32.0, 24.0), np.zeros((0, 12), np.float32), np.zeros(0, np.uint32))
