@@ -516,6 +516,16 @@ INSTA_API void insta_snapshot_close(insta_snapshot_file* file);
  * Best of `iters` launches after warm-up, GB/s of gathered bytes.  bench.py reports it as the L2-gather roofline. */
 INSTA_API int insta_microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, insta_stream stream);
 
+/* Host only: the sharding rule of SURVEY 8e for C / C++ callers (the Python helper insta_b200/shard.py states the same rule).  One process per GPU; rank r of
+ * `world` holds the frames r, r + world, r + 2 world, ... (their BVHs, transform tables and images never reach the other GPUs), draws its own ray batches
+ * over its frames and renders the frames it holds; the only exchange is insta_train_nerf's gradient sum.
+ *   insta_shard_frame_count : how many of n_frames global frames rank holds
+ *   insta_shard_owner       : owner rank and local index of a global frame id
+ *   insta_shard_local_ids   : per-sample holder values for this rank: local frame index where the sample's frame lives here, -1 (skipped by `warp`) elsewhere */
+INSTA_API uint32_t insta_shard_frame_count(uint32_t n_frames, uint32_t rank, uint32_t world);
+INSTA_API int insta_shard_owner(uint32_t global_frame, uint32_t world, uint32_t* rank, uint32_t* local_index);
+INSTA_API int insta_shard_local_ids(const int32_t* h_global_ids, uint64_t n, uint32_t rank, uint32_t world, int32_t* h_local_ids);
+
 /* number of kernels this library has launched on behalf of ctx since creation (bench.py's gpu_launches) */
 INSTA_API uint64_t insta_launch_count(const insta_ctx* ctx);
 

@@ -138,7 +138,7 @@ EXPORTS = [
     "insta_optimizer_step",
     "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
     "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
-    "insta_replace_frames", "insta_refit_frames", "insta_host_write_trajectory_json",
+    "insta_replace_frames", "insta_refit_frames", "insta_host_write_trajectory_json", "insta_shard_frame_count", "insta_shard_owner", "insta_shard_local_ids",
     "insta_microbench_gather", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
     "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",

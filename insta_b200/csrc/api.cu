@@ -971,6 +971,27 @@ int insta_host_write_depth_bin(const char* path, const uint32_t* h_depth_mm, uin
 	return write_depth_bin(path, h_depth_mm, (size_t)n_values);
 }
 
+uint32_t insta_shard_frame_count(uint32_t n_frames, uint32_t rank, uint32_t world) {
+	if (world == 0 || rank >= world || rank >= n_frames) return 0;
+	return (n_frames - rank + world - 1) / world;
+}
+
+int insta_shard_owner(uint32_t global_frame, uint32_t world, uint32_t* rank, uint32_t* local_index) {
+	if (world == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_shard_owner: world must be positive");
+	if (rank) *rank = global_frame % world;
+	if (local_index) *local_index = global_frame / world;
+	return INSTA_OK;
+}
+
+int insta_shard_local_ids(const int32_t* h_global_ids, uint64_t n, uint32_t rank, uint32_t world, int32_t* h_local_ids) {
+	if (world == 0 || rank >= world || (n && (!h_global_ids || !h_local_ids))) INSTA_FAIL(INSTA_ERR_INVALID, "insta_shard_local_ids: bad arguments");
+	for (uint64_t i = 0; i < n; ++i) {
+		const int32_t g = h_global_ids[i];
+		h_local_ids[i] = (g >= 0 && (uint32_t)g % world == rank) ? (int32_t)((uint32_t)g / world) : -1;
+	}
+	return INSTA_OK;
+}
+
 int insta_host_write_trajectory_json(const char* path, uint32_t width, uint32_t height, float fl_x, float fl_y, float cx, float cy, const insta_trajectory_frame* h_frames,
                                      uint32_t n_frames) {
 	if (!path || (!h_frames && n_frames)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_host_write_trajectory_json: bad arguments");

@@ -119,3 +119,25 @@ def test_shard_helpers():
     assert shard.loss_scale_of_rank(128.0, 8) == 16.0
     with pytest.raises(ValueError):
         shard.frames_of_rank(4, 2, 2)
+
+
+def test_c_abi_sharding_rule_equals_the_python_helper():
+    """insta_shard_* (for C / C++ callers) states the same rule as insta_b200/shard.py; host only, no device needed"""
+    import ctypes as C
+
+    import numpy as np
+
+    from insta_b200 import capi, shard
+
+    lib = capi.load_library()
+    lib.insta_shard_frame_count.restype = C.c_uint32
+    for n, world in ((10, 4), (1700, 8), (3, 8), (0, 2), (4000, 1)):
+        for rank in range(world):
+            assert lib.insta_shard_frame_count(n, rank, world) == len(shard.frames_of_rank(n, rank, world))
+    r, li = C.c_uint32(), C.c_uint32()
+    assert lib.insta_shard_owner(13, 4, C.byref(r), C.byref(li)) == 0 and (r.value, li.value) == shard.owner_of_frame(13, 4)
+    g = np.array([0, 1, 2, 3, 9, -1, 17], np.int32)
+    out = np.empty_like(g)
+    assert lib.insta_shard_local_ids(g.ctypes.data_as(C.c_void_p), C.c_uint64(len(g)), 1, 4, out.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(out, shard.local_frame_ids(g, 1, 4))
+    assert lib.insta_shard_local_ids(g.ctypes.data_as(C.c_void_p), C.c_uint64(len(g)), 4, 4, out.ctypes.data_as(C.c_void_p)) != 0
