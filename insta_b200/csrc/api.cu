@@ -32,10 +32,13 @@ static int upload_frame_table(insta_ctx* ctx) {
 	uint64_t lo = ~0ull, hi = 0;
 	for (uint32_t i = 0; i < n; ++i) {
 		const uint64_t q = (uint64_t)host[i].quads, to = (uint64_t)host[i].tris - q, xo = (uint64_t)host[i].xf - q;
+		const uint64_t co = host[i].cyl ? (uint64_t)host[i].cyl - q : 0;
 		if (i == 0) {
 			ctx->tris_off = (uint32_t)to;
 			ctx->xf_off = (uint32_t)xo;
+			ctx->cyl_off = (uint32_t)co;
 		}
+		if (co != ctx->cyl_off || (co & 15u) || co >= (1ull << 32)) ctx->cyl_off = 0;  // bounds of some frame missing or elsewhere: traversals run without them
 		if (to != ctx->tris_off || xo != ctx->xf_off || (uint64_t)host[i].tris < q || (uint64_t)host[i].xf < (uint64_t)host[i].tris) ctx->layout_uniform = false;
 		lo = std::min(lo, q);
 		hi = std::max(hi, (uint64_t)host[i].xf + (uint64_t)ctx->n_faces * sizeof(TriXf));
@@ -55,28 +58,52 @@ int sync_frame_table(insta_ctx* ctx, cudaStream_t) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Cylinder bounds (deform.cu) exist for topologies the compact-code traversal kernel handles; their block sits between a frame's quads and triangles.
+static size_t cyl_bytes(const insta_ctx* ctx, size_t n_quads) { return ctx->compact_entries && !ctx->disable_cyl ? align_up(n_quads * kCylStride, 256) : 0; }
+
+// The triangle range of every quad child: a function of the triangle count and the leaf size alone, uploaded with the first frame.
+static int ensure_child_ranges(insta_ctx* ctx, const HostBvh& bvh) {
+	if (!cyl_bytes(ctx, bvh.quads.size())) return INSTA_OK;
+	if (ctx->d_child_ranges && ctx->child_ranges_quads == bvh.quads.size()) return INSTA_OK;
+	if (ctx->d_child_ranges) {
+		INSTA_CUDA(cudaDeviceSynchronize());
+		cudaFree(ctx->d_child_ranges);
+		ctx->d_child_ranges = nullptr;
+	}
+	INSTA_CUDA(cudaMalloc(&ctx->d_child_ranges, bvh.child_ranges.size() * 4));
+	INSTA_CUDA(cudaMemcpy(ctx->d_child_ranges, bvh.child_ranges.data(), bvh.child_ranges.size() * 4, cudaMemcpyHostToDevice));
+	ctx->child_ranges_quads = (uint32_t)bvh.quads.size();
+	return INSTA_OK;
+}
+
 // Upload one prepared frame: BVH quads + BVH-order triangles from the host build, transform table computed on device.
 static int upload_frame(insta_ctx* ctx, const float* h_verts, const HostBvh& bvh, insta_ctx::Frame& fr) {
-	const size_t quads_b = align_up(bvh.quads.size() * sizeof(Quad), 256);
+	const size_t cyl_b = cyl_bytes(ctx, bvh.quads.size());
+	const size_t quads_b = align_up(bvh.quads.size() * sizeof(Quad), 256) + cyl_b;
 	const size_t tris_b = align_up(bvh.tris.size() * sizeof(Tri), 256);
 	const size_t xf_b = align_up((size_t)ctx->n_faces * sizeof(TriXf), 256);
 	const size_t verts_b = align_up((size_t)ctx->n_verts * 12, 256);
+	int rcr = ensure_child_ranges(ctx, bvh);
+	if (rcr) return rcr;
 	INSTA_CUDA(cudaMalloc(&fr.slab, quads_b + tris_b + xf_b + verts_b));
 	unsigned char* base = (unsigned char*)fr.slab;
 	Quad* d_quads = (Quad*)base;
 	Tri* d_tris = (Tri*)(base + quads_b);
 	TriXf* d_xf = (TriXf*)(base + quads_b + tris_b);
 	float* d_verts = (float*)(base + quads_b + tris_b + xf_b);
+	fr.dev.cyl = cyl_b ? base + quads_b - cyl_b : nullptr;
 	cudaStream_t s = ctx->streams[0];
 	INSTA_CUDA(cudaMemcpyAsync(d_quads, bvh.quads.data(), bvh.quads.size() * sizeof(Quad), cudaMemcpyHostToDevice, s));
 	INSTA_CUDA(cudaMemcpyAsync(d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(Tri), cudaMemcpyHostToDevice, s));
 	INSTA_CUDA(cudaMemcpyAsync(d_verts, h_verts, (size_t)ctx->n_verts * 12, cudaMemcpyHostToDevice, s));
 	int rc = launch_build_xf(ctx, d_verts, d_xf, ctx->d_canon_area, nullptr, s);
 	if (rc) return rc;
-	INSTA_CUDA(cudaStreamSynchronize(s));
 	fr.dev.quads = d_quads;
 	fr.dev.tris = d_tris;
 	fr.dev.xf = d_xf;
+	rc = launch_build_cyl(ctx, fr.dev, (uint32_t)bvh.quads.size(), s);
+	if (rc) return rc;
+	INSTA_CUDA(cudaStreamSynchronize(s));
 	fr.d_verts = d_verts;
 	fr.n_nodes = (uint32_t)bvh.nodes.size();
 	fr.n_quads = (uint32_t)bvh.quads.size();
@@ -92,7 +119,9 @@ static int upload_frames(insta_ctx* ctx, const float* h_verts, const std::vector
 	const size_t verts_b = align_up((size_t)ctx->n_verts * 12, 256);
 	std::vector<size_t> off(bvhs.size() + 1, 0);
 	for (size_t i = 0; i < bvhs.size(); ++i)
-		off[i + 1] = off[i] + align_up(bvhs[i].quads.size() * sizeof(Quad), 256) + align_up(bvhs[i].tris.size() * sizeof(Tri), 256) + xf_b + verts_b;
+		off[i + 1] = off[i] + align_up(bvhs[i].quads.size() * sizeof(Quad), 256) + cyl_bytes(ctx, bvhs[i].quads.size()) + align_up(bvhs[i].tris.size() * sizeof(Tri), 256) + xf_b + verts_b;
+	int rcr = ensure_child_ranges(ctx, bvhs[0]);
+	if (rcr) return rcr;
 	void* slab = nullptr;
 	INSTA_CUDA(cudaMalloc(&slab, off.back()));
 	cudaStream_t s = ctx->streams[0];
@@ -102,7 +131,8 @@ static int upload_frames(insta_ctx* ctx, const float* h_verts, const std::vector
 	for (size_t i = 0; i < bvhs.size() && !rc && e == cudaSuccess; ++i) {
 		const HostBvh& bvh = bvhs[i];
 		unsigned char* base = (unsigned char*)slab + off[i];
-		const size_t quads_b = align_up(bvh.quads.size() * sizeof(Quad), 256), tris_b = align_up(bvh.tris.size() * sizeof(Tri), 256);
+		const size_t cyl_b = cyl_bytes(ctx, bvh.quads.size());
+		const size_t quads_b = align_up(bvh.quads.size() * sizeof(Quad), 256) + cyl_b, tris_b = align_up(bvh.tris.size() * sizeof(Tri), 256);
 		Quad* d_quads = (Quad*)base;
 		Tri* d_tris = (Tri*)(base + quads_b);
 		TriXf* d_xf = (TriXf*)(base + quads_b + tris_b);
@@ -118,6 +148,8 @@ static int upload_frames(insta_ctx* ctx, const float* h_verts, const std::vector
 		fr.dev.quads = d_quads;
 		fr.dev.tris = d_tris;
 		fr.dev.xf = d_xf;
+		fr.dev.cyl = cyl_b ? base + quads_b - cyl_b : nullptr;
+		if (!rc) rc = launch_build_cyl(ctx, fr.dev, (uint32_t)bvh.quads.size(), s);
 		fr.d_verts = d_verts;
 		fr.n_nodes = (uint32_t)bvh.nodes.size();
 		fr.n_quads = (uint32_t)bvh.quads.size();
@@ -290,6 +322,7 @@ int insta_ctx_create(const insta_params* p, int device, insta_ctx** out) {
 		}
 		if (const char* rr = getenv("INSTA_RENDER_RECORDS")) ctx->render_full_records = std::string(rr) == "full";
 		if (const char* sd = getenv("INSTA_DEFORM_SEED")) ctx->disable_seed_bound = std::string(sd) == "0";
+		if (const char* sd = getenv("INSTA_DEFORM_CYL")) ctx->disable_cyl = std::string(sd) == "0";
 		if (const char* m = getenv("INSTA_DEFORM_COHERENT_MAX")) ctx->coherent_max_n = (uint32_t)strtoul(m, nullptr, 10);
 	}
 	int rc = init_grid_levels(ctx);
@@ -316,6 +349,7 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	if (ctx->d_canon_area) cudaFree(ctx->d_canon_area);
 	if (ctx->d_canon_xf) cudaFree(ctx->d_canon_xf);
 	if (ctx->d_seed_grid) cudaFree(ctx->d_seed_grid);
+	if (ctx->d_child_ranges) cudaFree(ctx->d_child_ranges);
 	if (ctx->d_counter) cudaFree(ctx->d_counter);
 	tracer_destroy(ctx);
 	recorder_destroy(ctx);
@@ -573,6 +607,7 @@ int insta_replace_frames(insta_ctx* ctx, const int32_t* h_frame_indices, const f
 				break;
 			}
 			rc = launch_build_xf(ctx, fr.d_verts, const_cast<TriXf*>(fr.dev.xf), ctx->d_canon_area, nullptr, s);
+			if (!rc) rc = launch_build_cyl(ctx, fr.dev, fr.n_quads, s);
 			for (size_t k = 0; k < bvh.tris.size(); ++k) fr.bvh_order_ids[k] = bvh.tris[k].id;
 			if (fr.d_order) {  // a refit would now follow a stale order
 				cudaFree(fr.d_order);
@@ -609,6 +644,7 @@ int insta_refit_frames(insta_ctx* ctx, const int32_t* h_frame_indices, const flo
 		INSTA_CUDA(cudaMemcpyAsync(fr.d_verts, h_verts + per * i, per * 4, cudaMemcpyHostToDevice, s));
 		rc = launch_build_xf(ctx, fr.d_verts, const_cast<TriXf*>(fr.dev.xf), ctx->d_canon_area, nullptr, s);
 		if (!rc) rc = launch_refit(ctx, fr.dev, fr.n_quads, fr.d_verts, fr.d_order, s);
+		if (!rc) rc = launch_build_cyl(ctx, fr.dev, fr.n_quads, s);
 		if (rc) return rc;
 	}
 	return INSTA_OK;

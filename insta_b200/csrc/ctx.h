@@ -67,17 +67,27 @@ struct __align__(16) TriXf {
 };
 static_assert(sizeof(TriXf) == 64, "TriXf is four 128-bit loads");
 
+// Tight bounds of the four children of one quad (deform.cu, "cylinder bounds"): per child the unit axis n (fp16, rounded away from zero), the slab
+// centre / half width along n and the radius around the axis through the centre of the child's BOX, the last three in doubled units.  A child is a
+// leaf or an inner node; the record lives kCylOffsetStride bytes per quad in a block of its own (FrameDev::cyl), 64 of them used.
+struct __align__(16) QuadCyl {
+	uint16_t child[4][8];  // fp16 bits: nx, ny, nz, zc2, h2, r2, 0, 0
+};
+static_assert(sizeof(QuadCyl) == 64, "QuadCyl is four 128-bit chunks");
+constexpr uint32_t kCylStride = 128;  // same stride as the quads: address of a quad's bounds = address of the quad + a per-context constant
+
 struct FrameDev {
 	const Quad* quads;
 	const Tri* tris;     // BVH order
 	const TriXf* xf;     // topology order
-	uint64_t pad;
+	const unsigned char* cyl;  // nullable: QuadCyl per quad at kCylStride
 };
 
 struct HostBvh {
 	std::vector<Node> nodes;   // reference layout
 	std::vector<Quad> quads;   // device layout
 	std::vector<Tri> tris;     // BVH order
+	std::vector<uint32_t> child_ranges;  // per quad and child: [begin, end) of the child's subtree in `tris` (depends on the triangle count only, not on the vertices)
 };
 
 // mesh_host.cpp
@@ -154,6 +164,10 @@ struct insta_ctx {
 	bool no_prefetch_deform = false;  // INSTA_DEFORM_KERNEL=wq1: round-1 warp-queue kernel (deform_wq_kernel) instead of deform_pf_kernel (A/B measurements)
 	bool layout_uniform = false;      // every resident frame has its triangle / transform tables at the same byte offsets from its quads (sync_frame_table)
 	uint32_t tris_off = 0, xf_off = 0;
+	uint32_t cyl_off = 0;             // byte offset of a frame's cylinder bounds from its quads (0 = none / not uniform)
+	uint32_t* d_child_ranges = nullptr;  // [n_quads][4][2]: triangle range of every quad child (same for every frame of a topology); build_cyl_kernel
+	uint32_t child_ranges_quads = 0;
+	bool disable_cyl = false;         // INSTA_DEFORM_CYL=0: traversals without the cylinder bounds (A/B measurements)
 	const unsigned char* arena = nullptr;  // lowest frame allocation; layout_uniform also requires every frame to end within 64 GB of it (32-bit offsets in 16-byte units)
 	void* d_recorder = nullptr;       // recorder read-back staging: 8-bit RGBA + millimetre depth (recorder.cu)
 	size_t recorder_cap = 0;          // pixels
@@ -191,6 +205,7 @@ namespace insta {
 int launch_build_xf(insta_ctx* ctx, const float* d_verts, TriXf* d_xf, const float* d_canon_area, float* d_area_out, cudaStream_t s);
 int launch_build_seed_grid(insta_ctx* ctx, cudaStream_t s);
 int launch_refit(insta_ctx* ctx, const FrameDev& fr, uint32_t n_quads, const float* d_verts, const uint32_t* d_order, cudaStream_t s);
+int launch_build_cyl(insta_ctx* ctx, const FrameDev& fr, uint32_t n_quads, cudaStream_t s);
 // recorder.cu
 int recorder_readback(insta_ctx* ctx, const float* d_rgba, const float* d_depth, uint32_t w, uint32_t h, int srgb_to_linear, uint8_t* h_rgba8, uint32_t* h_depth_mm,
                       cudaStream_t s);

@@ -244,6 +244,9 @@ void build_bvh(std::vector<Tri>& tris_in, uint32_t leaf_size, HostBvh& out) {
 	nodes.reserve(n + n / 2 + 8);
 	nodes.emplace_back();
 	bounds(tris_in, keys.data(), {0, n}, n, nodes[0].mn, nodes[0].mx);
+	std::vector<Range> node_range;
+	node_range.reserve(n + n / 2 + 8);
+	node_range.push_back({0, n});
 
 	struct Work {
 		uint32_t node;
@@ -271,6 +274,7 @@ void build_bvh(std::vector<Tri>& tris_in, uint32_t leaf_size, HostBvh& out) {
 		for (int i = 0; i < 4; ++i) {
 			const uint32_t idx = (uint32_t)nodes.size();
 			nodes.emplace_back();
+			node_range.push_back(ch[i]);
 			bounds(tris_in, keys.data(), ch[i], n, nodes[idx].mn, nodes[idx].mx);
 			if (ch[i].end - ch[i].begin <= leaf_size) {
 				nodes[idx].left_idx = -(int32_t)ch[i].begin - 1;
@@ -291,11 +295,14 @@ void build_bvh(std::vector<Tri>& tris_in, uint32_t leaf_size, HostBvh& out) {
 	for (size_t i = 0; i < nodes.size(); ++i)
 		if (nodes[i].left_idx >= 0) quad_of[i] = (int32_t)n_quads++;
 	out.quads.assign(n_quads, Quad{});
+	out.child_ranges.assign((size_t)n_quads * 8, 0u);
 	for (size_t i = 0; i < nodes.size(); ++i) {
 		if (nodes[i].left_idx < 0) continue;
 		Quad& q = out.quads[quad_of[i]];
 		for (int k = 0; k < 4; ++k) {
 			const Node& c = nodes[nodes[i].left_idx + k];
+			out.child_ranges[(size_t)quad_of[i] * 8 + 2 * k] = node_range[nodes[i].left_idx + k].begin;
+			out.child_ranges[(size_t)quad_of[i] * 8 + 2 * k + 1] = node_range[nodes[i].left_idx + k].end;
 			q.mnx[k] = c.mn[0]; q.mny[k] = c.mn[1]; q.mnz[k] = c.mn[2];
 			q.mxx[k] = c.mx[0]; q.mxy[k] = c.mx[1]; q.mxz[k] = c.mx[2];
 			if (c.left_idx >= 0) {

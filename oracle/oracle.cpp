@@ -617,6 +617,177 @@ void orc_closest_stats_bounded(const float* pts, int n, const orc_node* nodes, c
 	for (int k = 0; k < 8; ++k) out8[k] = acc[k];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// The product's cylinder bounds (insta_b200/csrc/deform.cu: build_cyl_kernel, cyl_cull), restated on the CPU.  NOT in the reference: this is
+// the checker of the product's pruning argument -- a child whose bound exceeds `best` holds no triangle the reference would accept (d <= best),
+// so skipping it changes neither `best` nor the winner.  tests/test_oracle_cyl_bound.py runs the reference traversal with the extra cull and
+// (a) compares the winners with the plain traversal, (b) checks every culled subtree exhaustively.
+namespace {
+// nearest half >= v (up = true) or <= v (up = false); v finite
+inline uint16_t f2h_dir(float v, bool up) {
+	if (v == 0.f) return 0;
+	const bool neg = v < 0.f;
+	const float a = std::fabs(v);
+	const bool mag_up = neg ? !up : up;  // round the magnitude up?
+	if (a > 65504.f) return (uint16_t)((neg ? 0x8000u : 0u) | (mag_up ? 0x7c00u : 0x7bffu));
+	int ex;
+	std::frexp(a, &ex);  // a = f * 2^ex, f in [0.5, 1)
+	int e = ex - 1;      // a in [2^e, 2^(e+1))
+	if (e < -14) e = -14;
+	const double ulp = std::ldexp(1.0, e - 10);
+	double k = (double)a / ulp;  // exact (power-of-two scaling)
+	double kk = mag_up ? std::ceil(k) : std::floor(k);
+	uint32_t bits;
+	if (e == -14 && kk < 1024.0) bits = (uint32_t)kk;  // subnormal
+	else {
+		if (kk >= 2048.0) { kk = 1024.0; ++e; }
+		bits = ((uint32_t)(e + 15) << 10) | ((uint32_t)kk - 1024u);
+	}
+	return (uint16_t)((neg ? 0x8000u : 0u) | bits);
+}
+inline uint16_t f2h_rn(float v) {
+	const uint16_t lo = f2h_dir(v, false), hi = f2h_dir(v, true);
+	const float fl = h2f(lo), fh = h2f(hi);
+	if (lo == hi) return lo;
+	const float dl = v - fl, dh = fh - v;
+	if (dl < dh) return lo;
+	if (dh < dl) return hi;
+	return (lo & 1u) ? hi : lo;
+}
+}  // namespace
+
+// out: 8 halves per NODE (nx, ny, nz, zc2, h2, r2, 0, 0); node 0 (the root) is never tested and gets the infinite cylinder
+void orc_cyl_build(const orc_node* nodes, int n_nodes, const orc_tri* tris, uint16_t* out) {
+	std::vector<int> lo(n_nodes), hi(n_nodes);
+	for (int i = n_nodes - 1; i >= 0; --i) {
+		if (nodes[i].left_idx < 0) { lo[i] = -nodes[i].left_idx - 1; hi[i] = -nodes[i].right_idx - 1; }
+		else {
+			lo[i] = 1 << 30; hi[i] = 0;
+			for (int k = 0; k < 4; ++k) { lo[i] = std::min(lo[i], lo[nodes[i].left_idx + k]); hi[i] = std::max(hi[i], hi[nodes[i].left_idx + k]); }
+		}
+	}
+	for (int i = 0; i < n_nodes; ++i) {
+		uint16_t* rec = out + 8 * i;
+		const uint16_t inf_rec[8] = {0, 0, 0x3c00, 0, 0x7c00, 0x7c00, 0, 0};
+		bool never = i == 0 || lo[i] >= hi[i];
+		float nx = 0.f, ny = 0.f, nz = 0.f;
+		for (int t = lo[i]; t < hi[i] && !never; ++t) {
+			const orc_tri& T = tris[t];
+			const float ux = T.b[0] - T.a[0], uy = T.b[1] - T.a[1], uz = T.b[2] - T.a[2];
+			const float vx = T.c[0] - T.a[0], vy = T.c[1] - T.a[1], vz = T.c[2] - T.a[2];
+			const float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+			const float c2 = cx * cx + cy * cy + cz * cz, uv = (ux * ux + uy * uy + uz * uz) * (vx * vx + vy * vy + vz * vz);
+			if (!(c2 >= 1e-4f * uv) || !(c2 > 0.f)) never = true;
+			nx += cx; ny += cy; nz += cz;
+		}
+		if (never) { memcpy(rec, inf_rec, 16); continue; }
+		const float l = std::sqrt(nx * nx + ny * ny + nz * nz);
+		if (l > 0.f && l < std::numeric_limits<float>::max()) { nx /= l; ny /= l; nz /= l; } else { nx = 0.f; ny = 0.f; nz = 1.f; }
+		const uint16_t hx = f2h_dir(nx, nx >= 0.f), hy = f2h_dir(ny, ny >= 0.f), hz = f2h_dir(nz, nz >= 0.f);
+		const double ax = h2f(hx), ay = h2f(hy), az = h2f(hz), s2 = ax * ax + ay * ay + az * az;
+		const orc_node& nd = nodes[i];
+		const double c2x = (double)nd.mn[0] + nd.mx[0], c2y = (double)nd.mn[1] + nd.mx[1], c2z = (double)nd.mn[2] + nd.mx[2];
+		double zlo = 1e300, zhi = -1e300, lat = 0.0;
+		for (int t = lo[i]; t < hi[i]; ++t) {
+			const float* v[3] = {tris[t].a, tris[t].b, tris[t].c};
+			for (int j = 0; j < 3; ++j) {
+				const double ux = 2.0 * v[j][0] - c2x, uy = 2.0 * v[j][1] - c2y, uz = 2.0 * v[j][2] - c2z;
+				const double z = ax * ux + ay * uy + az * uz;
+				zlo = std::min(zlo, z); zhi = std::max(zhi, z);
+				lat = std::max(lat, ux * ux + uy * uy + uz * uz - z * z / s2);
+			}
+		}
+		const double size2 = 2.0 * (((double)nd.mx[0] - nd.mn[0]) + ((double)nd.mx[1] - nd.mn[1]) + ((double)nd.mx[2] - nd.mn[2]));
+		const double slack = 2e-6 * size2 + 1e-12;
+		const uint16_t hzc = f2h_rn((float)(0.5 * (zlo + zhi)));
+		const double zc = h2f(hzc);
+		const double h2 = std::max(zhi - zc, zc - zlo) + slack, r2 = std::sqrt(std::max(lat, 0.0)) + slack;
+		if (!(size2 >= 0.0) || !(h2 < 6e4) || !(r2 < 6e4) || !(std::fabs(zc) < 6e4)) { memcpy(rec, inf_rec, 16); continue; }
+		auto up = [](double v) { float f = (float)v; if ((double)f < v) f = std::nextafter(f, std::numeric_limits<float>::infinity()); return f2h_dir(f, true); };
+		rec[0] = hx; rec[1] = hy; rec[2] = hz; rec[3] = hzc; rec[4] = up(h2); rec[5] = up(r2); rec[6] = rec[7] = 0;
+	}
+}
+
+// cyl_cull of deform.cu in fp32
+static inline bool cyl_cull_cpu(const uint16_t* rec, const float* mn, const float* mx, V3 p, float best4) {
+	const float pp[3] = {p.x, p.y, p.z};
+	float D[3];
+	for (int k = 0; k < 3; ++k) D[k] = (pp[k] - mx[k]) - (mn[k] - pp[k]);
+	const float nx = h2f(rec[0]), ny = h2f(rec[1]), nz = h2f(rec[2]), zc = h2f(rec[3]), h = h2f(rec[4]), r = h2f(rec[5]);
+	const float q = fmaf(nx, D[0], fmaf(ny, D[1], nz * D[2]));
+	const float DD = fmaf(D[0], D[0], fmaf(D[1], D[1], D[2] * D[2]));
+	const float rr = std::sqrt(std::max(fmaf(-q, q, DD), 0.f));
+	const float dz = std::max(std::fabs(q - zc) - h, 0.f), dr = std::max(rr - r, 0.f);
+	return fmaf(dz, dz, dr * dr) > fmaf(DD, 4e-6f, best4);
+}
+
+// The reference traversal (bvh.cuh:48-96) started from init_best (nullable: FLT_MAX) with the product's extra cull.
+// out_stats4 (nullable) += {quad expansions, leaf visits, children culled by the cylinder that the box test had passed, violations};
+// check != 0: every culled subtree is searched exhaustively for a triangle with d <= best (a violation of the argument).
+void orc_closest_triangle_cyl(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const uint16_t* cyl, const float* init_best, int* out_idx,
+                              double* out_stats4, int check) {
+	double acc[4] = {0, 0, 0, 0};
+	for (int q = 0; q < n; ++q) {
+		const V3 p = v3(pts + 3 * q);
+		int stack[64];
+		int sp = 0;
+		stack[sp++] = 0;
+		float best = init_best ? init_best[q] : std::numeric_limits<float>::max();
+		int best_i = -1;
+		while (sp > 0) {
+			const int idx = stack[--sp];
+			const orc_node& nd = nodes[idx];
+			if (nd.left_idx < 0) {
+				acc[1] += 1;
+				const int end = -nd.right_idx - 1;
+				for (int i = -nd.left_idx - 1; i < end; ++i) {
+					const float d = tri_distance_sq(tris[i], p);
+					if (d <= best) { best = d; best_i = i; }
+				}
+			} else {
+				acc[0] += 1;
+				float cd[4];
+				uint32_t ci[4];
+				const float best4 = best * 4.0088f;
+				for (uint32_t k = 0; k < 4; ++k) {
+					const orc_node& c = nodes[nd.left_idx + k];
+					cd[k] = box_distance_sq(c.mn, c.mx, p);
+					ci[k] = nd.left_idx + k;
+					if (cyl_cull_cpu(cyl + 8 * ci[k], c.mn, c.mx, p, best4)) ci[k] |= 0x80000000u;
+				}
+				auto cas = [&](int i, int j) {
+					if (cd[i] < cd[j]) { std::swap(cd[i], cd[j]); std::swap(ci[i], ci[j]); }
+				};
+				cas(0, 2); cas(1, 3); cas(0, 1); cas(2, 3); cas(1, 2);
+				for (int k = 0; k < 4; ++k) {
+					if (!(cd[k] <= best)) continue;
+					if (ci[k] & 0x80000000u) {
+						acc[2] += 1;
+						if (check) {
+							std::vector<int> todo{(int)(ci[k] & 0x7fffffffu)};
+							while (!todo.empty()) {
+								const int j = todo.back();
+								todo.pop_back();
+								if (nodes[j].left_idx < 0) {
+									for (int i = -nodes[j].left_idx - 1; i < -nodes[j].right_idx - 1; ++i)
+										if (tri_distance_sq(tris[i], p) <= best) acc[3] += 1;
+								} else
+									for (int c = 0; c < 4; ++c) todo.push_back(nodes[j].left_idx + c);
+							}
+						}
+						continue;
+					}
+					if (sp < 63) stack[sp++] = (int)ci[k];
+				}
+			}
+		}
+		out_idx[q] = best_i;
+	}
+	if (out_stats4)
+		for (int k = 0; k < 4; ++k) out_stats4[k] += acc[k];
+}
+
 float orc_triangle_distance_sq(const orc_tri* t, const float* p) { return tri_distance_sq(*t, v3(p)); }
 float orc_bbox_distance_sq(const float* mn, const float* mx, const float* p) { return box_distance_sq(mn, mx, v3(p)); }
 void orc_tri2projection(const orc_tri* t, float* out16) { tri2proj(*t, out16); }

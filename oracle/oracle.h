@@ -56,6 +56,10 @@ void orc_closest_triangle_bounded(const float* pts, int n, const orc_node* nodes
 /* diagnostic: traversal statistics (see oracle.cpp) */
 void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, double* out8);
 void orc_closest_stats_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, double* out8);
+/* The product's cylinder bounds restated (checker of the pruning argument; not in the reference): 8 halves per node */
+void orc_cyl_build(const orc_node* nodes, int n_nodes, const orc_tri* tris, uint16_t* out);
+void orc_closest_triangle_cyl(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const uint16_t* cyl, const float* init_best, int* out_idx,
+                              double* out_stats4, int check);
 float orc_triangle_distance_sq(const orc_tri* t, const float* p);
 float orc_bbox_distance_sq(const float* mn, const float* mx, const float* p);
 void orc_tri2projection(const orc_tri* t, float* out16_colmajor);

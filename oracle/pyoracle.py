@@ -76,6 +76,21 @@ class _Lib:
         self._fn("closest_triangle_bounded")(_p(pts), C.c_int(len(pts)), _p(nodes), _p(tris), _p(ib), _p(idx), C.c_int(n_threads or self.max_threads))
         return idx
 
+    def cyl_build(self, nodes, tris):
+        """The product's cylinder bounds (deform.cu build_cyl_kernel) restated: uint16[n_nodes, 8] fp16 bits."""
+        out = np.zeros((len(nodes), 8), np.uint16)
+        self._fn("cyl_build")(_p(nodes), C.c_int(len(nodes)), _p(tris), _p(out))
+        return out
+
+    def closest_triangle_cyl(self, pts, nodes, tris, cyl, init_best=None, check=False):
+        """Reference traversal + the product's cylinder cull; returns (idx, stats4 = expansions, leaf visits, culled children, violations)."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        ib = np.ascontiguousarray(init_best, np.float32) if init_best is not None else None
+        idx = np.empty(len(pts), np.int32)
+        st = np.zeros(4, np.float64)
+        self._fn("closest_triangle_cyl")(_p(pts), C.c_int(len(pts)), _p(nodes), _p(tris), _p(cyl), _p(ib), _p(idx), _p(st), C.c_int(int(check)))
+        return idx, st
+
     def warp(self, samples, stride, frame_id, nodes_list, tris_bvh_list, tris_topo_list, tris_canon, adjacency, aabb6,
              disable_interp=False, extra_dims=16, use_geo=False, frame_ids=None, n_threads=None):
         """In-place on `samples` (float32, n*stride). Returns (topology tri id, bvh-order idx) per sample."""
