@@ -69,12 +69,12 @@ static_assert(sizeof(TriXf) == 64, "TriXf is four 128-bit loads");
 
 // Tight bounds of the four children of one quad (deform.cu, "cylinder bounds"): per child the unit axis n (fp16, rounded away from zero), the slab
 // centre / half width along n and the radius around the axis through the centre of the child's BOX, the last three in doubled units.  A child is a
-// leaf or an inner node; the record lives kCylOffsetStride bytes per quad in a block of its own (FrameDev::cyl), 64 of them used.
+// leaf or an inner node; the records of a frame form a block of their own (FrameDev::cyl), kCylStride bytes per quad.
 struct __align__(16) QuadCyl {
 	uint16_t child[4][8];  // fp16 bits: nx, ny, nz, zc2, h2, r2, 0, 0
 };
 static_assert(sizeof(QuadCyl) == 64, "QuadCyl is four 128-bit chunks");
-constexpr uint32_t kCylStride = 128;  // same stride as the quads: address of a quad's bounds = address of the quad + a per-context constant
+constexpr uint32_t kCylStride = 64;  // packed: with 1,700 frames in a batch the L2 footprint per frame decides the traversal kernel's time
 
 struct FrameDev {
 	const Quad* quads;
