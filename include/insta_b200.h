@@ -115,6 +115,10 @@ INSTA_API int insta_set_aabb(insta_ctx* ctx, const float* h_aabb6);
  *   mask ids [n_faces], adjacency [n_faces*3] (-1 padded), BVH-order topology ids of a frame [n_faces] */
 INSTA_API int insta_get_topology(const insta_ctx* ctx, uint32_t* h_mask_ids, int32_t* h_adjacency);
 INSTA_API int insta_get_frame_bvh_order(const insta_ctx* ctx, int32_t frame, uint32_t* h_tri_ids, uint32_t* n_nodes);
+/* The traversal's cylinder bounds of a frame (this library's own pruning structure, not in the reference): per quad (= inner node of
+ * the reference tree, ngp triangle_bvh.cu:548-631, in node order) and child 8 fp16 values (axis x y z, slab centre, slab half width, radius, 0, 0; the
+ * last three in doubled units).  h_fp16_bits: n_quads * 4 * 8 uint16 (NULL: only the count).  Synchronises.  *n_quads = 0 when the topology has none. */
+INSTA_API int insta_get_frame_cylinders(insta_ctx* ctx, int32_t frame, uint16_t* h_fp16_bits, uint32_t* n_quads);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Stage 1 -- deformation.

@@ -130,7 +130,7 @@ EXPORTS = [
     "insta_params_default", "insta_last_error", "insta_version", "insta_ctx_create", "insta_ctx_destroy",
     "insta_set_canonical", "insta_load_canonical_obj", "insta_add_frame", "insta_add_frames", "insta_add_frame_obj",
     "insta_clear_frames", "insta_n_frames", "insta_get_render_aabb", "insta_set_aabb", "insta_get_topology",
-    "insta_get_frame_bvh_order", "insta_deform_samples", "insta_deform_samples_n", "insta_network_inference_n", "insta_deform_points", "insta_grid_layout", "insta_grid_n_params",
+    "insta_get_frame_bvh_order", "insta_get_frame_cylinders", "insta_deform_samples", "insta_deform_samples_n", "insta_network_inference_n", "insta_deform_points", "insta_grid_layout", "insta_grid_n_params",
     "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb", "insta_recorder_readback", "insta_host_write_png", "insta_host_write_depth_bin",
@@ -296,6 +296,15 @@ class Context:
         nn = C.c_uint32(0)
         self._check(self.lib.insta_get_frame_bvh_order(self.h, C.c_int32(frame), _vp(ids), C.byref(nn)))
         return ids, nn.value
+
+    def frame_cylinders(self, frame):
+        """uint16 [n_quads, 4, 8]: fp16 bits of the traversal's cylinder bounds (empty when the topology has none)"""
+        nq = C.c_uint32(0)
+        self._check(self.lib.insta_get_frame_cylinders(self.h, C.c_int32(frame), None, C.byref(nq)))
+        out = np.empty((nq.value, 4, 8), np.uint16)
+        if nq.value:
+            self._check(self.lib.insta_get_frame_cylinders(self.h, C.c_int32(frame), _vp(out), C.byref(nq)))
+        return out
 
     # ---- stage 1 ----
     def surface_closest_point(self, coords, tri_ids=None, stream=None):

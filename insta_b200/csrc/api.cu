@@ -679,6 +679,17 @@ int insta_get_frame_bvh_order(const insta_ctx* ctx, int32_t frame, uint32_t* h_t
 	return INSTA_OK;
 }
 
+int insta_get_frame_cylinders(insta_ctx* ctx, int32_t frame, uint16_t* h_fp16_bits, uint32_t* n_quads) {
+	if (!ctx || frame < 0 || (size_t)frame >= ctx->frames.size() || !n_quads) INSTA_FAIL(INSTA_ERR_INVALID, "insta_get_frame_cylinders: bad arguments");
+	const auto& f = ctx->frames[frame];
+	*n_quads = f.dev.cyl ? f.n_quads : 0u;
+	if (!f.dev.cyl || !h_fp16_bits) return INSTA_OK;
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	INSTA_CUDA(cudaDeviceSynchronize());
+	INSTA_CUDA(cudaMemcpy(h_fp16_bits, f.dev.cyl, (size_t)f.n_quads * kCylStride, cudaMemcpyDeviceToHost));
+	return INSTA_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 int insta_deform_samples(insta_ctx* ctx, float* d_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id, int32_t* d_tri_ids,
                          insta_stream stream) {

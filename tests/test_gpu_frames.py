@@ -114,3 +114,114 @@ def test_refit_frames_finds_a_nearest_triangle(oracle, scene, many_frames):
         ctx.close()
     finally:
         oracle.set_arith("host")
+
+
+def _frame_tris(scene, verts):
+    """a,b,c of every triangle of a frame (structured like the oracle's triangle records)"""
+    t = np.zeros(len(scene.faces), dtype=[("a", np.float32, 3), ("b", np.float32, 3), ("c", np.float32, 3)])
+    t["a"], t["b"], t["c"] = verts[scene.faces[:, 0]], verts[scene.faces[:, 1]], verts[scene.faces[:, 2]]
+    return t
+
+
+def _node_to_quad_child(nodes):
+    """(quad, child) of every non-root node of the reference tree: quads are the inner nodes in node order (mesh_host.cpp build_bvh)"""
+    inner = np.nonzero(nodes["left_idx"] >= 0)[0]
+    where = {}
+    for q, i in enumerate(inner):
+        for k in range(4):
+            where[int(nodes["left_idx"][i]) + k] = (q, k)
+    return where
+
+
+def test_cylinder_bounds_equal_the_checked_restatement(oracle, scene, many_frames):
+    """The bounds the traversal kernel prunes with (build_cyl_kernel, GPU, double precision) are the ones tests/test_oracle_cyl_bound.py checks
+    exhaustively on the CPU (oracle cyl_build): same fp16 values up to one ulp of the rounded-up slab / radius (fused vs unfused double arithmetic),
+    after an ingest, after insta_replace_frames and after insta_refit_frames."""
+    from insta_b200 import capi
+    from test_oracle_seed_bound import surface_points
+
+    def h2f(a):
+        return a.view(np.float16).astype(np.float64)
+
+    old, new = many_frames
+    ctx = capi.Context(device=0)
+    ctx.set_canonical(scene.verts, scene.faces, scene.masks)
+    ctx.add_frames(np.stack(old[:6]))
+
+    def check(frame, verts, rebuilt_tree=True):
+        t = oracle.build_triangles(verts, scene.faces, scene.masks, scene.canon)
+        nodes, tb = oracle.bvh_build(t)
+        got = ctx.frame_cylinders(frame)
+        assert got.shape[0] == int((nodes["left_idx"] >= 0).sum())
+        if not rebuilt_tree:  # refit: the frame keeps the tree it was built with (not the one a rebuild would give)
+            return got
+        want = oracle.cyl_build(nodes, tb)
+        where = _node_to_quad_child(nodes)
+        mine = np.zeros_like(want)
+        mine[0] = want[0]  # the root is never tested
+        same_axis = 0
+        for node, (q, k) in where.items():
+            g, w = got[q, k], want[node]
+            mine[node] = g
+            if (g[:3] == w[:3]).all():  # same axis (the fp32 normal sum is order dependent: a component may differ by one fp16 ulp) -> same slab, radius
+                same_axis += 1
+                assert abs(int(g[3]) - int(w[3])) <= 1 and abs(int(g[4]) - int(w[4])) <= 1 and abs(int(g[5]) - int(w[5])) <= 1, (frame, node, g, w)
+            else:
+                assert np.abs(h2f(g[:3]) - h2f(w[:3])).max() < 2e-3, (frame, node, g, w)
+        assert same_axis > 0.97 * len(where)
+        # ... and the GPU's own values pass the exhaustive check: no culled subtree holds a triangle the reference would accept, winners unchanged
+        rng = np.random.default_rng(frame)
+        lo, hi = scene.aabb[:3], scene.aabb[3:]
+        far = (rng.random((20000, 3), np.float32) * (hi - lo) + lo).astype(np.float32)
+        pts = np.concatenate([far, surface_points(tb, rng, 20000)])
+        ref_idx, _ = oracle.closest_triangle(pts, nodes, tb)
+        idx, st = oracle.closest_triangle_cyl(pts, nodes, tb, mine, None, check=True)
+        assert st[3] == 0 and st[2] > 0 and np.array_equal(idx, ref_idx)
+        return got
+
+    for f in (0, 5):
+        check(f, old[f])
+    ctx.replace_frames(np.array([5], np.int32), np.stack([new[5]]))
+    check(5, new[5])
+    before = ctx.frame_cylinders(2).copy()
+    ctx.refit_frames(np.array([2], np.int32), np.stack([new[2]]))
+    after = check(2, new[2], rebuilt_tree=False)
+    assert (after != before).any()  # the bounds followed the new vertices
+    assert np.isfinite(h2f(after[:, :, :4])).all()
+    ctx.close()
+
+
+def test_cylinder_cull_switch_gives_identical_records(scene, many_frames, monkeypatch):
+    """INSTA_DEFORM_CYL=0 (traversal with the reference's box test only) and the default produce the same bits: ids and deformed records, on random
+    samples and on points on / next to the surface where ties are the rule."""
+    import torch
+
+    from insta_b200 import capi, synth
+    from test_oracle_seed_bound import surface_points
+
+    old, _ = many_frames
+    n = 400000
+    fids = synth.train_regime_frame_ids(n, len(old))
+    rec = synth.make_records(n, scene.aabb, fids, seed=21, pad_fraction=0.01)
+    # a quarter of the batch sits on / next to the surface of its frame (vertices, edge midpoints, centroids: ties between neighbouring triangles)
+    rng = np.random.default_rng(4)
+    q = n // 4
+    for f in np.unique(fids[:q]):
+        sel = np.nonzero(fids[:q] == f)[0]
+        t = _frame_tris(scene, old[int(f)])
+        rec[sel, 0:3] = surface_points(t, rng, len(sel))
+    out = []
+    for env in ("1", "0"):
+        monkeypatch.setenv("INSTA_DEFORM_CYL", env)
+        ctx = capi.Context(device=0)
+        ctx.set_canonical(scene.verts, scene.faces, scene.masks)
+        ctx.add_frames(np.stack(old))
+        assert (ctx.frame_cylinders(0).shape[0] > 0) == (env == "1")
+        d = torch.from_numpy(rec.copy()).cuda()
+        tri = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+        ctx.surface_closest_point(d, tri)
+        torch.cuda.synchronize()
+        out.append((d.cpu().numpy(), tri.cpu().numpy()))
+        ctx.close()
+    assert (out[0][1] == out[1][1]).all()
+    assert (out[0][0].view(np.int32) == out[1][0].view(np.int32)).all()
