@@ -143,15 +143,44 @@ __device__ __forceinline__ void fwd_level_pairs(const GridLevels& L, uint32_t le
 	}
 }
 
+// TILES consecutive tiles per CTA, the positions of tile t + 1 requested before the gathers of tile t.  Measured (profiles/r2_hash_fwd_tiles_ab.txt): more
+// than one tile per CTA is SLOWER (1.51 -> 1.61 ms per 4M samples) -- the barrier per tile couples the 16 level-warps, while a one-tile CTA has no barrier
+// after its staging and a finished warp's slot goes to the next CTA -- so TILES = 1 ships.  What helps the one-tile CTA is an L2 prefetch of the records
+// a CTA `pf_tiles` further on will stage (one cp.async.bulk.prefetch per CTA): its 16 warps otherwise sit through a DRAM round trip at the barrier
+// (ncu: barrier stall 1.9 per issue); 300 tiles ahead: -2 %.
+template <int TILES>
 __global__ void __launch_bounds__(kFwdThreads, 2) hash_fwd_pairs_kernel(const __grid_constant__ GridLevels L, uint32_t n, const float* __restrict__ pos,
-                                                                     uint32_t stride, const uint4* __restrict__ table, __half* __restrict__ out) {
-	__shared__ float s_pos[kTile * 3];
-	const uint32_t tile_first = blockIdx.x * kTile;
-	stage_positions(s_pos, pos, stride, n, tile_first);
+                                                                     uint32_t stride, const uint4* __restrict__ table, __half* __restrict__ out, uint32_t pf_tiles) {
+	__shared__ float s_pos[TILES > 1 ? 2 : 1][kTile * 3];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-	for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
-		if (L.hashed[level]) fwd_level_pairs<true>(L, level, n, tile_first, lane, s_pos, table, out);
-		else fwd_level_pairs<false>(L, level, n, tile_first, lane, s_pos, table, out);
+	uint32_t tile_first = blockIdx.x * (kTile * TILES);
+	if (tile_first >= n) return;
+	if (pf_tiles && threadIdx.x == 0) {
+		const uint64_t first = (uint64_t)(blockIdx.x + pf_tiles) * (kTile * TILES);
+		if (first + kTile * TILES <= n) {
+			const uint64_t a0 = reinterpret_cast<uint64_t>(pos + first * stride) & ~15ull;
+			const uint32_t bytes = (kTile * TILES * stride * 4u + 31u) & ~15u;
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+		}
+	}
+	stage_positions(s_pos[0], pos, stride, n, tile_first);
+#pragma unroll 1
+	for (int t = 0; t < TILES; ++t, tile_first += kTile) {
+		const uint32_t next_first = tile_first + kTile;
+		const bool more = t + 1 < TILES && next_first < n;  // CTA-uniform
+		float nxt = 0.0f;
+		if (more && threadIdx.x < kTile * 3u) {
+			const uint32_t j = threadIdx.x / 3u, d = threadIdx.x - 3u * j, i = next_first + j;
+			if (i < n) nxt = ld_stream_f32(pos + (size_t)i * stride + d);
+		}
+		const float* sp = s_pos[TILES > 1 ? (t & 1) : 0];
+		for (uint32_t level = warp; level < L.n_levels; level += kFwdWarps) {
+			if (L.hashed[level]) fwd_level_pairs<true>(L, level, n, tile_first, lane, sp, table, out);
+			else fwd_level_pairs<false>(L, level, n, tile_first, lane, sp, table, out);
+		}
+		if (!more) break;
+		if (threadIdx.x < kTile * 3u) s_pos[TILES > 1 ? ((t + 1) & 1) : 0][threadIdx.x] = nxt;
+		__syncthreads();
 	}
 }
 
@@ -312,7 +341,12 @@ int launch_hash_fwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_
 	const dim3 grid((n + kTile - 1) / kTile);
 	static const bool v1 = [] { const char* e = getenv("INSTA_HASH_FWD"); return e && std::string(e) == "v1"; }();  // A/B: the sample-pair-per-lane kernel of round 1
 	if (v1) hash_fwd_kernel<<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out);
-	else hash_fwd_pairs_kernel<<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out);
+	else {
+		static const uint32_t pf = [] { const char* e = getenv("INSTA_HASH_PF"); return e ? (uint32_t)atoi(e) : 300u; }();  // tiles ahead (0 = no prefetch; A/B)
+		static const bool t4 = [] { const char* e = getenv("INSTA_HASH_FWD"); return e && std::string(e) == "t4"; }();       // A/B: four tiles per CTA
+		if (t4) hash_fwd_pairs_kernel<4><<<(grid.x + 3) / 4, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out, pf / 4);
+		else hash_fwd_pairs_kernel<1><<<grid, kFwdThreads, 0, s>>>(ctx->levels, n, d_pos, stride, (const uint4*)table, (__half*)out, pf);
+	}
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
