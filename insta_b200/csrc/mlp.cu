@@ -193,14 +193,27 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 		const uint32_t row = e & (kTileM - 1), half_id = e >> 7;  // levels [8 half_id, 8 half_id + 8)
 		const uint4* table = reinterpret_cast<const uint4*>(a.params + kOffGrid);
 		uint32_t it = 0;
+		// the position of this row's sample in the NEXT tile is requested a tile ahead: the records come from HBM, and a DRAM round trip at the head
+		// of every tile (~1 of ~9 us) is time the encoder warps -- which bound the kernel -- do not gather
+		const float* nrec = nullptr;
+		float npx = 0.f, npy = 0.f, npz = 0.f;
+		auto request = [&](uint32_t tile) {
+			const uint32_t i = tile * kTileM + row;
+			nrec = nullptr;
+			if (tile < n_tiles && i < n_samples) {
+				nrec = a.records + (size_t)(a.index ? __ldg(a.index + i) : i) * a.stride;
+				npx = __ldg(nrec); npy = __ldg(nrec + 1); npz = __ldg(nrec + 2);
+			}
+		};
+		request(blockIdx.x);
 		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
 			const uint32_t b = it & 1u;
+			const float* rec = nrec;
+			const float px = npx, py = npy, pz = npz;
+			request(tile + gridDim.x);
 			mbar_wait(bar_empty0 + 8 * b, ((it >> 1) & 1u) ^ 1u);
 			unsigned char* A0 = smem + kSmA0 + b * kBytesA0 + (row >> 3) * 128 + (row & 7) * 16;
-			const uint32_t i = tile * kTileM + row;
-			if (i < n_samples) {
-				const float* rec = a.records + (size_t)(a.index ? __ldg(a.index + i) : i) * a.stride;
-				const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
+			if (rec) {
 #pragma unroll 2
 				for (uint32_t l = 0; l < 8; ++l) {
 					const uint32_t level = half_id * 8 + l;
