@@ -363,6 +363,28 @@ def run_ours(args):
         e2e_total = float(t.item())
     e2e_value = world * N_SAMPLES * len(e2e_t) / e2e_total
 
+    # ---- the same records through deformation + the fused network, host in / host out (insta_deform_infer_host): what a caller of the reference's render or
+    # training loop consumes after `warp`; 108 B in + 8 B out per sample instead of 108 + 364 ----
+    pn_e2e = torch.from_numpy(synth.make_network_params(ctx.network_n_params, seed=1337)).cuda()
+    h_rgbs = torch.empty((N_SAMPLES, 4), dtype=torch.float16).pin_memory()
+    inf_t = []
+    for it in range(1 + e2e_steps):
+        barrier()
+        a = time.perf_counter()
+        ctx.deform_infer_host(h_rec0, frame_id, pn_e2e, h_rgbs)
+        b = time.perf_counter()
+        if it >= 1:
+            inf_t.append(b - a)
+    inf_total = float(np.sum(inf_t))
+    if world > 1:
+        t = torch.tensor([inf_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        inf_total = float(t.item())
+    e2e_infer = {"value": world * N_SAMPLES * len(inf_t) / inf_total, "unit": "deformed+evaluated samples/s", "h2d_bytes_per_step": int(h_rec0.numel() * 4),
+                 "d2h_bytes_per_step": int(h_rgbs.numel() * 2), "steps": len(inf_t),
+                 "note": "insta_deform_infer_host: pinned host records in, r g b sigma (fp16) out; deformation + fused encode / MLP kernels per 2^19-sample chunk on two streams"}
+    del pn_e2e, h_rgbs
+
     # ---- the reference's own CUDA kernels on the same device buffers (test infrastructure, oracle/ref_legs.py): AFTER our timed regions, rank 0 at N = 1 ----
     refc = None
     ref_hooks = {}
@@ -448,6 +470,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": N_SAMPLES * STRIDE * 4 + N_SAMPLES * 128 * 2, "steps": len(e2e_t), "numa_binding_rank0": numa,
                     "note": "insta_deform_encode_host: pinned host records in, deformed records + fp16 encodings out (1.98 GB over PCIe per step and rank): the "
                             "figure is the host link, not the kernels"},
+            "e2e_inference": e2e_infer,
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t1 - t0,
             "ingest": {"frames": int(n_local), "seconds": t_ing, "frames_per_s": n_local / max(t_ing, 1e-9), "host_threads": os.cpu_count(), "turnover": turn,
                        "note": "insta_add_frames (rta::Core::load_meshes, core.cu:294-334): per-frame host BVH build + H2D + transform table; outside the timed region"},

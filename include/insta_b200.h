@@ -457,6 +457,12 @@ INSTA_API int insta_grad_allreduce(insta_ctx* ctx, void* d_gradients_f16, uint64
  * ------------------------------------------------------------------------------------------------------------ */
 INSTA_API int insta_deform_encode_host(insta_ctx* ctx, float* h_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id,
                                        const void* d_table_f16, void* h_out_soa_f16);
+/* The same for a caller that wants what the reference's render / training loops consume after `warp`: deformation (rta::Core::surface_closest_point /
+ * render_deformed, src/core.cu:581-637) followed by NerfNetwork::inference_mixed_precision (ngp nerf_network.h:159-232) on host records; out = 4 halves
+ * (r, g, b, sigma logits) per sample.  The records are NOT copied back (h_coords is read only): 108 B in, 8 B out per sample over PCIe instead of
+ * 108 in + 364 out. */
+INSTA_API int insta_deform_infer_host(insta_ctx* ctx, const float* h_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id,
+                                      const void* d_params_f16, void* h_out_rgbsigma_f16);
 INSTA_API int insta_host_alloc(void** p, uint64_t bytes);
 INSTA_API int insta_host_free(void* p);
 

@@ -131,7 +131,7 @@ EXPORTS = [
     "insta_set_canonical", "insta_load_canonical_obj", "insta_add_frame", "insta_add_frames", "insta_add_frame_obj",
     "insta_clear_frames", "insta_n_frames", "insta_get_render_aabb", "insta_set_aabb", "insta_get_topology",
     "insta_get_frame_bvh_order", "insta_get_frame_cylinders", "insta_deform_samples", "insta_deform_samples_n", "insta_network_inference_n", "insta_deform_points", "insta_grid_layout", "insta_grid_n_params",
-    "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_host_alloc",
+    "insta_hash_encode_fwd", "insta_hash_encode_bwd", "insta_hash_slots", "insta_deform_encode_host", "insta_deform_infer_host", "insta_host_alloc",
     "insta_host_free", "insta_launch_count", "insta_host_bvh_build", "insta_host_build_triangles", "insta_host_adjacency",
     "insta_host_load_canonical_obj", "insta_host_mesh_aabb", "insta_recorder_readback", "insta_host_write_png", "insta_host_write_depth_bin",
     "insta_network_n_params", "insta_network_inference", "insta_network_density", "insta_network_forward_backward", "insta_training_set_images", "insta_generate_training_samples", "insta_compute_loss",
@@ -586,6 +586,12 @@ class Context:
         n, stride = h_coords.shape
         self._check(self.lib.insta_deform_encode_host(self.h, C.c_void_p(h_coords.data_ptr()), C.c_uint32(n), C.c_uint32(stride), C.c_int32(frame_id),
                                                       _dev(table), C.c_void_p(h_out.data_ptr())))
+
+    def deform_infer_host(self, h_coords, frame_id, params, h_out):
+        """h_coords: pinned float32 torch tensor [n, stride] (read only); h_out: pinned fp16 [n, 4] (r, g, b, sigma logits)."""
+        n, stride = h_coords.shape
+        self._check(self.lib.insta_deform_infer_host(self.h, C.c_void_p(h_coords.data_ptr()), C.c_uint32(n), C.c_uint32(stride), C.c_int32(frame_id),
+                                                     _dev(params), C.c_void_p(h_out.data_ptr())))
 
     def microbench_gather(self, buffer_bytes, chunk_bytes=16, iters=5):
         """GB/s of fully divergent chunk_bytes gathers from a buffer of buffer_bytes (L2-resident when it fits)."""

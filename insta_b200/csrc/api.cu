@@ -1079,6 +1079,35 @@ int insta_deform_encode_host(insta_ctx* ctx, float* h_coords, uint32_t n, uint32
 	return INSTA_OK;
 }
 
+int insta_deform_infer_host(insta_ctx* ctx, const float* h_coords, uint32_t n, uint32_t stride_floats, int32_t frame_id, const void* d_params_f16,
+                            void* h_out_rgbsigma_f16) {
+	if (!ctx || !h_coords || !d_params_f16 || !h_out_rgbsigma_f16) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_infer_host: bad arguments");
+	if (ctx->frames.empty()) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_infer_host: no frames loaded");
+	if (stride_floats < 11 + ctx->p.exp_params + ctx->p.geo_params) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_infer_host: records too short for the network's inputs");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	const uint32_t chunk = 1u << 19;
+	int rc = ensure_stage(ctx, std::min(chunk, std::max(n, 1u)), stride_floats);  // the encoding stage buffer (128 halves per sample) holds the 4 output halves
+	if (rc) return rc;
+	rc = sync_frame_table(ctx, ctx->streams[0]);
+	if (rc) return rc;
+	uint32_t k = 0;
+	for (uint32_t first = 0; first < n; first += chunk, ++k) {
+		const uint32_t m = std::min(chunk, n - first);
+		const int b = k & 1;
+		cudaStream_t s = ctx->streams[b];
+		float* d_rec = ctx->d_stage_rec[b];
+		INSTA_CUDA(cudaMemcpyAsync(d_rec, h_coords + (size_t)first * stride_floats, (size_t)m * stride_floats * 4, cudaMemcpyHostToDevice, s));
+		rc = launch_deform(ctx, d_rec, m, stride_floats, frame_id, nullptr, false, nullptr, s);
+		if (rc) return rc;
+		rc = launch_network_fwd(ctx, d_rec, stride_floats, m, d_params_f16, ctx->d_stage_enc[b], 0, s);
+		if (rc) return rc;
+		INSTA_CUDA(cudaMemcpyAsync((__half*)h_out_rgbsigma_f16 + (size_t)first * 4, ctx->d_stage_enc[b], (size_t)m * 8, cudaMemcpyDeviceToHost, s));
+	}
+	INSTA_CUDA(cudaStreamSynchronize(ctx->streams[0]));
+	INSTA_CUDA(cudaStreamSynchronize(ctx->streams[1]));
+	return INSTA_OK;
+}
+
 int insta_host_alloc(void** p, uint64_t bytes) {
 	if (!p) INSTA_FAIL(INSTA_ERR_INVALID, "p is null");
 	INSTA_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));

@@ -135,3 +135,23 @@ def test_host_buffer_path_matches_device_path(gpu_ctx, scene, layout):
     torch.cuda.synchronize()
     assert torch.equal(h_rec, d.cpu())
     assert torch.equal(h_out, out.cpu())
+
+
+def test_host_buffer_inference_path_matches_device_path(gpu_ctx, scene):
+    """insta_deform_infer_host (records in, r g b sigma out; nothing else crosses PCIe) = insta_deform_samples + insta_network_inference on the device"""
+    import torch
+
+    n = (1 << 19) + 4321                                        # two chunks, ragged
+    fids = synth.train_regime_frame_ids(n, 2)
+    rec = synth.make_records(n, scene.aabb, fids, seed=22, pad_fraction=0.01)
+    params = torch.from_numpy(synth.make_network_params(gpu_ctx.network_n_params, seed=1337)).cuda()
+    h_rec = torch.from_numpy(rec.copy()).pin_memory()
+    h_out = torch.zeros((n, 4), dtype=torch.float16).pin_memory()
+    gpu_ctx.deform_infer_host(h_rec, -1, params, h_out)
+    assert torch.equal(h_rec, torch.from_numpy(rec))             # read only
+    d = torch.from_numpy(rec.copy()).cuda()
+    gpu_ctx.surface_closest_point(d)
+    out = torch.empty((n, 4), dtype=torch.float16, device="cuda")
+    gpu_ctx.network_inference(d, params, out)
+    torch.cuda.synchronize()
+    assert torch.equal(h_out.view(torch.int16), out.cpu().view(torch.int16))
