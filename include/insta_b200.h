@@ -446,6 +446,10 @@ INSTA_API int insta_update_density_grid_mean_and_bitfield(insta_ctx* ctx, const 
 INSTA_API int insta_comm_unique_id(void* h_id128);  /* ncclGetUniqueId on rank 0; distribute the 128 bytes to the other ranks */
 INSTA_API int insta_comm_init_rank(insta_ctx* ctx, int world_size, int rank, const void* h_id128);
 INSTA_API int insta_comm_destroy(insta_ctx* ctx);
+/* How insta_train_nerf sums the gradients of this context's ranks: 0 = single rank / no communicator, 1 = ncclAllReduce, 2 = this library's own kernel over
+ * peer memory (NVLink / NVSwitch; one node, <= 8 ranks, buffers shared with cudaIpc: set up at the first training step, ncclAllReduce when that fails on any
+ * rank).  INSTA_GRAD_EXCHANGE = p2p | serial | overlap | none selects the mode at insta_trainer_create. */
+INSTA_API int insta_comm_exchange_mode(const insta_ctx* ctx);
 /* in-place sum over the ranks; insta_train_nerf calls it itself, pre-scaling each rank's loss by 1 / world_size */
 INSTA_API int insta_grad_allreduce(insta_ctx* ctx, void* d_gradients_f16, uint64_t n_halves, insta_stream stream);
 

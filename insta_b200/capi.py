@@ -140,7 +140,7 @@ EXPORTS = [
     "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
     "insta_replace_frames", "insta_refit_frames", "insta_host_write_trajectory_json", "insta_shard_frame_count", "insta_shard_owner", "insta_shard_local_ids",
     "insta_microbench_gather", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
-    "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_grad_allreduce",
+    "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_comm_exchange_mode", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
 
@@ -485,6 +485,11 @@ class Context:
 
     def comm_destroy(self):
         self._check(self.lib.insta_comm_destroy(self.h))
+
+    @property
+    def comm_exchange_mode(self):
+        """0 = single rank, 1 = ncclAllReduce, 2 = the library's own peer-memory kernel (after the first training step)"""
+        return int(self.lib.insta_comm_exchange_mode(self.h))
 
     def grad_allreduce(self, grads16, stream=None):
         self._check(self.lib.insta_grad_allreduce(self.h, _dev(grads16), C.c_uint64(grads16.numel()), _stream(stream)))

@@ -930,6 +930,8 @@ int insta_comm_destroy(insta_ctx* ctx) {
 	return INSTA_OK;
 }
 
+int insta_comm_exchange_mode(const insta_ctx* ctx) { return ctx ? comm_exchange_mode(ctx) : 0; }
+
 int insta_grad_allreduce(insta_ctx* ctx, void* d_gradients_f16, uint64_t n_halves, insta_stream stream) {
 	if (!ctx || (!d_gradients_f16 && n_halves)) INSTA_FAIL(INSTA_ERR_INVALID, "insta_grad_allreduce: bad arguments");
 	return grad_allreduce(ctx, d_gradients_f16, n_halves, (cudaStream_t)stream);

@@ -267,6 +267,7 @@ void comm_destroy(insta_ctx* ctx);
 int comm_unique_id(void* h_id128);
 int comm_init(insta_ctx* ctx, int world, int rank, const void* h_id128);
 int comm_world(const insta_ctx* ctx);
+int comm_exchange_mode(const insta_ctx* ctx);
 int grad_allreduce(insta_ctx* ctx, void* d_grads_f16, uint64_t n, cudaStream_t s);
 int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg);
 int trainer_state(const insta_ctx* ctx, insta_train_stats* out);

@@ -8,6 +8,7 @@
 //     needs a host round trip to learn the real count.  Here the deformation and inference kernels read the generator's sample counter on
 //     the device (`n_ptr`), so exactly the generated samples are processed, with no host synchronisation before the loss.
 //   * the workspace the reference carves out of the tcnn arena every step (testbed_nerf.cu:3175-3202) is allocated once per trainer.
+#include <cuda_fp16.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -28,6 +29,7 @@ struct NcclApi {
 	int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
 	int (*CommDestroy)(NcclComm) = nullptr;
 	int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+	int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;  // optional: peer-memory exchange setup
 	const char* (*GetErrorString)(int) = nullptr;
 };
 constexpr int kNcclHalf = 6, kNcclFloat = 7, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
@@ -50,6 +52,7 @@ NcclApi* nccl_api(std::string& err) {
 			api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
 			api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
 			api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+			api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
 			api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
 			if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) {
 				load_err = "NCCL library lacks a required symbol";
@@ -65,9 +68,25 @@ NcclApi* nccl_api(std::string& err) {
 }
 }  // namespace
 
+// Peer-memory gradient exchange (one node, world <= 8): every rank owns an exchange buffer E (the gradient vector) and a flag line, both exported with
+// cudaIpcGetMemHandle and mapped by every other rank.  See p2p_reduce_kernel.
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+	bool tried = false, ready = false;
+	uint64_t n_halves = 0;
+	__half* E = nullptr;              // this rank's exchange buffer
+	uint32_t* flags = nullptr;        // this rank's flag line: flags[p] = last phase rank p has signalled
+	__half* peer_E[kMaxPeers] = {};   // peer_E[rank] = E
+	uint32_t* peer_flags[kMaxPeers] = {};
+	uint32_t phase = 0;
+	void* d_tables = nullptr;         // PeerTables on the device
+};
+struct Comm;
+static void peer_exchange_free(Comm* c);
 struct Comm {
 	NcclComm comm = nullptr;
 	int rank = 0, world = 1;
+	PeerExchange px;
 };
 
 struct Trainer {
@@ -97,6 +116,7 @@ struct Trainer {
 	// gradient exchange (world > 1)
 	GradExchange ex{};
 	bool serial_exchange = false;  // INSTA_GRAD_EXCHANGE=serial
+	bool p2p_exchange = false;     // INSTA_GRAD_EXCHANGE=p2p: peer-memory exchange (peer_exchange_run); falls back to ncclAllReduce when the setup fails on any rank
 	bool no_exchange = false;      // INSTA_GRAD_EXCHANGE=none: the step without its collective (measurement only: the ranks' parameters diverge)
 };
 
@@ -142,6 +162,8 @@ void comm_destroy(insta_ctx* ctx) {
 	Comm* c = (Comm*)ctx->comm;
 	if (!c) return;
 	std::string err;
+	cudaDeviceSynchronize();
+	peer_exchange_free(c);
 	if (c->comm)
 		if (NcclApi* api = nccl_api(err)) api->CommDestroy(c->comm);
 	delete c;
@@ -184,6 +206,11 @@ int comm_init(insta_ctx* ctx, int world, int rank, const void* h_id128) {
 }
 
 int comm_world(const insta_ctx* ctx) { return ctx->comm ? ((Comm*)ctx->comm)->world : 1; }
+int comm_exchange_mode(const insta_ctx* ctx) {
+	const Comm* c = (const Comm*)ctx->comm;
+	if (!c || c->world <= 1) return 0;
+	return c->px.ready ? 2 : 1;
+}
 
 int grad_allreduce(insta_ctx* ctx, void* d_grads_f16, uint64_t n, cudaStream_t s) {
 	Comm* c = (Comm*)ctx->comm;
@@ -193,6 +220,170 @@ int grad_allreduce(insta_ctx* ctx, void* d_grads_f16, uint64_t n, cudaStream_t s
 	if (!api) INSTA_FAIL(INSTA_ERR_INVALID, "insta_grad_allreduce: " + err);
 	const int rc = api->AllReduce(d_grads_f16, d_grads_f16, (size_t)n, kNcclHalf, kNcclSum, c->comm, s);
 	if (rc != 0) INSTA_FAIL(INSTA_ERR_CUDA, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+	return INSTA_OK;
+}
+
+
+// ---- gradient exchange over peer memory (NVLink / NVSwitch) ---------------------------------------------------------------------------------------
+// The backward pass of rank r writes its gradient vector into E_r.  Then, instead of ncclAllReduce:
+//   barrier (every rank's E is final) -> p2p_reduce_kernel -> barrier (every rank's writes have landed) -> optimizer step on E_r.
+// p2p_reduce_kernel on rank r owns slice r of the vector: per 16-byte chunk it loads the chunk from all `world` exchange buffers (world - 1 of the loads
+// cross NVLink), adds the eight halves in fp32 in rank order -- every rank would compute the same bits for a chunk, so the replicas stay identical -- and
+// stores the fp16 sum into slice r of ALL buffers (world - 1 remote stores).  Per rank 2 (world - 1) / world of the vector cross the link, as in a ring
+// all-reduce, but in one pass of independent 16-byte accesses with nothing between the two directions except the kernel itself.  Slice r of any buffer is
+// read and written by rank r only; a buffer is not overwritten by the next step's backward pass before every peer has passed the second barrier.
+__global__ void __launch_bounds__(256) p2p_reduce_kernel(const uint4* const* __restrict__ src, uint4* const* __restrict__ dst, uint32_t world, uint64_t first, uint64_t count) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	uint4 v[kMaxPeers];
+#pragma unroll
+	for (int p = 0; p < kMaxPeers; ++p)
+		if ((uint32_t)p < world) v[p] = src[p][first + i];
+	float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+	for (int p = 0; p < kMaxPeers; ++p)
+		if ((uint32_t)p < world) {
+			const __half2* h = reinterpret_cast<const __half2*>(&v[p]);
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const float2 f = __half22float2(h[k]);
+				acc[2 * k] += f.x;
+				acc[2 * k + 1] += f.y;
+			}
+		}
+	uint4 out;
+	__half2* o = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) o[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+#pragma unroll
+	for (int p = 0; p < kMaxPeers; ++p)
+		if ((uint32_t)p < world) dst[p][first + i] = out;
+}
+
+// One warp: lane p tells rank p "rank `rank` has reached `phase`", then waits until every rank has told this one.  A kernel boundary precedes it on the
+// stream, so this rank's earlier writes (local and remote) have been issued; the fence orders them before the flag at system scope.
+__global__ void p2p_barrier_kernel(uint32_t* const* __restrict__ peer_flags, volatile uint32_t* __restrict__ my_flags, uint32_t rank, uint32_t world, uint32_t phase) {
+	const uint32_t p = threadIdx.x;
+	__threadfence_system();
+	if (p < world) {
+		asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p] + rank), "r"(phase) : "memory");
+		uint32_t seen;
+		do {
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flags + p) : "memory");
+		} while ((int32_t)(seen - phase) < 0);
+	}
+	__syncwarp();
+	__threadfence_system();
+}
+
+struct PeerTables {  // device copies of the pointer tables (kernel arguments by pointer keep the kernels' parameter space small)
+	const uint4* src[kMaxPeers];
+	uint4* dst[kMaxPeers];
+	uint32_t* flags[kMaxPeers];
+};
+
+static void peer_exchange_free(Comm* c) {
+	PeerExchange& x = c->px;
+	for (int p = 0; p < kMaxPeers; ++p) {
+		if (p != c->rank && x.peer_E[p]) cudaIpcCloseMemHandle(x.peer_E[p]);
+		if (p != c->rank && x.peer_flags[p]) cudaIpcCloseMemHandle(x.peer_flags[p]);
+		x.peer_E[p] = nullptr;
+		x.peer_flags[p] = nullptr;
+	}
+	if (x.E) cudaFree(x.E);
+	if (x.flags) cudaFree(x.flags);
+	if (x.d_tables) cudaFree(x.d_tables);
+	x.d_tables = nullptr;
+	x.E = nullptr;
+	x.flags = nullptr;
+	x.ready = false;
+}
+
+// Collective: every rank calls it at the same point (first training step).  Any failure on any rank (no IPC, world > 8, old NCCL) makes ALL ranks fall back
+// to ncclAllReduce -- the outcome is agreed upon with an all-reduce of a flag.
+static bool peer_exchange_setup(insta_ctx* ctx, uint64_t n_halves, cudaStream_t s) {
+	Comm* c = (Comm*)ctx->comm;
+	PeerExchange& x = c->px;
+	if (x.tried) return x.ready && x.n_halves == n_halves;
+	x.tried = true;
+	std::string err;
+	NcclApi* api = nccl_api(err);
+	if (!api || !api->AllGather || c->world > kMaxPeers) return false;
+	struct Blob { cudaIpcMemHandle_t e, f; int ok; int pad[3]; };
+	Blob mine{};
+	bool ok = cudaMalloc(&x.E, n_halves * 2) == cudaSuccess && cudaMalloc(&x.flags, 256) == cudaSuccess;
+	ok = ok && cudaMemset(x.flags, 0, 256) == cudaSuccess && cudaMemset(x.E, 0, n_halves * 2) == cudaSuccess;
+	ok = ok && cudaIpcGetMemHandle(&mine.e, x.E) == cudaSuccess && cudaIpcGetMemHandle(&mine.f, x.flags) == cudaSuccess;
+	mine.ok = ok ? 1 : 0;
+	cudaGetLastError();
+	Blob* d_blobs = nullptr;
+	std::vector<Blob> all(c->world);
+	bool coll = cudaMalloc(&d_blobs, sizeof(Blob) * (c->world + 1)) == cudaSuccess;
+	if (coll) {
+		cudaMemcpy(d_blobs + c->world, &mine, sizeof(Blob), cudaMemcpyHostToDevice);
+		coll = api->AllGather(d_blobs + c->world, d_blobs, sizeof(Blob), /*ncclChar*/ 0, c->comm, s) == 0 && cudaStreamSynchronize(s) == cudaSuccess;
+		if (coll) cudaMemcpy(all.data(), d_blobs, sizeof(Blob) * c->world, cudaMemcpyDeviceToHost);
+	}
+	bool all_ok = coll;
+	for (int p = 0; p < c->world && all_ok; ++p) all_ok = all[p].ok == 1;
+	if (all_ok) {
+		for (int p = 0; p < c->world && all_ok; ++p) {
+			if (p == c->rank) {
+				x.peer_E[p] = x.E;
+				x.peer_flags[p] = x.flags;
+				continue;
+			}
+			void *pe = nullptr, *pf = nullptr;
+			all_ok = cudaIpcOpenMemHandle(&pe, all[p].e, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+			         cudaIpcOpenMemHandle(&pf, all[p].f, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+			x.peer_E[p] = (__half*)pe;
+			x.peer_flags[p] = (uint32_t*)pf;
+		}
+		cudaGetLastError();
+	}
+	// agree: min over the ranks of "I mapped everybody" (the blob buffer doubles as the flag's storage)
+	int agreed = 0;
+	if (coll) {
+		const float mine_ok = all_ok ? 0.f : 1.f;  // sum of failures
+		cudaMemcpy(d_blobs, &mine_ok, 4, cudaMemcpyHostToDevice);
+		float total = 1.f;
+		if (api->AllReduce(d_blobs, d_blobs, 1, kNcclFloat, kNcclSum, c->comm, s) == 0 && cudaStreamSynchronize(s) == cudaSuccess &&
+		    cudaMemcpy(&total, d_blobs, 4, cudaMemcpyDeviceToHost) == cudaSuccess)
+			agreed = total == 0.f ? 1 : 0;
+	}
+	if (d_blobs) cudaFree(d_blobs);
+	if (agreed) {
+		PeerTables t{};
+		for (int p = 0; p < c->world; ++p) {
+			t.src[p] = reinterpret_cast<const uint4*>(x.peer_E[p]);
+			t.dst[p] = reinterpret_cast<uint4*>(x.peer_E[p]);
+			t.flags[p] = x.peer_flags[p];
+		}
+		if (cudaMalloc(&x.d_tables, sizeof(PeerTables)) != cudaSuccess || cudaMemcpy(x.d_tables, &t, sizeof(PeerTables), cudaMemcpyHostToDevice) != cudaSuccess) agreed = 0;
+		// (a rank failing here would leave the others waiting at the first barrier: 100 bytes of device memory do not fail after 51 MB succeeded)
+	}
+	if (!agreed) {
+		peer_exchange_free(c);
+		return false;
+	}
+	x.n_halves = n_halves;
+	x.ready = true;
+	return true;
+}
+
+// barrier -> reduce -> barrier on stream s; E holds the summed gradients on every rank afterwards
+static int peer_exchange_run(insta_ctx* ctx, cudaStream_t s) {
+	Comm* c = (Comm*)ctx->comm;
+	PeerExchange& x = c->px;
+	PeerTables* d_tables = (PeerTables*)x.d_tables;
+	const uint64_t chunks = x.n_halves / 8;  // the parameter count is a multiple of 8 (16-byte grid entries, 25,600 MLP weights)
+	const uint64_t per = (chunks + c->world - 1) / c->world;
+	const uint64_t first = std::min<uint64_t>(per * c->rank, chunks), count = std::min<uint64_t>(per, chunks - first);
+	p2p_barrier_kernel<<<1, 32, 0, s>>>(d_tables->flags, x.flags, (uint32_t)c->rank, (uint32_t)c->world, ++x.phase);
+	if (count) p2p_reduce_kernel<<<(uint32_t)((count + 255) / 256), 256, 0, s>>>(d_tables->src, d_tables->dst, (uint32_t)c->world, first, count);
+	p2p_barrier_kernel<<<1, 32, 0, s>>>(d_tables->flags, x.flags, (uint32_t)c->rank, (uint32_t)c->world, ++x.phase);
+	ctx->launches += 3;
+	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
 }
 
@@ -208,6 +399,7 @@ int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
 	if (const char* e = getenv("INSTA_GRAD_EXCHANGE")) {
 		t->serial_exchange = std::string(e) != "overlap";
 		t->no_exchange = std::string(e) == "none";
+		t->p2p_exchange = std::string(e) == "p2p";
 	}
 	const uint32_t target = cfg->target_batch_size;
 	const uint32_t max_samples = target * 16;  // "somewhat of a worst case" (testbed_nerf.cu:3172)
@@ -346,16 +538,25 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 		for (int g = 0; g < 4; ++g) INSTA_CUDA(cudaEventCreateWithFlags(&t->ex.ev_grid_ready[g], cudaEventDisableTiming));
 		INSTA_CUDA(cudaEventCreateWithFlags(&t->ex.ev_grid_summed, cudaEventDisableTiming));
 	}
-	rc = launch_network_fwd_bwd(ctx, t->coords_compacted, stride, target, opt->d_params_f16, t->dloss, kOutWidth, (void*)opt->d_gradients_f16, nullptr, s, overlap ? &t->ex : nullptr);
+	// INSTA_GRAD_EXCHANGE=p2p: the backward pass writes into this rank's exported exchange buffer, the sum is formed over peer memory (peer_exchange_run)
+	const bool p2p = world > 1 && t->p2p_exchange && !t->no_exchange && peer_exchange_setup(ctx, network_n_params(ctx), s);
+	void* grads = p2p ? (void*)((Comm*)ctx->comm)->px.E : (void*)opt->d_gradients_f16;
+	rc = launch_network_fwd_bwd(ctx, t->coords_compacted, stride, target, opt->d_params_f16, t->dloss, kOutWidth, grads, nullptr, s, overlap && !p2p ? &t->ex : nullptr);
 	if (rc) return rc;
 	t->rng_advances += 1;  // m_rng.advance() (testbed_nerf.cu:3419)
-	if (!overlap && !t->no_exchange) {
+	if (p2p) {
+		rc = peer_exchange_run(ctx, s);
+		if (rc) return rc;
+		// the caller's gradient buffer holds the summed gradients after the step, as with the collective
+		INSTA_CUDA(cudaMemcpyAsync((void*)opt->d_gradients_f16, grads, (size_t)network_n_params(ctx) * 2, cudaMemcpyDeviceToDevice, s));
+	} else if (!overlap && !t->no_exchange) {
 		rc = grad_allreduce(ctx, (void*)opt->d_gradients_f16, network_n_params(ctx), s);
 		if (rc) return rc;
 	}
 	// Trainer::optimizer_step(stream, LOSS_SCALE) (testbed_nerf.cu:2974)
 	if (!c.freeze_parameters) {
 		insta_optimizer o = *opt;
+		o.d_gradients_f16 = (decltype(o.d_gradients_f16))grads;
 		o.loss_scale = c.loss_scale;
 		rc = optimizer_step(ctx, &o, network_n_params(ctx), 25600u, s);
 		if (rc) return rc;

@@ -61,7 +61,10 @@ def run(rank, world, seed, out_path, uid_path=None):
     torch.cuda.synchronize()
     assert torch.equal(p16, ema) and torch.equal(p32, p16.float()), "frozen parameters moved"
     np.save(out_path, grads.cpu().numpy())
+    mode = ctx.comm_exchange_mode
     if world > 1:
+        want = os.environ.get("EXPECT_EXCHANGE_MODE")
+        assert want is None or mode == int(want), "exchange mode %d, expected %s" % (mode, want)
         ctx.comm_destroy()
     ctx.close()
     return st
