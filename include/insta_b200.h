@@ -529,6 +529,9 @@ INSTA_API void insta_snapshot_close(insta_snapshot_file* file);
  * read by 8 cooperating lanes) from an internal buffer of buffer_bytes -- L2-resident when it fits the 126 MB L2, HBM-bound otherwise.
  * Best of `iters` launches after warm-up, GB/s of gathered bytes.  bench.py reports it as the L2-gather roofline. */
 INSTA_API int insta_microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, insta_stream stream);
+/* The same for the scatter side (roofline of kernel_grid_backward, tcnn encodings/grid.h:312-435): every lane adds 8 halves to a pseudo-random 16-byte entry with one
+ * vector reduction at L2; chunk_bytes 32 / 64 = 2 / 4 adjacent lanes on adjacent entries.  GB/s of reduced bytes (16 per lane and reduction). */
+INSTA_API int insta_microbench_scatter(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, insta_stream stream);
 
 /* Host only: the sharding rule of SURVEY 8e for C / C++ callers (the Python helper insta_b200/shard.py states the same rule).  One process per GPU; rank r of
  * `world` holds the frames r, r + world, r + 2 world, ... (their BVHs, transform tables and images never reach the other GPUs), draws its own ray batches

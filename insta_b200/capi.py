@@ -139,7 +139,7 @@ EXPORTS = [
     "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
     "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
     "insta_replace_frames", "insta_refit_frames", "insta_host_write_trajectory_json", "insta_shard_frame_count", "insta_shard_owner", "insta_shard_local_ids",
-    "insta_microbench_gather", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
+    "insta_microbench_gather", "insta_microbench_scatter", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
     "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_comm_exchange_mode", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
@@ -602,6 +602,12 @@ class Context:
         """GB/s of fully divergent chunk_bytes gathers from a buffer of buffer_bytes (L2-resident when it fits)."""
         g = C.c_float(0)
         self._check(self.lib.insta_microbench_gather(self.h, C.c_uint64(buffer_bytes), C.c_uint32(chunk_bytes), C.c_uint32(iters), C.byref(g), _stream(None)))
+        return float(g.value)
+
+    def microbench_scatter(self, buffer_bytes, chunk_bytes=16, iters=5):
+        """GB/s of fully divergent 16-byte fp16 vector reductions into a buffer of buffer_bytes (chunk_bytes 32 / 64: 2 / 4 adjacent lanes on adjacent entries)."""
+        g = C.c_float(0)
+        self._check(self.lib.insta_microbench_scatter(self.h, C.c_uint64(buffer_bytes), C.c_uint32(chunk_bytes), C.c_uint32(iters), C.byref(g), _stream(None)))
         return float(g.value)
 
     @property

@@ -913,6 +913,12 @@ int insta_microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chun
 	return microbench_gather(ctx, buffer_bytes, chunk_bytes, iters, h_gbs, (cudaStream_t)stream);
 }
 
+int insta_microbench_scatter(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, insta_stream stream) {
+	if (!ctx || !h_gbs || iters == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_microbench_scatter: bad arguments");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	return microbench_scatter(ctx, buffer_bytes, chunk_bytes, iters, h_gbs, (cudaStream_t)stream);
+}
+
 int insta_comm_unique_id(void* h_id128) {
 	if (!h_id128) INSTA_FAIL(INSTA_ERR_INVALID, "insta_comm_unique_id: null buffer");
 	return comm_unique_id(h_id128);

@@ -256,6 +256,7 @@ int snapshot_open(const char* path, SnapshotFile** out_file, insta_snapshot* s);
 void snapshot_close(SnapshotFile* f);
 // microbench.cu
 int microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, cudaStream_t s);
+int microbench_scatter(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, cudaStream_t s);
 // occupancy.cu
 void occupancy_destroy(insta_ctx* ctx);
 int density_grid_update(insta_ctx* ctx, insta_density_grid* g, const void* d_params_f16, uint32_t n_uniform, uint32_t n_nonuniform, cudaStream_t s);

@@ -282,6 +282,97 @@ __global__ void __launch_bounds__(kBwdThreads) hash_bwd_kernel(const __grid_cons
 	}
 }
 
+// Lane-pair version (default), the mapping of hash_fwd_pairs_kernel: lane l = x-side (l & 1) of the samples 4 (l >> 1) + {0, 1, 2, 3} of the tile.  In every
+// reduction instruction the two lanes of a pair address the entries (x, y, z) and (x + 1, y, z): neighbours in the table, the same 32-byte sector whenever the
+// slot of the x-side 0 is even, which the memory system then handles as ONE request (insta_microbench_scatter: 32-byte chunks shared by two lanes against
+// 16-byte chunks).  Same products and the same fp16 rounding as kernel_grid_backward (grid.h:352); the order of the additions is not defined in the reference either.
+// TILED: dLdy in the layout the fused network kernel (mlp_bwd.cu) produces -- [tile of 128 samples][level][sample][8 features], the 8 gradients of a level in
+// one 16-byte load -- instead of kernel_grid_backward's SoA rows.
+template <bool HASHED, bool TILED>
+__device__ __forceinline__ void bwd_level_pairs(const GridLevels& L, uint32_t level, uint32_t n, uint32_t pitch, uint32_t tile_first, uint32_t lane,
+                                                const float* __restrict__ s_pos, const __half* __restrict__ dLdy, uint4* __restrict__ grad) {
+	const uint32_t b = lane & 1u, g = lane >> 1;
+	const uint32_t i0 = tile_first + 4u * g;
+	if (i0 >= n) return;
+	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
+	const float scale = L.scale[level];
+	grad += L.offset[level];
+	const __half* row = dLdy + (size_t)(level * 8) * pitch + i0;
+	uint32_t gr[4][4];  // [sample][feature pair] as half2 bits
+	if (TILED) {
+#pragma unroll
+		for (uint32_t q = 0; q < 4; ++q) {
+			const uint32_t i = i0 + q;
+			uint4 v = make_uint4(0, 0, 0, 0);
+			if (i < n) v = __ldg(reinterpret_cast<const uint4*>(dLdy + ((size_t)(i >> 7) * 16u + level) * 1024u + (i & 127u) * 8u));
+			gr[q][0] = v.x; gr[q][1] = v.y; gr[q][2] = v.z; gr[q][3] = v.w;
+		}
+	} else if (i0 + 3u < n && (pitch % 4u == 0)) {
+		uint2 raw[8];
+#pragma unroll
+		for (int f = 0; f < 8; ++f) raw[f] = __ldg(reinterpret_cast<const uint2*>(row + (size_t)f * pitch));  // feature f of the 4 samples
+#pragma unroll
+		for (int h = 0; h < 4; ++h) {
+			gr[0][h] = __byte_perm(raw[2 * h].x, raw[2 * h + 1].x, 0x5410);
+			gr[1][h] = __byte_perm(raw[2 * h].x, raw[2 * h + 1].x, 0x7632);
+			gr[2][h] = __byte_perm(raw[2 * h].y, raw[2 * h + 1].y, 0x5410);
+			gr[3][h] = __byte_perm(raw[2 * h].y, raw[2 * h + 1].y, 0x7632);
+		}
+	} else {
+#pragma unroll
+		for (uint32_t q = 0; q < 4; ++q)
+#pragma unroll
+			for (int h = 0; h < 4; ++h) {
+				const uint32_t lo = i0 + q < n ? __half_as_ushort(row[(size_t)(2 * h) * pitch + q]) : 0u;
+				const uint32_t hi = i0 + q < n ? __half_as_ushort(row[(size_t)(2 * h + 1) * pitch + q]) : 0u;
+				gr[q][h] = lo | (hi << 16);
+			}
+	}
+#pragma unroll
+	for (uint32_t q = 0; q < 4; ++q) {
+		// adding +0 to every slot is a no-op (and -0 + x = x): skip samples whose gradient is all zeros
+		if (((gr[q][0] | gr[q][1] | gr[q][2] | gr[q][3]) & 0x7fff7fffu) == 0u) continue;
+		const float* sp = s_pos + 3u * (4u * g + q);
+		const Corner c = pos_fract3(sp[0], sp[1], sp[2], scale);
+		const float wx = b ? c.fr[0] : __fsub_rn(1.0f, c.fr[0]);  // 1 * wx is exact
+		const uint32_t gx = c.g[0] + b;
+		float gf[8];
+#pragma unroll
+		for (int h = 0; h < 4; ++h) {
+			const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gr[q][h]));
+			gf[2 * h] = f.x;
+			gf[2 * h + 1] = f.y;
+		}
+#pragma unroll
+		for (uint32_t k = 0; k < 4; ++k) {
+			const uint32_t dy = k & 1u, dz = k >> 1;
+			float wk = __fmul_rn(wx, dy ? c.fr[1] : __fsub_rn(1.0f, c.fr[1]));
+			wk = __fmul_rn(wk, dz ? c.fr[2] : __fsub_rn(1.0f, c.fr[2]));
+			uint32_t packed[4];
+#pragma unroll
+			for (int h = 0; h < 4; ++h) {
+				const __half2 v = __floats2half2_rn(__fmul_rn(gf[2 * h], wk), __fmul_rn(gf[2 * h + 1], wk));  // grid.h:352
+				packed[h] = *reinterpret_cast<const uint32_t*>(&v);
+			}
+			red_add_v4_f16x2(grad + slot_of<HASHED>(gx, c.g[1] + dy, c.g[2] + dz, size, mul1, mul2), packed[0], packed[1], packed[2], packed[3]);
+		}
+	}
+}
+
+template <bool TILED>
+__global__ void __launch_bounds__(kBwdThreads) hash_bwd_pairs_kernel(const __grid_constant__ GridLevels L, uint32_t n, uint32_t pitch, const float* __restrict__ pos,
+                                                                     uint32_t stride, const __half* __restrict__ dLdy, uint4* __restrict__ grad, uint32_t level_begin,
+                                                                     uint32_t level_end) {
+	__shared__ float s_pos[kTile * 3];
+	const uint32_t tile_first = blockIdx.x * kTile;
+	stage_positions(s_pos, pos, stride, n, tile_first);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
+	for (uint32_t level = level_begin + warp; level < level_end; level += n_warps) {
+		if (L.hashed[level]) bwd_level_pairs<true, TILED>(L, level, n, pitch, tile_first, lane, s_pos, dLdy, grad);
+		else bwd_level_pairs<false, TILED>(L, level, n, pitch, tile_first, lane, s_pos, dLdy, grad);
+	}
+}
+
 }  // namespace
 
 // Offset table exactly as the ctor builds it (grid.h:898-922), with the per-level scale taken from the device.
@@ -356,7 +447,7 @@ int launch_hash_bwd(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_
 	return launch_hash_bwd_pitched(ctx, d_pos, stride, n, dLdy, n, grad, zero_first, s);
 }
 
-// dLdy rows are `pitch` samples apart (pitch >= n)
+// dLdy rows are `pitch` samples apart (pitch >= n); pitch == 0: the tiled layout of the fused network kernel (bwd_level_pairs)
 int launch_hash_bwd_pitched(insta_ctx* ctx, const float* d_pos, uint32_t stride, uint32_t n, const void* dLdy, uint32_t pitch, void* grad, int zero_first, cudaStream_t s) {
 	return launch_hash_bwd_levels(ctx, d_pos, stride, n, dLdy, pitch, grad, zero_first, 0, ctx->levels.n_levels, s);
 }
@@ -370,7 +461,10 @@ int launch_hash_bwd_levels(insta_ctx* ctx, const float* d_pos, uint32_t stride, 
 	if (n == 0) return INSTA_OK;
 	const dim3 grid((n + kTile - 1) / kTile);
 	const uint32_t warps = std::min<uint32_t>(level_end - level_begin, (uint32_t)kFwdWarps);
-	hash_bwd_kernel<<<grid, warps * 32, 0, s>>>(L, n, pitch, d_pos, stride, (const __half*)dLdy, (uint4*)grad, level_begin, level_end);
+	static const bool v1 = [] { const char* e = getenv("INSTA_HASH_BWD"); return e && std::string(e) == "v1"; }();  // A/B: the sample-pair-per-lane kernel of round 1
+	if (pitch == 0) hash_bwd_pairs_kernel<true><<<grid, warps * 32, 0, s>>>(L, n, pitch, d_pos, stride, (const __half*)dLdy, (uint4*)grad, level_begin, level_end);
+	else if (v1) hash_bwd_kernel<<<grid, warps * 32, 0, s>>>(L, n, pitch, d_pos, stride, (const __half*)dLdy, (uint4*)grad, level_begin, level_end);
+	else hash_bwd_pairs_kernel<false><<<grid, warps * 32, 0, s>>>(L, n, pitch, d_pos, stride, (const __half*)dLdy, (uint4*)grad, level_begin, level_end);
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;

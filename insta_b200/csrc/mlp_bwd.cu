@@ -11,7 +11,7 @@
 //                       and output gradient dY_l is written once to a global fp16 scratch (row-major) for the weight gradients;
 //                       dL/d(grid features) leaves as the SoA matrix kernel hash_bwd_kernel scatters.
 //   net_wgrad_kernel    dW_l = dY_l^T X_l for all seven layers in one pass over the samples: both operands are used in their
-//                       MN-major (transposed) UMMA form, which is exactly the row-major scratch copied in 16-byte chunks; all
+//                       MN-major (transposed) UMMA form, which is exactly the scratch copied in 16-byte chunks; all
 //                       seven fp32 accumulators (496 columns) live in tensor memory for the whole kernel; one fp32 atomicAdd
 //                       pass per CTA at the end.  M is padded to 128 by letting the descriptor run into the next layers' tiles
 //                       (rows >= n_out are never read back).
@@ -30,8 +30,10 @@ using namespace griddev;
 using namespace umma;
 
 constexpr int kTileM = 128;
-constexpr int kMlpWarps = 4, kEncWarps = 8;
-constexpr int kMlpThreads = kMlpWarps * 32, kNetThreads = (kMlpWarps + kEncWarps) * 32;
+constexpr int kEncWarps = 8;
+// MLP warps: 4 x SPLIT.  A warp reads the 32 tensor-memory lanes (tile rows) 32 (w % 4) ..; with SPLIT = 2 the warps w and w + 4 share those rows and take
+// half of a layer's columns each, so an epilogue -- the part of the 15-stage dependent chain of a tile that is not the GEMM -- takes half as long.
+constexpr int kSplit = 2;
 constexpr int kWidth = 64, kInDensity = 144, kInRgb = 32, kOutPad = 16;
 constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kWidth * kInDensity, kOffW3 = kOffW2 + kWidth * kWidth;
 constexpr uint32_t kOffV1 = kOffW3 + kOutPad * kWidth, kOffV2 = kOffV1 + kWidth * kInRgb, kOffV3 = kOffV2 + kWidth * kWidth;
@@ -43,6 +45,8 @@ __constant__ const uint32_t c_kin[7] = {144, 64, 64, 32, 64, 64, 64};
 __constant__ const uint32_t c_woff[7] = {kOffW1, kOffW2, kOffW3, kOffV1, kOffV2, kOffV3, kOffV4};
 // column offsets (halves) of X_l / dY_l inside one scratch row
 constexpr uint32_t kXCols = 496, kDyCols = 352;
+// scratch layout: [tile][chunk][row][8 halves]; halves per chunk of a tile and chunks per tile
+constexpr uint32_t kChunkHalves = kTileM * 8, kXChunks = kXCols / 8, kDyChunks = kDyCols / 8, kFeatChunks = 16;
 __constant__ const uint32_t c_xoff[7] = {0, 144, 208, 272, 304, 368, 432};
 __constant__ const uint32_t c_dyoff[7] = {0, 64, 128, 144, 208, 272, 336};
 
@@ -53,7 +57,8 @@ constexpr uint32_t kSmA0 = 0, kSmH = kSmA0 + 2 * kBytesA0, kSmA3 = kSmH + 2 * kB
 constexpr uint32_t kSmBar = kSmWt + kWBytes, kSmTotal = kSmBar + 64;
 constexpr uint32_t kTmemCols = 256;
 
-__device__ __forceinline__ void mlp_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMlpThreads) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void mlp_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 template <int N, int K>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem, uint32_t a_saddr, uint32_t b_saddr, uint32_t mma_bar) {
@@ -85,56 +90,61 @@ __device__ __forceinline__ void stage_wt(unsigned char* dst, const __half* __res
 	}
 }
 
-// forward epilogue: TMEM row -> (ReLU, mask bits) -> fp16 -> next operand tile + global scratch row
+// W (16 or 32) consecutive accumulator columns of this thread's row
+template <int W>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+	if (W == 32) tmem_ld32(taddr, v);
+	else tmem_ld16(taddr, v);
+}
+
+// forward epilogue: N_COLS columns of a TMEM row -> (ReLU, mask bits: one word per 32 columns) -> fp16 -> next operand tile (16-byte chunks from `chunk0`)
 template <int N_COLS, bool RELU>
-__device__ __forceinline__ void epi_fwd(uint32_t taddr, unsigned char* tile, uint32_t tile_chunk0, uint32_t row, uint32_t* mask, __half* grow, float* keep0) {
+__device__ __forceinline__ void epi_fwd(uint32_t taddr, unsigned char* tile, uint32_t chunk0, uint32_t row, uint32_t* mask, float* keep0) {
+	constexpr int W = N_COLS >= 32 ? 32 : 16;
 	unsigned char* dst = tile + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
-	for (int c0 = 0; c0 < N_COLS; c0 += 16) {
-		float v[16];
-		tmem_ld16(taddr + c0, v);
+	for (int c0 = 0; c0 < N_COLS; c0 += W) {
+		float v[W];
+		tmem_ld_cols<W>(taddr + c0, v);
 		if (RELU) {
 			uint32_t bits = 0;
 #pragma unroll
-			for (int k = 0; k < 16; ++k) {
+			for (int k = 0; k < W; ++k) {
 				bits |= (v[k] > 0.0f ? 1u : 0u) << k;
 				v[k] = fmaxf(v[k], 0.0f);
 			}
-			mask[c0 / 32] |= bits << (c0 % 32);
+			mask[c0 / 32] = bits;
 		}
-		const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-		const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-		*reinterpret_cast<uint4*>(dst + (tile_chunk0 + c0 / 8) * kChunkA) = lo;
-		*reinterpret_cast<uint4*>(dst + (tile_chunk0 + c0 / 8 + 1) * kChunkA) = hi;
-		if (grow) {
-			*reinterpret_cast<uint4*>(grow + c0) = lo;
-			*reinterpret_cast<uint4*>(grow + c0 + 8) = hi;
+#pragma unroll
+		for (int j = 0; j < W / 8; ++j) {
+			const uint4 q = make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]), pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+			*reinterpret_cast<uint4*>(dst + (chunk0 + c0 / 8 + j) * kChunkA) = q;
 		}
 		if (keep0 && c0 == 0) *keep0 = v[0];
 	}
 }
 
-// backward epilogue: TMEM row -> (mask) -> fp16 -> operand tile of the next data-gradient GEMM + global scratch row.
+// backward epilogue: TMEM row -> (mask) -> fp16 -> operand tile of the next data-gradient GEMM.
 // add0 is added to column 0 before rounding (the density gradient joining the colour MLP's input gradient).
 template <int N_COLS, bool MASK>
-__device__ __forceinline__ void epi_bwd(uint32_t taddr, unsigned char* tile, uint32_t row, const uint32_t* mask, __half* grow, float add0) {
+__device__ __forceinline__ void epi_bwd(uint32_t taddr, unsigned char* tile, uint32_t chunk0, uint32_t row, const uint32_t* mask, float add0) {
+	constexpr int W = N_COLS >= 32 ? 32 : 16;
 	unsigned char* dst = tile + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
-	for (int c0 = 0; c0 < N_COLS; c0 += 16) {
-		float v[16];
-		tmem_ld16(taddr + c0, v);
+	for (int c0 = 0; c0 < N_COLS; c0 += W) {
+		float v[W];
+		tmem_ld_cols<W>(taddr + c0, v);
 		if (MASK) {
-			const uint32_t bits = mask[c0 / 32] >> (c0 % 32);
+			const uint32_t bits = mask[c0 / 32];
 #pragma unroll
-			for (int k = 0; k < 16; ++k) v[k] = ((bits >> k) & 1u) ? v[k] : 0.0f;
+			for (int k = 0; k < W; ++k) v[k] = ((bits >> k) & 1u) ? v[k] : 0.0f;
 		}
 		if (c0 == 0) v[0] += add0;
-		const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-		const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-		*reinterpret_cast<uint4*>(dst + (c0 / 8) * kChunkA) = lo;
-		*reinterpret_cast<uint4*>(dst + (c0 / 8 + 1) * kChunkA) = hi;
-		*reinterpret_cast<uint4*>(grow + c0) = lo;
-		*reinterpret_cast<uint4*>(grow + c0 + 8) = hi;
+#pragma unroll
+		for (int j = 0; j < W / 8; ++j) {
+			const uint4 q = make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]), pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+			*reinterpret_cast<uint4*>(dst + (chunk0 + c0 / 8 + j) * kChunkA) = q;
+		}
 	}
 }
 
@@ -168,13 +178,15 @@ struct BwdArgs {
 	const __half* dloss;    // dloss_width halves per sample: d(r, g, b, sigma)
 	uint32_t dloss_width;
 	__half* out;            // nullable: forward output, 4 halves per sample
-	__half* xs;             // [n_pad][kXCols]
-	__half* dys;            // [n_pad][kDyCols]
-	__half* dfeat;          // [128][n_pad] SoA: dL/d(grid features)
+	__half* xs;             // [n_pad / 128][kXChunks][128][8]
+	__half* dys;            // [n_pad / 128][kDyChunks][128][8]
+	__half* dfeat;          // [n_pad / 128][16 levels][128][8]: dL/d(grid features)
 	GridLevels L;
 };
 
-__global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __grid_constant__ BwdArgs a) {
+template <int SPLIT>
+__global__ void __launch_bounds__((4 * SPLIT + kEncWarps) * 32, 1) net_fwd_bwd_kernel(const __grid_constant__ BwdArgs a) {
+	constexpr int kMlpWarps = 4 * SPLIT, kMlpThreads = kMlpWarps * 32;
 	extern __shared__ __align__(1024) unsigned char smem[];
 	const uint32_t sbase = smem_u32(smem);
 	const uint32_t bar_full0 = sbase + kSmBar, bar_empty0 = sbase + kSmBar + 16, bar_mma = sbase + kSmBar + 32;
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __gri
 	const uint32_t tmem_base = *tmem_slot;
 
 	if (warp >= kMlpWarps) {
-		// =================================== encoders (as in mlp.cu, plus the global copy of X0) ===================================
+		// =================================== encoders (as in mlp.cu; the MLP side sends the finished tile to the X scratch) ===================================
 		const uint32_t e = threadIdx.x - kMlpThreads;
 		const uint32_t row = e & (kTileM - 1), half_id = e >> 7;
 		const uint4* table = reinterpret_cast<const uint4*>(a.params + kOffGrid);
@@ -216,7 +228,6 @@ __global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __gri
 			mbar_wait(bar_empty0 + 8 * b, ((it >> 1) & 1u) ^ 1u);
 			unsigned char* A0 = smem + kSmA0 + b * kBytesA0 + (row >> 3) * 128 + (row & 7) * 16;
 			const uint32_t i = tile * kTileM + row;
-			__half* x0 = a.xs + (size_t)i * kXCols;  // i < n_pad always
 			if (i < a.n) {
 				const float* rec = a.records + (size_t)i * a.stride;
 				const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
@@ -232,7 +243,6 @@ __global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __gri
 					const uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&acc[0]), *reinterpret_cast<uint32_t*>(&acc[1]), *reinterpret_cast<uint32_t*>(&acc[2]),
 					                           *reinterpret_cast<uint32_t*>(&acc[3]));
 					*reinterpret_cast<uint4*>(A0 + level * kChunkA) = v;
-					*reinterpret_cast<uint4*>(x0 + level * 8) = v;
 				}
 				float ex[8];
 #pragma unroll
@@ -242,16 +252,13 @@ __global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __gri
 				}
 				const uint4 v = make_uint4(pack2(ex[0], ex[1]), pack2(ex[2], ex[3]), pack2(ex[4], ex[5]), pack2(ex[6], ex[7]));
 				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = v;
-				*reinterpret_cast<uint4*>(x0 + (16 + half_id) * 8) = v;
 			} else {
 				const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
 				for (uint32_t l = 0; l < 8; ++l) {
 					*reinterpret_cast<uint4*>(A0 + (half_id * 8 + l) * kChunkA) = z;
-					*reinterpret_cast<uint4*>(x0 + (half_id * 8 + l) * 8) = z;
 				}
 				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = z;
-				*reinterpret_cast<uint4*>(x0 + (16 + half_id) * 8) = z;
 			}
 			fence_proxy_async();
 			__syncwarp();
@@ -259,8 +266,11 @@ __global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __gri
 		}
 	} else {
 		// =================================== MLP warps: forward chain, then data-gradient chain ===================================
-		const uint32_t row = threadIdx.x;
-		const uint32_t taddr = tmem_base + ((warp * 32u) << 16);
+		// thread = (tile row, column part h): NC columns of every 64-wide layer from column cb on; the 16-wide layers belong to part 0
+		constexpr int NC = kWidth / SPLIT;
+		const uint32_t row = threadIdx.x & (kTileM - 1), h = threadIdx.x >> 7;
+		const uint32_t cb = h * NC;
+		const uint32_t taddr = tmem_base + (((warp & 3u) * 32u) << 16);
 		unsigned char* H0 = smem + kSmH;
 		unsigned char* H1 = smem + kSmH + kBytesH;
 		unsigned char* A3 = smem + kSmA3;
@@ -271,17 +281,22 @@ __global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __gri
 	mbar_wait(bar_mma, mma_phase);        \
 	mma_phase ^= 1u;                      \
 	tc_fence_after()
-#define TILE_READY()     \
-	fence_proxy_async(); \
-	tc_fence_before();   \
-	mlp_bar_sync();      \
+// the issuer's earlier bulk copies have read their tiles (each was issued a whole stage ago) before anybody may overwrite one
+#define TILE_READY()                   \
+	if (issuer) bulk_wait_read0();     \
+	fence_proxy_async();               \
+	tc_fence_before();                 \
+	mlp_bar_sync<kMlpThreads>();       \
 	tc_fence_after()
+// issuer only: `chunks` finished 16-byte-column chunks of a shared-memory tile -> the same chunks of this tile in a scratch matrix
+#define SEND(gbase, tile_chunks, chunk0, saddr, chunks)                                                                                             \
+	bulk_store((gbase) + ((size_t)tile * (tile_chunks) + (chunk0)) * kChunkHalves, (saddr), (chunks) * kChunkA);                                    \
+	bulk_commit()
 		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
 			const uint32_t b = it & 1u;
 			const uint32_t i = tile * kTileM + row;
 			const bool valid = i < a.n;
-			__half* xrow = a.xs + (size_t)i * kXCols;
-			__half* dyrow = a.dys + (size_t)i * kDyCols;
+			const uint32_t sA0 = sbase + kSmA0 + b * kBytesA0;
 			float dx = 0.5f, dy = 0.5f, dz = 0.5f;
 			float g_rgb[3] = {0.f, 0.f, 0.f}, g_sigma = 0.f;
 			if (valid) {
@@ -295,106 +310,145 @@ __global__ void __launch_bounds__(kNetThreads, 1) net_fwd_bwd_kernel(const __gri
 			// ---------------- forward ----------------
 			mbar_wait(bar_full0 + 8 * b, (it >> 1) & 1u);
 			tc_fence_after();
-			if (issuer) issue_gemm<kWidth, kInDensity>(tmem_base, sbase + kSmA0 + b * kBytesA0, sW + kOffW1 * 2, bar_mma);
-			{
+			if (issuer) {
+				issue_gemm<kWidth, kInDensity>(tmem_base, sA0, sW + kOffW1 * 2, bar_mma);
+				SEND(a.xs, kXChunks, 0, sA0, kInDensity / 8);  // X0: grid features + expression inputs, as the encoders wrote them
+			}
+			if (h == 0) {
 				uint4 lo, hi;
 				sh4(dx * 2.f - 1.f, dy * 2.f - 1.f, dz * 2.f - 1.f, lo, hi);
 				unsigned char* dst = A3 + (row >> 3) * 128 + (row & 7) * 16;
 				*reinterpret_cast<uint4*>(dst + 2 * kChunkA) = lo;
 				*reinterpret_cast<uint4*>(dst + 3 * kChunkA) = hi;
-				*reinterpret_cast<uint4*>(xrow + 272 + 16) = lo;
-				*reinterpret_cast<uint4*>(xrow + 272 + 24) = hi;
 			}
 			MMA_WAIT();
-			if (issuer) mbar_arrive(bar_empty0 + 8 * b);
-			epi_fwd<kWidth, true>(taddr, H0, 0, row, m1, xrow + 144, nullptr);
+			epi_fwd<NC, true>(taddr + cb, H0, cb / 8, row, m1, nullptr);
 			TILE_READY();
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sW + kOffW2 * 2, bar_mma);
+			if (issuer) {
+				if (it > 0) mbar_arrive(bar_empty0 + 8 * (b ^ 1u));
+				issue_gemm<kWidth, kWidth>(tmem_base, sH0, sW + kOffW2 * 2, bar_mma);
+				SEND(a.xs, kXChunks, 18, sH0, 8);
+			}
 			MMA_WAIT();
-			epi_fwd<kWidth, true>(taddr, H1, 0, row, m2, xrow + 208, nullptr);
+			epi_fwd<NC, true>(taddr + cb, H1, cb / 8, row, m2, nullptr);
 			TILE_READY();
-			if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH1, sW + kOffW3 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kOutPad, kWidth>(tmem_base, sH1, sW + kOffW3 * 2, bar_mma);
+				SEND(a.xs, kXChunks, 26, sH1, 8);
+			}
 			MMA_WAIT();
 			float sigma = 0.f;
-			epi_fwd<kOutPad, false>(taddr, A3, 0, row, nullptr, xrow + 272, &sigma);
+			if (h == 0) epi_fwd<kOutPad, false>(taddr, A3, 0, row, nullptr, &sigma);
 			TILE_READY();
-			if (issuer) issue_gemm<kWidth, kInRgb>(tmem_base, sA3, sW + kOffV1 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kInRgb>(tmem_base, sA3, sW + kOffV1 * 2, bar_mma);
+				SEND(a.xs, kXChunks, 34, sA3, 4);  // density network outputs + SH of the direction
+			}
 			MMA_WAIT();
-			epi_fwd<kWidth, true>(taddr, H0, 0, row, m4, xrow + 304, nullptr);
+			epi_fwd<NC, true>(taddr + cb, H0, cb / 8, row, m4, nullptr);
 			TILE_READY();
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sW + kOffV2 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kWidth>(tmem_base, sH0, sW + kOffV2 * 2, bar_mma);
+				SEND(a.xs, kXChunks, 38, sH0, 8);
+			}
 			MMA_WAIT();
-			epi_fwd<kWidth, true>(taddr, H1, 0, row, m5, xrow + 368, nullptr);
+			epi_fwd<NC, true>(taddr + cb, H1, cb / 8, row, m5, nullptr);
 			TILE_READY();
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH1, sW + kOffV3 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kWidth>(tmem_base, sH1, sW + kOffV3 * 2, bar_mma);
+				SEND(a.xs, kXChunks, 46, sH1, 8);
+			}
 			MMA_WAIT();
-			epi_fwd<kWidth, true>(taddr, H0, 0, row, m6, xrow + 432, nullptr);
+			epi_fwd<NC, true>(taddr + cb, H0, cb / 8, row, m6, nullptr);
 			TILE_READY();
+			if (issuer) { SEND(a.xs, kXChunks, 54, sH0, 8); }
 			if (a.out) {  // forward output, when the caller wants it
 				if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH0, sW + kOffV4 * 2, bar_mma);
 				MMA_WAIT();
-				float o[16];
-				tmem_ld16(taddr, o);
-				tc_fence_before();
-				if (valid) {
-					const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], __half2float(__float2half_rn(sigma)));
-					*reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
+				if (h == 0) {
+					float o[16];
+					tmem_ld16(taddr, o);
+					if (valid) {
+						const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], __half2float(__float2half_rn(sigma)));
+						*reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
+					}
 				}
-				mlp_bar_sync();
+				tc_fence_before();
+				mlp_bar_sync<kMlpThreads>();
 				tc_fence_after();
 			}
 			// ---------------- backward: data gradients ----------------
-			{
+			if (h == SPLIT - 1) {
 				// dOut (colour output layer): d(r, g, b) in columns 0-2, the rest 0
 				const uint4 lo = make_uint4(pack2(g_rgb[0], g_rgb[1]), pack2(g_rgb[2], 0.f), 0u, 0u), z = make_uint4(0, 0, 0, 0);
 				unsigned char* dst = H1 + (row >> 3) * 128 + (row & 7) * 16;
 				*reinterpret_cast<uint4*>(dst) = lo;
 				*reinterpret_cast<uint4*>(dst + kChunkA) = z;
-				*reinterpret_cast<uint4*>(dyrow + 336) = lo;
-				*reinterpret_cast<uint4*>(dyrow + 344) = z;
 			}
 			TILE_READY();
 			// dG3 = dOut V4  (K = 16)
-			if (issuer) issue_gemm<kWidth, kOutPad>(tmem_base, sH1, sWt + kOffV4 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kOutPad>(tmem_base, sH1, sWt + kOffV4 * 2, bar_mma);
+				SEND(a.dys, kDyChunks, 42, sH1, 2);
+			}
 			MMA_WAIT();
-			epi_bwd<kWidth, true>(taddr, H0, row, m6, dyrow + 272, 0.f);
+			epi_bwd<NC, true>(taddr + cb, H0, cb / 8, row, m6, 0.f);
 			TILE_READY();
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sWt + kOffV3 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kWidth>(tmem_base, sH0, sWt + kOffV3 * 2, bar_mma);
+				SEND(a.dys, kDyChunks, 34, sH0, 8);
+			}
 			MMA_WAIT();
-			epi_bwd<kWidth, true>(taddr, H1, row, m5, dyrow + 208, 0.f);
+			epi_bwd<NC, true>(taddr + cb, H1, cb / 8, row, m5, 0.f);
 			TILE_READY();
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH1, sWt + kOffV2 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kWidth>(tmem_base, sH1, sWt + kOffV2 * 2, bar_mma);
+				SEND(a.dys, kDyChunks, 26, sH1, 8);
+			}
 			MMA_WAIT();
-			epi_bwd<kWidth, true>(taddr, H0, row, m4, dyrow + 144, 0.f);
+			epi_bwd<NC, true>(taddr + cb, H0, cb / 8, row, m4, 0.f);
 			TILE_READY();
 			// d(colour MLP input) = dG1 V1: columns 0-15 are the density network's outputs (+ d sigma on column 0), 16-31 the SH
-			if (issuer) issue_gemm<kInRgb, kWidth>(tmem_base, sH0, sWt + kOffV1 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kInRgb, kWidth>(tmem_base, sH0, sWt + kOffV1 * 2, bar_mma);
+				SEND(a.dys, kDyChunks, 18, sH0, 8);
+			}
 			MMA_WAIT();
-			epi_bwd<kOutPad, false>(taddr, H1, row, nullptr, dyrow + 128, g_sigma);
+			if (h == 0) epi_bwd<kOutPad, false>(taddr, H1, 0, row, nullptr, g_sigma);
 			TILE_READY();
 			// dH2 = dD W3 (K = 16)
-			if (issuer) issue_gemm<kWidth, kOutPad>(tmem_base, sH1, sWt + kOffW3 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kOutPad>(tmem_base, sH1, sWt + kOffW3 * 2, bar_mma);
+				SEND(a.dys, kDyChunks, 16, sH1, 2);
+			}
 			MMA_WAIT();
-			epi_bwd<kWidth, true>(taddr, H0, row, m2, dyrow + 64, 0.f);
+			epi_bwd<NC, true>(taddr + cb, H0, cb / 8, row, m2, 0.f);
 			TILE_READY();
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sWt + kOffW2 * 2, bar_mma);
+			if (issuer) {
+				issue_gemm<kWidth, kWidth>(tmem_base, sH0, sWt + kOffW2 * 2, bar_mma);
+				SEND(a.dys, kDyChunks, 8, sH0, 8);
+			}
 			MMA_WAIT();
-			epi_bwd<kWidth, true>(taddr, H1, row, m1, dyrow + 0, 0.f);
+			epi_bwd<NC, true>(taddr + cb, H1, cb / 8, row, m1, 0.f);
 			TILE_READY();
 			// dX0 = dH1 W1: 144 columns; the first 128 are the grid features
-			if (issuer) issue_gemm<kInDensity, kWidth>(tmem_base, sH1, sWt + kOffW1 * 2, bar_mma);
-			MMA_WAIT();
-#pragma unroll 1
-			for (int c0 = 0; c0 < 128; c0 += 16) {
-				float v[16];
-				tmem_ld16(taddr + c0, v);
-#pragma unroll
-				for (int k = 0; k < 16; ++k) a.dfeat[(size_t)(c0 + k) * a.n_pad + i] = __float2half_rn(v[k]);
+			if (issuer) {
+				issue_gemm<kInDensity, kWidth>(tmem_base, sH1, sWt + kOffW1 * 2, bar_mma);
+				SEND(a.dys, kDyChunks, 0, sH1, 8);
 			}
-			tc_fence_before();
-			mlp_bar_sync();
-			tc_fence_after();
+			MMA_WAIT();
+			// staged in this tile's A0 buffer (its GEMM and its bulk copy are long done; the encoders get the buffer back only after this)
+			{
+				unsigned char* T = smem + kSmA0 + b * kBytesA0;
+#pragma unroll
+				for (int part = 0; part < 2 / SPLIT; ++part) epi_bwd<64, false>(taddr + 64 * (h + part), T, 8 * (h + part), row, nullptr, 0.f);
+			}
+			TILE_READY();
+			// the encoders get this buffer back behind the next tile's first barrier, where the issuer has waited for this copy (they are a tile ahead anyway)
+			if (issuer) { SEND(a.dfeat, kFeatChunks, 0, sA0, kFeatChunks); }
 		}
+		if (issuer) bulk_wait0();
+#undef SEND
 #undef MMA_WAIT
 #undef TILE_READY
 	}
@@ -411,7 +465,8 @@ constexpr uint32_t kWgSbo = (kWgK / 8) * 128 + 16;     // 528: stride between 8-
 constexpr uint32_t kWgXGroups = kXCols / 8, kWgDyGroups = kDyCols / 8;
 constexpr uint32_t kWgXBytes = kWgXGroups * kWgSbo, kWgDyBytes = (kWgDyGroups + 16) * kWgSbo;  // + 16 groups the M = 128 descriptor may touch
 constexpr uint32_t kWgStage = kWgXBytes + kWgDyBytes;
-constexpr uint32_t kWgBar = 2 * kWgStage, kWgSmTotal = kWgBar + 64;
+constexpr uint32_t kWgStages = 3;                      // blocks of kWgK samples in shared memory: two of them being copied while the MMAs read the third
+constexpr uint32_t kWgBar = kWgStages * kWgStage, kWgSmTotal = kWgBar + 64;
 constexpr uint32_t kWgTmemCols = 512;
 __constant__ const uint32_t c_wgcol[7] = {0, 144, 208, 272, 304, 368, 432};  // accumulator column of layer l (= c_xoff)
 
@@ -427,17 +482,16 @@ struct WgArgs {
 __global__ void __launch_bounds__(kWgThreads, 1) net_wgrad_kernel(const WgArgs a) {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	const uint32_t sbase = smem_u32(smem);
-	const uint32_t bar_free0 = sbase + kWgBar, bar_done = sbase + kWgBar + 16;
-	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWgBar + 24);
+	const uint32_t bar_free0 = sbase + kWgBar, bar_done = bar_free0 + 8 * kWgStages;  // one mbarrier per stage, then the final one
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kWgBar + 8 * kWgStages + 8);
 	const uint32_t warp = threadIdx.x >> 5;
 	if (threadIdx.x == 0) {
-		mbar_init(bar_free0, 1);
-		mbar_init(bar_free0 + 8, 1);
+		for (uint32_t st = 0; st < kWgStages; ++st) mbar_init(bar_free0 + 8 * st, 1);
 		mbar_init(bar_done, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	// the padding groups behind the dY tiles are read by the M = 128 descriptors: keep them finite
-	for (uint32_t t = threadIdx.x; t < 2 * kWgStage / 16; t += blockDim.x) reinterpret_cast<uint4*>(smem)[t] = make_uint4(0, 0, 0, 0);
+	for (uint32_t t = threadIdx.x; t < kWgStages * kWgStage / 16; t += blockDim.x) reinterpret_cast<uint4*>(smem)[t] = make_uint4(0, 0, 0, 0);
 	if (warp == 0) {
 		__syncwarp();
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kWgTmemCols) : "memory");
@@ -450,27 +504,38 @@ __global__ void __launch_bounds__(kWgThreads, 1) net_wgrad_kernel(const WgArgs a
 	const uint32_t tmem_base = *tmem_slot;
 
 	const uint32_t n_blocks = a.n_pad / kWgK;
+	// copies of block `blk` (kWgK samples of X and dY) into stage st; chunk (sample k, feature group g): 16 bytes of the row-major scratch -> MN-major unit.
+	// Always closes a cp.async group, also past the last block, so that "all but the newest group" means the same thing in every iteration
+	auto request = [&](uint32_t blk, uint32_t st) {
+		if (blk < n_blocks) {
+			const uint32_t sx = sbase + st * kWgStage, sdy = sx + kWgXBytes;
+			// scratch layout [tile][chunk g][row][8 halves]: the kWgK rows of a chunk are 512 contiguous bytes on both sides
+			const uint32_t tile = blk / (kTileM / kWgK), r0 = (blk % (kTileM / kWgK)) * kWgK;
+			const __half* xsrc = a.xs + (size_t)tile * kXChunks * kChunkHalves + r0 * 8;
+			const __half* dysrc = a.dys + (size_t)tile * kDyChunks * kChunkHalves + r0 * 8;
+			for (uint32_t t = threadIdx.x; t < kWgK * kWgXGroups; t += blockDim.x) {
+				const uint32_t g = t / kWgK, k = t % kWgK;
+				cp_async16(sx + g * kWgSbo + k * 16, xsrc + (size_t)g * kChunkHalves + k * 8);
+			}
+			for (uint32_t t = threadIdx.x; t < kWgK * kWgDyGroups; t += blockDim.x) {
+				const uint32_t g = t / kWgK, k = t % kWgK;
+				cp_async16(sdy + g * kWgSbo + k * 16, dysrc + (size_t)g * kChunkHalves + k * 8);
+			}
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	request(blockIdx.x, 0);
+	request(blockIdx.x + gridDim.x, 1);
 	uint32_t it = 0;
 	for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
-		const uint32_t s = it & 1u;
-		mbar_wait(bar_free0 + 8 * s, ((it >> 1) & 1u) ^ 1u);  // the MMAs that read this stage two iterations ago are done
-		const uint32_t sx = sbase + s * kWgStage, sdy = sx + kWgXBytes;
-		const size_t row0 = (size_t)blk * kWgK;
-		// chunk (sample k, feature group g): 16 bytes of the row-major scratch -> MN-major unit
-		for (uint32_t t = threadIdx.x; t < kWgK * kWgXGroups; t += blockDim.x) {
-			const uint32_t k = t / kWgXGroups, g = t - k * kWgXGroups;
-			cp_async16(sx + g * kWgSbo + (k >> 3) * 128 + (k & 7) * 16, a.xs + (row0 + k) * kXCols + g * 8);
-		}
-		for (uint32_t t = threadIdx.x; t < kWgK * kWgDyGroups; t += blockDim.x) {
-			const uint32_t k = t / kWgDyGroups, g = t - k * kWgDyGroups;
-			cp_async16(sdy + g * kWgSbo + (k >> 3) * 128 + (k & 7) * 16, a.dys + (row0 + k) * kDyCols + g * 8);
-		}
-		asm volatile("cp.async.wait_all;" ::: "memory");
+		const uint32_t st = it % kWgStages;
+		asm volatile("cp.async.wait_group 1;" ::: "memory");  // this block's copies have landed (the next block's may still be in flight)
 		fence_proxy_async();
 		tc_fence_before();
 		__syncthreads();
 		tc_fence_after();
 		if (threadIdx.x == 0) {
+			const uint32_t sx = sbase + st * kWgStage, sdy = sx + kWgXBytes;
 #pragma unroll
 			for (int l = 0; l < 7; ++l) {
 				const uint32_t idesc = umma_idesc(128, c_kin[l], 1, 1);
@@ -481,8 +546,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) net_wgrad_kernel(const WgArgs a
 					umma_f16(tmem_base + c_wgcol[l], ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
 				}
 			}
-			umma_commit(bar_free0 + 8 * s);
+			umma_commit(bar_free0 + 8 * st);
 		}
+		// the block after next goes where the PREVIOUS block was: its MMAs were issued an iteration ago
+		const uint32_t nst = (it + 2) % kWgStages;
+		if (it > 0) mbar_wait(bar_free0 + 8 * nst, ((it - 1) / kWgStages) & 1u);
+		request(blk + 2 * gridDim.x, nst);
 	}
 	// all MMAs done -> epilogue
 	if (threadIdx.x == 0) umma_commit(bar_done);
@@ -572,11 +641,17 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 	a.dys = sc->dys;
 	a.dfeat = sc->dfeat;
 	a.L = ctx->levels;
-	// rows [n, n_pad) of the dY scratch are read by the weight-gradient kernel: they must be zero
-	if (n_pad > n) INSTA_CUDA(cudaMemsetAsync(sc->dys + (size_t)n * kDyCols, 0, (size_t)(n_pad - n) * kDyCols * 2, s));
-	INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+	// rows [n, n_pad) of the scratch matrices are read by the weight-gradient kernel: the kernel writes every row of every tile, and a row without a sample
+	// (zero inputs, zero loss gradient) is all zeros in X and dY
 	const uint32_t n_tiles = n_pad / kTileM;
-	net_fwd_bwd_kernel<<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), kNetThreads, kSmTotal, s>>>(a);
+	static const bool split1 = [] { const char* e = getenv("INSTA_NET_BWD_SPLIT"); return e && atoi(e) == 1; }();  // A/B: four MLP warps, a whole row per thread (round 1)
+	if (split1) {
+		INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+		net_fwd_bwd_kernel<1><<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), (4 + kEncWarps) * 32, kSmTotal, s>>>(a);
+	} else {
+		INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+		net_fwd_bwd_kernel<kSplit><<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), (4 * kSplit + kEncWarps) * 32, kSmTotal, s>>>(a);
+	}
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	const uint64_t n_grid = (uint64_t)ctx->levels.offset[ctx->levels.n_levels] * 8u;
@@ -592,7 +667,7 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 			uint32_t le = lb + 1;
 			while (le < L.n_levels && (g + 1 == n_groups || (uint64_t)L.offset[le] * n_groups < (uint64_t)L.offset[L.n_levels] * (g + 1))) ++le;
 			if (g + 1 == n_groups) le = L.n_levels;
-			int rc = launch_hash_bwd_levels(ctx, d_records, stride, n, sc->dfeat, n_pad, (__half*)d_grads + kOffGrid, 1, lb, le, s);
+			int rc = launch_hash_bwd_levels(ctx, d_records, stride, n, sc->dfeat, 0 /* tiled */, (__half*)d_grads + kOffGrid, 1, lb, le, s);
 			if (rc) return rc;
 			INSTA_CUDA(cudaEventRecord(ex->ev_grid_ready[g], s));
 			INSTA_CUDA(cudaStreamWaitEvent(ex->side, ex->ev_grid_ready[g], 0));
@@ -623,7 +698,7 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 		return INSTA_OK;
 	}
 	// grid gradients: kernel_grid_backward on the SoA dL/d(features)
-	return launch_hash_bwd_pitched(ctx, d_records, stride, n, sc->dfeat, n_pad, (__half*)d_grads + kOffGrid, 1, s);
+	return launch_hash_bwd_pitched(ctx, d_records, stride, n, sc->dfeat, 0 /* tiled */, (__half*)d_grads + kOffGrid, 1, s);
 }
 
 }  // namespace insta

@@ -20,6 +20,7 @@
 #include <float.h>
 
 #include <algorithm>
+#include <cstring>
 #include <cmath>
 
 #include "ctx.h"
@@ -144,10 +145,13 @@ struct RenderSched {
 
 // one thread: closes iteration k - 1 (survivor count -> n_alive) and sets up iteration k
 __global__ void render_schedule_kernel(RenderSched* __restrict__ sc, const uint32_t* __restrict__ n_survivors, uint32_t* __restrict__ counter_to_zero, uint32_t budget,
-                                       uint32_t max_steps, int first) {
+                                       uint32_t max_steps, int first, uint32_t tail_budget, uint32_t tail_max_steps) {
 	const uint32_t n = *n_survivors;
 	const uint32_t prev_steps = first ? 0u : sc->n_steps;
-	const uint32_t ns = n ? min(max(budget / n, 1u), max_steps) : 0u;
+	uint32_t ns = n ? min(max(budget / n, 1u), max_steps) : 0u;
+	// the tail of a frame: few rays left -- let them march further, so that the last iterations (each a full chain of launches for a few ten thousand records)
+	// collapse into one
+	if (n && n * ns < tail_budget) ns = min(max(tail_budget / n, ns), max(tail_max_steps, ns));
 	sc->step = first ? 1u : sc->step + prev_steps;
 	sc->n_alive = n;
 	sc->n_steps = ns;
@@ -493,6 +497,11 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 	// (512^2, B200: 9.55 ms per frame with the reference's schedule, 7.00 with 16 steps, 7.24 with 32, 7.76 with 64 -- profiles/r1_render_schedule.txt).
 	const uint32_t max_steps = opts && opts->max_steps_per_iteration ? std::min(opts->max_steps_per_iteration, 0xffffu) : 16u;
 	const uint32_t budget = max_steps <= 8u ? n_pix : std::max(n_pix, 1u << 21);
+	// library default only: an iteration that would carry fewer than 2^tail records marches up to tail_steps steps instead (INSTA_RENDER_TAIL="log2 records,steps", "0,0" = off)
+	static const uint32_t tail_log2 = [] { const char* e = getenv("INSTA_RENDER_TAIL"); return e ? (uint32_t)atoi(e) : 19u; }();
+	static const uint32_t tail_steps_env = [] { const char* e = getenv("INSTA_RENDER_TAIL"); const char* c = e ? strchr(e, ',') : nullptr; return c ? (uint32_t)atoi(c + 1) : 64u; }();
+	const bool tail_on = !(opts && opts->max_steps_per_iteration) && tail_log2 > 0 && tail_log2 < 31;
+	const uint32_t tail_budget = tail_on ? std::min(1u << tail_log2, budget) : 0u, tail_steps = tail_on ? tail_steps_env : 0u;
 	if (budget > t->scratch_cap || stride != t->scratch_stride) {
 		INSTA_CUDA(cudaDeviceSynchronize());
 		if (t->d_records) cudaFree(t->d_records);
@@ -531,7 +540,7 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 	while (true) {
 		for (uint32_t g = 0; g < group; ++g, ++enqueued) {
 			uint32_t* cnt_next = t->d_counters + 1 + (cur ^ 1u);
-			render_schedule_kernel<<<1, 1, 0, s>>>(t->d_sched, first ? t->d_counters : t->d_counters + 1 + cur, cnt_next, budget, max_steps, first ? 1 : 0);
+			render_schedule_kernel<<<1, 1, 0, s>>>(t->d_sched, first ? t->d_counters : t->d_counters + 1 + cur, cnt_next, budget, max_steps, first ? 1 : 0, tail_budget, tail_steps);
 			nerf_march_kernel<<<ray_blocks, 128, march_smem, s>>>(t->args, t->set[cur], 0, t->d_records, stride, 0, (float)frame_id, extra, stride - 11, t->d_sched);
 			ctx->launches += 2;
 			INSTA_CUDA(cudaGetLastError());

@@ -61,6 +61,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 	for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
 }
 
+// 32 lanes x 32 bit, 32 consecutive columns per thread: one round trip to tensor memory instead of two
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+	uint32_t r[32];
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+	      "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+	      "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+	    : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// TMA bulk copy shared -> global (contiguous, 16-byte granularity), tracked by the issuing thread's bulk groups.  The shared-memory source must have been
+// made visible to the async proxy (fence_proxy_async by the writers + a barrier) and must stay untouched until bulk_wait_read0() returns.
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t saddr, uint32_t bytes) {
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
 	const __half2 h = __floats2half2_rn(a, b);
 	return *reinterpret_cast<const uint32_t*>(&h);
