@@ -458,6 +458,303 @@ __global__ void __launch_bounds__((4 * SPLIT + kEncWarps) * 32, 1) net_fwd_bwd_k
 }
 
 // ======================================================================================================================
+// The same chain with the activations kept in TENSOR MEMORY between the GEMMs (default; net_fwd_bwd_kernel above = INSTA_NET_BWD=ss).
+// With the operand tiles in shared memory every epilogue ends in fence.proxy.async (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) before the barrier, and the MLP warps
+// spent 40 % of their time there even with no global store outstanding (profiles/r2_net_fwd_bwd_bulk_ncu_summary.txt) -- the fence queues behind the encoder
+// warps' gathers.  Here an epilogue packs its fp16 pairs and writes them with tcgen05.st into the columns the next GEMM reads as its A operand (".ts" form:
+// row in lane, two K elements per 32-bit column), so a stage is tcgen05.ld -> ALU -> tcgen05.st -> wait::st -> barrier: no shared-memory tile, no proxy fence.
+// The same registers go to the scratch matrices with 16-byte stores that are contiguous across a warp in the tile layout (row = lane) and that nobody waits
+// for.  Only the first GEMM of a tile takes A from shared memory (the encoders' tile), which also leaves for the X scratch by one bulk copy.
+constexpr uint32_t kTsSmW = 2 * kBytesA0, kTsSmWt = kTsSmW + kWBytes, kTsSmBar = kTsSmWt + kWBytes, kTsSmTotal = kTsSmBar + 64;
+// tensor-memory columns of the A operands: hidden activations / their gradients (K = 64: 32 columns), colour-MLP input (K = 32: 16), 16-wide gradients (K = 16: 8)
+constexpr uint32_t kColH = 160, kColA3 = 192, kColS = 208;
+
+template <int N, int K>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_saddr, uint32_t mma_bar) {
+	constexpr uint32_t idesc = umma_idesc(kTileM, N);
+#pragma unroll
+	for (int j = 0; j < K / 16; ++j) {
+		const uint64_t bd = umma_desc(b_saddr + j * 2 * (N * 16), N * 16, 128);
+		umma_f16_ts(tmem_d, tmem_a + j * 8, bd, idesc, j > 0 ? 1u : 0u);
+	}
+	umma_commit(mma_bar);
+}
+
+// N_COLS (16 or 32) accumulator columns of this thread's row -> MODE 1: ReLU, mask bits recorded / MODE 2: mask applied / MODE 0: as is -> fp16 pairs ->
+// the A-operand columns at taddr_a + one 16-byte chunk per 8 columns of the scratch tile at g (this row's slot of the first chunk)
+template <int N_COLS, int MODE>
+__device__ __forceinline__ void epi_ts(uint32_t taddr_d, uint32_t taddr_a, uint32_t& mask, __half* g, float add0, float* keep0) {
+	float v[N_COLS];
+	tmem_ld_cols<N_COLS>(taddr_d, v);
+	if (MODE == 1) {
+		uint32_t bits = 0;
+#pragma unroll
+		for (int k = 0; k < N_COLS; ++k) {
+			bits |= (v[k] > 0.0f ? 1u : 0u) << k;
+			v[k] = fmaxf(v[k], 0.0f);
+		}
+		mask = bits;
+	}
+	if (MODE == 2) {
+#pragma unroll
+		for (int k = 0; k < N_COLS; ++k) v[k] = ((mask >> k) & 1u) ? v[k] : 0.0f;
+	}
+	v[0] += add0;
+	if (keep0) *keep0 = v[0];
+	uint32_t p[N_COLS / 2];
+#pragma unroll
+	for (int k = 0; k < N_COLS / 2; ++k) p[k] = pack2(v[2 * k], v[2 * k + 1]);
+	if (N_COLS == 32) tmem_st16(taddr_a, p);
+	else tmem_st8(taddr_a, p);
+#pragma unroll
+	for (int j = 0; j < N_COLS / 8; ++j) *reinterpret_cast<uint4*>(g + (size_t)j * kChunkHalves) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__((4 * SPLIT + kEncWarps) * 32, 1) net_fwd_bwd_ts_kernel(const __grid_constant__ BwdArgs a) {
+	constexpr int kMlpWarps = 4 * SPLIT, kMlpThreads = kMlpWarps * 32;
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const uint32_t sbase = smem_u32(smem);
+	const uint32_t bar_full0 = sbase + kTsSmBar, bar_empty0 = sbase + kTsSmBar + 16, bar_mma = sbase + kTsSmBar + 32;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kTsSmBar + 40);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t n_tiles = (a.n + kTileM - 1) / kTileM;
+
+	for (int l = 0; l < 7; ++l) {
+		stage_w(smem + kTsSmW + c_woff[l] * 2, a.params + c_woff[l], (int)c_nout[l], (int)c_kin[l]);
+		stage_wt(smem + kTsSmWt + c_woff[l] * 2, a.params + c_woff[l], (int)c_nout[l], (int)c_kin[l]);
+	}
+	if (threadIdx.x == 0) {
+		mbar_init(bar_full0, kEncWarps);
+		mbar_init(bar_full0 + 8, kEncWarps);
+		mbar_init(bar_empty0, 1);
+		mbar_init(bar_empty0 + 8, 1);
+		mbar_init(bar_mma, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 0) {
+		__syncwarp();
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	fence_proxy_async();
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp >= kMlpWarps) {
+		// =================================== encoders: the tile of grid features + expression inputs, as in mlp.cu ===================================
+		const uint32_t e = threadIdx.x - kMlpThreads;
+		const uint32_t row = e & (kTileM - 1), half_id = e >> 7;
+		const uint4* table = reinterpret_cast<const uint4*>(a.params + kOffGrid);
+		uint32_t it = 0;
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+			const uint32_t b = it & 1u;
+			mbar_wait(bar_empty0 + 8 * b, ((it >> 1) & 1u) ^ 1u);
+			unsigned char* A0 = smem + b * kBytesA0 + (row >> 3) * 128 + (row & 7) * 16;
+			const uint32_t i = tile * kTileM + row;
+			if (i < a.n) {
+				const float* rec = a.records + (size_t)i * a.stride;
+				const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
+#pragma unroll 2
+				for (uint32_t l = 0; l < 8; ++l) {
+					const uint32_t level = half_id * 8 + l;
+					__half2 acc[4] = {__half2(), __half2(), __half2(), __half2()};
+					if (level < a.L.n_levels) {
+						const Corner c = pos_fract3(px, py, pz, a.L.scale[level]);
+						if (a.L.hashed[level]) encode_one<true>(table + a.L.offset[level], c, a.L.size[level], 0, 0, acc);
+						else encode_one<false>(table + a.L.offset[level], c, a.L.size[level], a.L.mul1[level], a.L.mul2[level], acc);
+					}
+					*reinterpret_cast<uint4*>(A0 + level * kChunkA) = make_uint4(*reinterpret_cast<uint32_t*>(&acc[0]), *reinterpret_cast<uint32_t*>(&acc[1]),
+					                                                            *reinterpret_cast<uint32_t*>(&acc[2]), *reinterpret_cast<uint32_t*>(&acc[3]));
+				}
+				float ex[8];
+#pragma unroll
+				for (uint32_t k = 0; k < 8; ++k) {
+					const uint32_t d = half_id * 8 + k;
+					ex[k] = d < a.n_extra ? __ldg(rec + a.stride - a.n_extra + d) : 0.0f;
+				}
+				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = make_uint4(pack2(ex[0], ex[1]), pack2(ex[2], ex[3]), pack2(ex[4], ex[5]), pack2(ex[6], ex[7]));
+			} else {
+				const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+				for (uint32_t l = 0; l < 8; ++l) *reinterpret_cast<uint4*>(A0 + (half_id * 8 + l) * kChunkA) = z;
+				*reinterpret_cast<uint4*>(A0 + (16 + half_id) * kChunkA) = z;
+			}
+			fence_proxy_async();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_full0 + 8 * b);
+		}
+	} else {
+		// =================================== MLP warps ===================================
+		// thread = (tile row, column part h): NC columns of every 64-wide layer from column cb on; the 16-wide layers belong to part 0
+		constexpr int NC = kWidth / SPLIT, NP = NC / 32;  // columns per thread, in NP pieces of 32 (one mask word each)
+		const uint32_t row = threadIdx.x & (kTileM - 1), h = threadIdx.x >> 7;
+		const uint32_t cb = h * NC;
+		const uint32_t tlane = tmem_base + (((warp & 3u) * 32u) << 16);  // this warp's 32 lanes (tile rows), column 0
+		const uint32_t sW = sbase + kTsSmW, sWt = sbase + kTsSmWt;
+		const uint32_t tH = tmem_base + kColH, tA3 = tmem_base + kColA3, tS = tmem_base + kColS;
+		uint32_t mma_phase = 0, it = 0;
+		const bool issuer = threadIdx.x == 0;
+#define MMA_WAIT()                        \
+	mbar_wait(bar_mma, mma_phase);        \
+	mma_phase ^= 1u;                      \
+	tc_fence_after()
+// what the epilogue stored into tensor memory is complete before anybody -- the issuer's next GEMM -- may read it
+#define STAGE_DONE()             \
+	tmem_st_wait();              \
+	tc_fence_before();           \
+	mlp_bar_sync<kMlpThreads>(); \
+	tc_fence_after()
+// a 64-wide layer: this thread's NC columns -> A-operand columns kColH.. + scratch chunks from `chunk0` of matrix g
+#define HIDDEN(MODE, m, g, chunk0)                                                                                                                 \
+	_Pragma("unroll") for (int part = 0; part < NP; ++part)                                                                                         \
+	    epi_ts<32, MODE>(tlane + cb + 32 * part, tlane + kColH + (cb + 32 * part) / 2, m[part], (g) + (size_t)((chunk0) + (cb + 32 * part) / 8) * kChunkHalves, 0.f, nullptr)
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+			const uint32_t b = it & 1u;
+			const uint32_t i = tile * kTileM + row;
+			const bool valid = i < a.n;
+			const uint32_t sA0 = sbase + b * kBytesA0;
+			__half* xs_t = a.xs + (size_t)tile * kXChunks * kChunkHalves + row * 8;
+			__half* dys_t = a.dys + (size_t)tile * kDyChunks * kChunkHalves + row * 8;
+			float dx = 0.5f, dy = 0.5f, dz = 0.5f;
+			float g_rgb[3] = {0.f, 0.f, 0.f}, g_sigma = 0.f;
+			if (valid) {
+				const float* rec = a.records + (size_t)i * a.stride;
+				dx = __ldg(rec + 8); dy = __ldg(rec + 9); dz = __ldg(rec + 10);
+				const uint2 raw = *reinterpret_cast<const uint2*>(a.dloss + (size_t)i * a.dloss_width);
+				const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+				g_rgb[0] = lo.x; g_rgb[1] = lo.y; g_rgb[2] = hi.x; g_sigma = hi.y;
+			}
+			uint32_t m1[2] = {0, 0}, m2[2] = {0, 0}, m4[2] = {0, 0}, m5[2] = {0, 0}, m6[2] = {0, 0}, no_mask = 0;
+			// ---------------- forward ----------------
+			mbar_wait(bar_full0 + 8 * b, (it >> 1) & 1u);
+			tc_fence_after();
+			if (issuer) {
+				issue_gemm<kWidth, kInDensity>(tmem_base, sA0, sW + kOffW1 * 2, bar_mma);
+				bulk_store(a.xs + (size_t)tile * kXChunks * kChunkHalves, sA0, kBytesA0);  // X0: grid features + expression inputs, as the encoders wrote them
+				bulk_commit();
+			}
+			if (h == 0) {
+				// SH of the direction: the second half of the colour MLP's input
+				uint4 lo, hi;
+				sh4(dx * 2.f - 1.f, dy * 2.f - 1.f, dz * 2.f - 1.f, lo, hi);
+				const uint32_t p[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+				tmem_st8(tlane + kColA3 + 8, p);
+				*reinterpret_cast<uint4*>(xs_t + (size_t)36 * kChunkHalves) = lo;
+				*reinterpret_cast<uint4*>(xs_t + (size_t)37 * kChunkHalves) = hi;
+			}
+			MMA_WAIT();
+			HIDDEN(1, m1, xs_t, 18);
+			STAGE_DONE();
+			if (issuer) {
+				// the first GEMM and the bulk copy have read the encoders' tile
+				bulk_wait_read0();
+				mbar_arrive(bar_empty0 + 8 * b);
+				issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sW + kOffW2 * 2, bar_mma);
+			}
+			MMA_WAIT();
+			HIDDEN(1, m2, xs_t, 26);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kOutPad, kWidth>(tmem_base, tH, sW + kOffW3 * 2, bar_mma);
+			MMA_WAIT();
+			float sigma = 0.f;
+			if (h == 0) epi_ts<kOutPad, 0>(tlane, tlane + kColA3, no_mask, xs_t + (size_t)34 * kChunkHalves, 0.f, &sigma);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kInRgb>(tmem_base, tA3, sW + kOffV1 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(1, m4, xs_t, 38);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sW + kOffV2 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(1, m5, xs_t, 46);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sW + kOffV3 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(1, m6, xs_t, 54);
+			STAGE_DONE();
+			if (a.out) {  // forward output, when the caller wants it
+				if (issuer) issue_gemm_ts<kOutPad, kWidth>(tmem_base, tH, sW + kOffV4 * 2, bar_mma);
+				MMA_WAIT();
+				if (h == 0) {
+					float o[16];
+					tmem_ld16(tlane, o);
+					if (valid) {
+						const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], __half2float(__float2half_rn(sigma)));
+						*reinterpret_cast<uint2*>(a.out + (size_t)i * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
+					}
+				}
+				tc_fence_before();
+				mlp_bar_sync<kMlpThreads>();
+				tc_fence_after();
+			}
+			// ---------------- backward: data gradients ----------------
+			if (h == SPLIT - 1) {
+				// dOut (colour output layer): d(r, g, b) in columns 0-2, the rest 0
+				const uint32_t p[8] = {pack2(g_rgb[0], g_rgb[1]), pack2(g_rgb[2], 0.f), 0u, 0u, 0u, 0u, 0u, 0u};
+				tmem_st8(tlane + kColS, p);
+				*reinterpret_cast<uint4*>(dys_t + (size_t)42 * kChunkHalves) = make_uint4(p[0], p[1], 0u, 0u);
+				*reinterpret_cast<uint4*>(dys_t + (size_t)43 * kChunkHalves) = make_uint4(0u, 0u, 0u, 0u);
+			}
+			STAGE_DONE();
+			// dG3 = dOut V4  (K = 16)
+			if (issuer) issue_gemm_ts<kWidth, kOutPad>(tmem_base, tS, sWt + kOffV4 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(2, m6, dys_t, 34);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sWt + kOffV3 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(2, m5, dys_t, 26);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sWt + kOffV2 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(2, m4, dys_t, 18);
+			STAGE_DONE();
+			// d(colour MLP input) = dG1 V1: columns 0-15 are the density network's outputs (+ d sigma on column 0), 16-31 the SH
+			if (issuer) issue_gemm_ts<kInRgb, kWidth>(tmem_base, tH, sWt + kOffV1 * 2, bar_mma);
+			MMA_WAIT();
+			if (h == 0) epi_ts<kOutPad, 0>(tlane, tlane + kColS, no_mask, dys_t + (size_t)16 * kChunkHalves, g_sigma, nullptr);
+			STAGE_DONE();
+			// dH2 = dD W3 (K = 16)
+			if (issuer) issue_gemm_ts<kWidth, kOutPad>(tmem_base, tS, sWt + kOffW3 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(2, m2, dys_t, 8);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sWt + kOffW2 * 2, bar_mma);
+			MMA_WAIT();
+			HIDDEN(2, m1, dys_t, 0);
+			STAGE_DONE();
+			// dX0 = dH1 W1: 144 columns; the first 128 are the grid features -> [tile][level][row][8 features], what hash_bwd_pairs_kernel<true> reads
+			if (issuer) issue_gemm_ts<kInDensity, kWidth>(tmem_base, tH, sWt + kOffW1 * 2, bar_mma);
+			MMA_WAIT();
+			{
+				__half* df_t = a.dfeat + (size_t)tile * kFeatChunks * kChunkHalves + row * 8;
+#pragma unroll 1
+				for (uint32_t c0 = h * (128 / SPLIT); c0 < (h + 1) * (128 / SPLIT); c0 += 32) {
+					float v[32];
+					tmem_ld32(tlane + c0, v);
+#pragma unroll
+					for (int j = 0; j < 4; ++j)
+						*reinterpret_cast<uint4*>(df_t + (size_t)(c0 / 8 + j) * kChunkHalves) =
+						    make_uint4(pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]), pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+				}
+			}
+			tc_fence_before();
+			mlp_bar_sync<kMlpThreads>();
+			tc_fence_after();
+		}
+		if (issuer) bulk_wait0();
+#undef MMA_WAIT
+#undef STAGE_DONE
+#undef HIDDEN
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
+// ======================================================================================================================
 // Weight gradients.
 constexpr int kWgThreads = 256;
 constexpr uint32_t kWgK = 32;                          // samples per stage
@@ -645,12 +942,22 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 	// (zero inputs, zero loss gradient) is all zeros in X and dY
 	const uint32_t n_tiles = n_pad / kTileM;
 	static const bool split1 = [] { const char* e = getenv("INSTA_NET_BWD_SPLIT"); return e && atoi(e) == 1; }();  // A/B: four MLP warps, a whole row per thread (round 1)
-	if (split1) {
-		INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
-		net_fwd_bwd_kernel<1><<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), (4 + kEncWarps) * 32, kSmTotal, s>>>(a);
+	static const bool ss = [] { const char* e = getenv("INSTA_NET_BWD"); return e && e[0] == 's'; }();                   // A/B: activations through shared-memory operand tiles
+	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
+	if (ss) {
+		if (split1) {
+			INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+			net_fwd_bwd_kernel<1><<<grid, (4 + kEncWarps) * 32, kSmTotal, s>>>(a);
+		} else {
+			INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+			net_fwd_bwd_kernel<kSplit><<<grid, (4 * kSplit + kEncWarps) * 32, kSmTotal, s>>>(a);
+		}
+	} else if (split1) {
+		INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmTotal));
+		net_fwd_bwd_ts_kernel<1><<<grid, (4 + kEncWarps) * 32, kTsSmTotal, s>>>(a);
 	} else {
-		INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
-		net_fwd_bwd_kernel<kSplit><<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), (4 * kSplit + kEncWarps) * 32, kSmTotal, s>>>(a);
+		INSTA_CUDA(cudaFuncSetAttribute(net_fwd_bwd_ts_kernel<kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmTotal));
+		net_fwd_bwd_ts_kernel<kSplit><<<grid, (4 * kSplit + kEncWarps) * 32, kTsSmTotal, s>>>(a);
 	}
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());

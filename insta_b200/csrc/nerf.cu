@@ -497,8 +497,9 @@ int render_frame(insta_ctx* ctx, const insta_camera* cam, const insta_render_opt
 	// (512^2, B200: 9.55 ms per frame with the reference's schedule, 7.00 with 16 steps, 7.24 with 32, 7.76 with 64 -- profiles/r1_render_schedule.txt).
 	const uint32_t max_steps = opts && opts->max_steps_per_iteration ? std::min(opts->max_steps_per_iteration, 0xffffu) : 16u;
 	const uint32_t budget = max_steps <= 8u ? n_pix : std::max(n_pix, 1u << 21);
-	// library default only: an iteration that would carry fewer than 2^tail records marches up to tail_steps steps instead (INSTA_RENDER_TAIL="log2 records,steps", "0,0" = off)
-	static const uint32_t tail_log2 = [] { const char* e = getenv("INSTA_RENDER_TAIL"); return e ? (uint32_t)atoi(e) : 19u; }();
+	// opt-in (INSTA_RENDER_TAIL="log2 records,steps"): an iteration that would carry fewer than 2^tail records marches up to `steps` steps instead.  Measured
+	// (profiles/r2_bwd_ab_v1_scatter_roofline_render_tail.log): "19,64" turns 6 iterations into 4 but evaluates 7 % more samples -- 4.92 ms per 512^2 frame either way, so it is off
+	static const uint32_t tail_log2 = [] { const char* e = getenv("INSTA_RENDER_TAIL"); return e ? (uint32_t)atoi(e) : 0u; }();
 	static const uint32_t tail_steps_env = [] { const char* e = getenv("INSTA_RENDER_TAIL"); const char* c = e ? strchr(e, ',') : nullptr; return c ? (uint32_t)atoi(c + 1) : 64u; }();
 	const bool tail_on = !(opts && opts->max_steps_per_iteration) && tail_log2 > 0 && tail_log2 < 31;
 	const uint32_t tail_budget = tail_on ? std::min(1u << tail_log2, budget) : 0u, tail_steps = tail_on ? tail_steps_env : 0u;

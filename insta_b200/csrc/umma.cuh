@@ -75,6 +75,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 	for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
 }
 
+// A operand from TENSOR MEMORY (the ".ts" form): row m of A in lane m, two consecutive K elements (fp16) per 32-bit column, K-major only; B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+	    "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> tensor memory: 8 / 16 consecutive 32-bit columns of this thread's lane; tmem_st_wait() before anybody else may read them
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+	             "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+	             "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+	             : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // TMA bulk copy shared -> global (contiguous, 16-byte granularity), tracked by the issuing thread's bulk groups.  The shared-memory source must have been
 // made visible to the async proxy (fence_proxy_async by the writers + a barrier) and must stay untouched until bulk_wait_read0() returns.
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t saddr, uint32_t bytes) {
