@@ -13,7 +13,8 @@
 //              into the K-major operand tile A0 (double buffered); the 16 expression floats fill K = 128..143.
 //   warps 0-3  "MLP": one elected thread issues tcgen05.mma (M = 128 samples, N = 64 / 16, K = 16 per instruction, fp16
 //              operands from shared memory, fp32 accumulators in TENSOR MEMORY); all four warps run the epilogues
-//              (tcgen05.ld of their 32 TMEM lanes, ReLU, fp16, store as the next layer's operand tile).
+//              (tcgen05.ld of their 32 TMEM lanes, ReLU, fp16 pairs, tcgen05.st into the columns the next layer's GEMM reads as its A operand:
+//              after the first layer the activations never leave tensor memory).
 //   density MLP 144 -> 64 -> 64 -> 16, colour MLP (16 density features | 16 SH) 32 -> 64 -> 64 -> 64 -> 16 (3 used): seven
 //   dependent GEMMs per tile (~51 kFLOP/sample), hidden behind the gathers of the next tile through the mbarrier ring.
 // Operand tiles use the canonical no-swizzle K-major UMMA layout: 8 rows x 16 bytes core matrices, 128 bytes apart along
@@ -43,7 +44,9 @@ constexpr int kWidth = 64;        // n_neurons
 constexpr int kInDensity = 144;   // 128 grid features + 16 expression dims
 constexpr int kInRgb = 32;        // 16 density outputs + 16 SH
 constexpr int kOutPad = 16;       // padded output width
-constexpr uint32_t kTmemCols = 64;
+// tensor memory: accumulators in columns 0-63; the A operands of the GEMMs after the first one: hidden activations (K = 64 -> 32 columns of fp16 pairs)
+// and the colour MLP's input (16 density outputs | 16 SH -> 16 columns)
+constexpr uint32_t kTmemCols = 128, kColH = 64, kColA3 = 96;
 
 // parameter offsets (halves) in the trainer's order: density MLP, rgb MLP, grid (ngp nerf_network.h:492-525)
 constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kWidth * kInDensity, kOffW3 = kOffW2 + kWidth * kWidth;
@@ -54,12 +57,8 @@ static_assert(kOffGrid == 25600, "MLP parameter count of the shipped config");
 // shared-memory map (bytes)
 constexpr uint32_t kChunkA = kTileM * 16;                       // one K-chunk (8 halves) of a 128-row operand tile
 constexpr uint32_t kBytesA0 = (kInDensity / 8) * kChunkA;       // 36,864
-constexpr uint32_t kBytesH = (kWidth / 8) * kChunkA;            // 16,384
-constexpr uint32_t kBytesA3 = (kInRgb / 8) * kChunkA;           // 8,192
 constexpr uint32_t kSmA0 = 0;                                   // two buffers
-constexpr uint32_t kSmH = kSmA0 + 2 * kBytesA0;                 // two buffers
-constexpr uint32_t kSmA3 = kSmH + 2 * kBytesH;
-constexpr uint32_t kSmW1 = kSmA3 + kBytesA3;
+constexpr uint32_t kSmW1 = kSmA0 + 2 * kBytesA0;
 constexpr uint32_t kSmW2 = kSmW1 + kWidth * kInDensity * 2;
 constexpr uint32_t kSmW3 = kSmW2 + kWidth * kWidth * 2;
 constexpr uint32_t kSmV1 = kSmW3 + kOutPad * kWidth * 2;
@@ -84,22 +83,38 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem, uint32_t a_saddr, uint
 	umma_commit(mma_bar);
 }
 
-// TMEM accumulators of this thread's row -> ReLU -> fp16 -> operand tile of the next layer (N_COLS / 8 chunks of 16 bytes)
-template <int N_COLS, bool RELU>
-__device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, unsigned char* tile, uint32_t row, float* keep0 /* nullable: receives column 0 as fp16-rounded */) {
-	unsigned char* dst = tile + (row >> 3) * 128 + (row & 7) * 16;
+// the same with A in tensor memory (row in lane, two K elements per 32-bit column): the layers after the first one
+template <int N, int K>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_saddr, uint32_t mma_bar) {
+	constexpr uint32_t idesc = umma_idesc(kTileM, N);
 #pragma unroll
-	for (int c0 = 0; c0 < N_COLS; c0 += 16) {
-		float v[16];
-		tmem_ld16(taddr + c0, v);
+	for (int j = 0; j < K / 16; ++j) {
+		const uint64_t bd = umma_desc(b_saddr + j * 2 * (N * 16), N * 16, 128);
+		umma_f16_ts(tmem_d, tmem_a + j * 8, bd, idesc, j > 0 ? 1u : 0u);
+	}
+	umma_commit(mma_bar);
+}
+
+// TMEM accumulators of this thread's row -> ReLU -> fp16 pairs -> the A-operand columns of the next layer, again in tensor memory (tcgen05.st): no
+// shared-memory tile and no fence.proxy.async between two layers (with the tile in shared memory that fence -- MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, queued
+// behind the encoder warps' gathers -- was 40 % of the MLP warps' time in the training kernel; profiles/r2_net_fwd_bwd_bulk_ncu_summary.txt)
+template <int N_COLS, bool RELU>
+__device__ __forceinline__ void epilogue_to_tmem(uint32_t taddr_d, uint32_t taddr_a, float* keep0 /* nullable: receives column 0 as fp16-rounded */) {
+	constexpr int W = N_COLS >= 32 ? 32 : 16;
+#pragma unroll
+	for (int c0 = 0; c0 < N_COLS; c0 += W) {
+		float v[W];
+		if (W == 32) tmem_ld32(taddr_d + c0, v);
+		else tmem_ld16(taddr_d + c0, v);
 		if (RELU) {
 #pragma unroll
-			for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.0f);
+			for (int k = 0; k < W; ++k) v[k] = fmaxf(v[k], 0.0f);
 		}
-		const uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-		const uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-		*reinterpret_cast<uint4*>(dst + (c0 / 8) * kChunkA) = lo;
-		*reinterpret_cast<uint4*>(dst + (c0 / 8 + 1) * kChunkA) = hi;
+		uint32_t p[W / 2];
+#pragma unroll
+		for (int k = 0; k < W / 2; ++k) p[k] = pack2(v[2 * k], v[2 * k + 1]);
+		if (W == 32) tmem_st16(taddr_a + c0 / 2, p);
+		else tmem_st8(taddr_a + c0 / 2, p);
 		if (keep0 && c0 == 0) *keep0 = __half2float(__float2half_rn(v[0]));
 	}
 }
@@ -251,12 +266,15 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 		// =================================== MLP warps ===================================
 		const uint32_t row = threadIdx.x;                        // == TMEM lane
 		const uint32_t taddr = tmem_base + ((warp * 32u) << 16);  // this warp's lane quadrant
-		unsigned char* H0 = smem + kSmH;
-		unsigned char* H1 = smem + kSmH + kBytesH;
-		unsigned char* A3 = smem + kSmA3;
-		const uint32_t sH0 = sbase + kSmH, sH1 = sH0 + kBytesH, sA3 = sbase + kSmA3;
+		const uint32_t tH = tmem_base + kColH, tA3 = tmem_base + kColA3;
 		uint32_t mma_phase = 0, it = 0;
 		const bool issuer = threadIdx.x == 0;
+// what the epilogue stored into tensor memory is complete before the issuer's next GEMM reads it
+#define STAGE_DONE()   \
+	tmem_st_wait();    \
+	tc_fence_before(); \
+	mlp_bar_sync();    \
+	tc_fence_after()
 		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
 			const uint32_t b = it & 1u;
 			const uint32_t i = tile * kTileM + row;
@@ -267,54 +285,53 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 				const float* rec = a.records + (size_t)si * a.stride;
 				dx = __ldg(rec + 8); dy = __ldg(rec + 9); dz = __ldg(rec + 10);
 			}
-			// ---- density layer 1: A0 (144) -> 64 ----
+			// ---- density layer 1: A0 (144, shared memory) -> 64 ----
 			mbar_wait(bar_full0 + 8 * b, (it >> 1) & 1u);
 			tc_fence_after();
 			if (issuer) issue_gemm<kWidth, kInDensity>(tmem_base, sbase + kSmA0 + b * kBytesA0, sbase + kSmW1, bar_mma);
 			{
 				uint4 lo, hi;
 				sh4(dx * 2.f - 1.f, dy * 2.f - 1.f, dz * 2.f - 1.f, lo, hi);
-				unsigned char* dst = A3 + (row >> 3) * 128 + (row & 7) * 16;
-				*reinterpret_cast<uint4*>(dst + 2 * kChunkA) = lo;
-				*reinterpret_cast<uint4*>(dst + 3 * kChunkA) = hi;
+				const uint32_t p[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+				tmem_st8(taddr + kColA3 + 8, p);
 			}
 			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
 			tc_fence_after();
 			if (issuer) mbar_arrive(bar_empty0 + 8 * b);  // A0[b] has been consumed: the encoders may refill it
-			epilogue_to_tile<kWidth, true>(taddr, H0, row, nullptr);
-			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
 			// ---- density layer 2: 64 -> 64 ----
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sbase + kSmW2, bar_mma);
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sbase + kSmW2, bar_mma);
 			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
 			tc_fence_after();
-			epilogue_to_tile<kWidth, true>(taddr, H1, row, nullptr);
-			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
 			// ---- density output: 64 -> 16, no activation; column 0 is the density logit ----
-			if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH1, sbase + kSmW3, bar_mma);
+			if (issuer) issue_gemm_ts<kOutPad, kWidth>(tmem_base, tH, sbase + kSmW3, bar_mma);
 			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
 			tc_fence_after();
 			float sigma = 0.f;
-			epilogue_to_tile<kOutPad, false>(taddr, A3, row, &sigma);
-			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			epilogue_to_tmem<kOutPad, false>(taddr, taddr + kColA3, &sigma);
+			STAGE_DONE();
 			// ---- colour layer 1: (16 density | 16 SH) -> 64 ----
-			if (issuer) issue_gemm<kWidth, kInRgb>(tmem_base, sA3, sbase + kSmV1, bar_mma);
+			if (issuer) issue_gemm_ts<kWidth, kInRgb>(tmem_base, tA3, sbase + kSmV1, bar_mma);
 			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
 			tc_fence_after();
-			epilogue_to_tile<kWidth, true>(taddr, H0, row, nullptr);
-			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
 			// ---- colour layers 2, 3 ----
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH0, sbase + kSmV2, bar_mma);
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sbase + kSmV2, bar_mma);
 			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
 			tc_fence_after();
-			epilogue_to_tile<kWidth, true>(taddr, H1, row, nullptr);
-			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
-			if (issuer) issue_gemm<kWidth, kWidth>(tmem_base, sH1, sbase + kSmV3, bar_mma);
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sbase + kSmV3, bar_mma);
 			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
 			tc_fence_after();
-			epilogue_to_tile<kWidth, true>(taddr, H0, row, nullptr);
-			fence_proxy_async(); tc_fence_before(); mlp_bar_sync(); tc_fence_after();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
 			// ---- colour output: 64 -> 16 (3 used) ----
-			if (issuer) issue_gemm<kOutPad, kWidth>(tmem_base, sH0, sbase + kSmV4, bar_mma);
+			if (issuer) issue_gemm_ts<kOutPad, kWidth>(tmem_base, tH, sbase + kSmV4, bar_mma);
 			mbar_wait(bar_mma, mma_phase); mma_phase ^= 1u;
 			tc_fence_after();
 			float o[16];
@@ -336,6 +353,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 			// the next tile's first GEMM overwrites the accumulator columns: all reads above must have completed
 			mlp_bar_sync();
 		}
+#undef STAGE_DONE
 	}
 
 	tc_fence_before();
