@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.h"
@@ -118,6 +120,12 @@ struct Trainer {
 	bool serial_exchange = false;  // INSTA_GRAD_EXCHANGE=serial
 	bool p2p_exchange = false;     // INSTA_GRAD_EXCHANGE=p2p: peer-memory exchange (peer_exchange_run); falls back to ncclAllReduce when the setup fails on any rank
 	bool no_exchange = false;      // INSTA_GRAD_EXCHANGE=none: the step without its collective (measurement only: the ranks' parameters diverge)
+	// INSTA_TRAIN_PROFILE=1: CUDA events between the phases of a step, averaged and printed to stderr every 20 steps (measurement aid; ncu's serialised,
+	// cold-cache launch times overstate the latency-bound kernels)
+	bool profile = false;
+	cudaEvent_t pev[7] = {};
+	double pms[6] = {};
+	uint32_t psteps = 0;
 };
 
 namespace {
@@ -149,6 +157,8 @@ void free_trainer(Trainer* t) {
 	for (int g = 0; g < 4; ++g)
 		if (t->ex.ev_grid_ready[g]) cudaEventDestroy(t->ex.ev_grid_ready[g]);
 	if (t->ex.ev_grid_summed) cudaEventDestroy(t->ex.ev_grid_summed);
+	for (auto& ev : t->pev)
+		if (ev) cudaEventDestroy(ev);
 	delete t;
 }
 }  // namespace
@@ -396,6 +406,9 @@ int trainer_create(insta_ctx* ctx, const insta_trainer_config* cfg) {
 	// a side stream) measured no better on 2 GPUs (3.17 vs 3.14 ms per step, 3.01 without the collective; profiles/r2_train_exchange.txt): four short scatter
 	// launches and four latency-bound collectives cost what the overlap gains, and next to the persistent weight-gradient kernel NCCL's kernel finds no SM.
 	t->serial_exchange = true;
+	if (const char* e = getenv("INSTA_TRAIN_PROFILE")) t->profile = atoi(e) != 0;
+	if (t->profile)
+		for (auto& ev : t->pev) cudaEventCreate(&ev);
 	if (const char* e = getenv("INSTA_GRAD_EXCHANGE")) {
 		t->serial_exchange = std::string(e) != "overlap";
 		t->no_exchange = std::string(e) == "none";
@@ -496,8 +509,11 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	st.d_numsteps = t->numsteps;
 	t->n_rays_total += n_rays;  // testbed_nerf.cu:3235
 
+	auto mark = [&](int k) { if (t->profile) cudaEventRecord(t->pev[k], s); };
+	mark(0);
 	int rc = train_generate(ctx, &st, s);
 	if (rc) return rc;
+	mark(1);
 	// rta::Core::surface_closest_point on the generated records (testbed_nerf.cu:3290), then the network on the same records (3292)
 	{
 		std::lock_guard<std::mutex> lock(ctx->mu);
@@ -527,8 +543,10 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 			if (rc) return rc;
 		}
 	}
+	mark(2);
 	rc = train_loss(ctx, &st, t->mlp_out, kOutWidth, t->coords_compacted, t->dloss, t->loss, d_mean_density, s);
 	if (rc) return rc;
+	mark(3);
 	// forward + backward on the compacted, rolled-over batch (testbed_nerf.cu:3366-3371)
 	// data-parallel exchange step (world > 1): one ncclAllReduce over the whole gradient vector after the backward pass, or (INSTA_GRAD_EXCHANGE=overlap)
 	// the grid gradients summed group of levels by group of levels on a side stream while the scatter kernel works on the next group
@@ -544,6 +562,7 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	rc = launch_network_fwd_bwd(ctx, t->coords_compacted, stride, target, opt->d_params_f16, t->dloss, kOutWidth, grads, nullptr, s, overlap && !p2p ? &t->ex : nullptr);
 	if (rc) return rc;
 	t->rng_advances += 1;  // m_rng.advance() (testbed_nerf.cu:3419)
+	mark(4);
 	if (p2p) {
 		rc = peer_exchange_run(ctx, s);
 		if (rc) return rc;
@@ -553,6 +572,7 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 		rc = grad_allreduce(ctx, (void*)opt->d_gradients_f16, network_n_params(ctx), s);
 		if (rc) return rc;
 	}
+	mark(5);
 	// Trainer::optimizer_step(stream, LOSS_SCALE) (testbed_nerf.cu:2974)
 	if (!c.freeze_parameters) {
 		insta_optimizer o = *opt;
@@ -562,6 +582,7 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 		if (rc) return rc;
 	}
 	t->training_step += 1;
+	mark(6);
 
 	// Counters::update_after_training (testbed_nerf.cu:2889-2914): one read-back per step, as in the reference
 	if (get_loss_scalar) {
@@ -572,6 +593,20 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 	}
 	INSTA_CUDA(cudaMemcpyAsync(t->h_counters, t->counters, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, s));
 	INSTA_CUDA(cudaStreamSynchronize(s));
+	if (t->profile) {
+		static const char* const names[6] = {"generate", "deform+network", "loss+compaction", "forward+backward", "exchange", "optimizer"};
+		for (int k = 0; k < 6; ++k) {
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, t->pev[k], t->pev[k + 1]);
+			t->pms[k] += ms;
+		}
+		if (++t->psteps == 20) {
+			fprintf(stderr, "[insta_train_nerf] step %u, mean of 20 steps (ms):", t->training_step);
+			for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.3f", names[k], t->pms[k] / 20.0), t->pms[k] = 0.0;
+			fprintf(stderr, "\n");
+			t->psteps = 0;
+		}
+	}
 	const uint32_t generated = t->h_counters[1], compacted = t->h_counters[2];
 	float loss_scalar = 0.f;
 	t->measured_batch_size = t->measured_batch_size_before_compaction = 0;
