@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "ctx.h"
 #include "grid_device.cuh"
@@ -361,6 +362,253 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
 }
 
+
+// ======================================================================================================================
+// The same network with LANE-PAIR encoders (default; nerf_network_fwd_kernel above = INSTA_NET_FWD=v1).
+// The kernel above is bound by the L1's sector rate (88 % of peak: 32 lanes = 32 samples = 32 sectors per gather instruction).  hash_fwd_pairs_kernel's mapping --
+// lanes 2j / 2j + 1 = the two x-sides of a cell: neighbouring table entries, one sector half of the time -- removes a quarter of that work but costs shuffles and
+// issue slots, which 8 encoder warps do not have (measured in round 2: 1.92 -> 2.28 ms).  With the activations in tensor memory the MLP side needs 4 light warps and no
+// shared-memory tiles, so the CTA affords 12 encoder warps.  They no longer own rows: the work of a tile is 32 TASKS (level x half of the tile's rows: 64 samples x
+// 4 gathers per lane), a warp takes the tasks w, w + 12, w + 24, ... of the endless sequence tile 0 task 0..31, tile 1 task 0..31, ... -- no assignment problem (32 is not
+// a multiple of 12) and no atomics; a tile is complete when its 32 tasks have arrived on its mbarrier.  Positions and the 16 expression inputs of a tile are staged by the
+// MLP threads (thread = row; they read the record anyway for the view direction), two tiles ahead, behind the first layer's epilogue.
+constexpr int kEncWarpsP = 12, kNetThreadsP = kMlpThreads + kEncWarpsP * 32;
+constexpr uint32_t kTasksPerTile = 32;
+constexpr uint32_t kSmPos = kSmBar + 64, kSmTotalP = kSmPos + 2 * kTileM * 3 * 4;
+
+template <bool HASHED>
+__device__ __forceinline__ void encoder_task(const GridLevels& L, const uint4* __restrict__ table, uint32_t level, const float* __restrict__ pos, uint32_t hf, uint32_t lane,
+                                             unsigned char* A0) {
+	const uint32_t b = lane & 1u, g = lane >> 1;
+	const uint32_t size = L.size[level], mul1 = L.mul1[level], mul2 = L.mul2[level];
+	const float scale = L.scale[level];
+	table += L.offset[level];
+	// this lane's rows: 64 hf + g + 16 p -- for a fixed p the 16 lane pairs write 256 contiguous bytes of the operand tile
+	__half2 acc[4][2];
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		uint4 v[2][4];
+		float w[2][4];
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			const float* sp = pos + 3u * (64u * hf + g + 16u * (2 * h + q));
+			pair_load<HASHED>(table, pos_fract3(sp[0], sp[1], sp[2], scale), b, size, mul1, mul2, v[q], w[q]);
+		}
+#pragma unroll
+		for (int q = 0; q < 2; ++q) pair_accumulate(v[q], w[q], b, acc[2 * h + q][0], acc[2 * h + q][1]);
+	}
+#pragma unroll
+	for (int p = 0; p < 4; ++p) {
+		const uint32_t row = 64u * hf + g + 16u * p;
+		*reinterpret_cast<uint2*>(A0 + level * kChunkA + row * 16u + 8u * b) =
+		    make_uint2(*reinterpret_cast<const uint32_t*>(&acc[p][0]), *reinterpret_cast<const uint32_t*>(&acc[p][1]));  // features 4b .. 4b+3 of the level
+	}
+}
+
+__global__ void __launch_bounds__(kNetThreadsP, 1) nerf_network_fwd_pairs_kernel(const __grid_constant__ NetArgs a) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	const uint32_t sbase = smem_u32(smem);
+	const uint32_t bar_full0 = sbase + kSmBar, bar_empty0 = sbase + kSmBar + 16, bar_mma = sbase + kSmBar + 32;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 40);
+	float* pos = reinterpret_cast<float*>(smem + kSmPos);  // [2][128][3]
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t n_samples = a.n_ptr ? min(a.n, __ldg(a.n_ptr)) : a.n;
+	const uint32_t n_tiles = (n_samples + kTileM - 1) / kTileM;
+
+	stage_weights(smem + kSmW1, a.params + kOffW1, kWidth, kInDensity);
+	stage_weights(smem + kSmW2, a.params + kOffW2, kWidth, kWidth);
+	stage_weights(smem + kSmW3, a.params + kOffW3, kOutPad, kWidth);
+	stage_weights(smem + kSmV1, a.params + kOffV1, kWidth, kInRgb);
+	stage_weights(smem + kSmV2, a.params + kOffV2, kWidth, kWidth);
+	stage_weights(smem + kSmV3, a.params + kOffV3, kWidth, kWidth);
+	stage_weights(smem + kSmV4, a.params + kOffV4, kOutPad, kWidth);
+	if (threadIdx.x == 0) {
+		mbar_init(bar_full0, kTasksPerTile);
+		mbar_init(bar_full0 + 8, kTasksPerTile);
+		mbar_init(bar_empty0, 1);
+		mbar_init(bar_empty0 + 8, 1);
+		mbar_init(bar_mma, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 0) {
+		__syncwarp();
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	// MLP thread = tile row: position and the 16 expression inputs (extract_expressions) of that row's sample in tile `tile`
+	struct RowIn {
+		float px, py, pz;
+		uint32_t ex[8];
+	};
+	auto fetch = [&](uint32_t tile, uint32_t row) {
+		RowIn r{};
+		const uint32_t i = tile * kTileM + row;
+		if (tile < n_tiles && i < n_samples) {
+			const float* rec = a.records + (size_t)(a.index ? __ldg(a.index + i) : i) * a.stride;
+			r.px = __ldg(rec); r.py = __ldg(rec + 1); r.pz = __ldg(rec + 2);
+			const bool ones = a.density_only || (a.uniform_extra && __ldg(rec + 4) == -2.0f);
+			const float* exsrc = a.uniform_extra ? a.uniform_extra : rec + a.stride - a.n_extra;
+#pragma unroll
+			for (uint32_t k = 0; k < 8; ++k) {
+				const float e0 = 2 * k < a.n_extra ? (ones ? 1.0f : __ldg(exsrc + 2 * k)) : 0.0f;
+				const float e1 = 2 * k + 1 < a.n_extra ? (ones ? 1.0f : __ldg(exsrc + 2 * k + 1)) : 0.0f;
+				r.ex[k] = pack2(e0, e1);
+			}
+		}
+		return r;
+	};
+	auto stage = [&](uint32_t b, uint32_t row, const RowIn& r) {
+		float* P = pos + (b * kTileM + row) * 3u;
+		P[0] = r.px; P[1] = r.py; P[2] = r.pz;
+		unsigned char* A = smem + kSmA0 + b * kBytesA0 + row * 16u;
+		*reinterpret_cast<uint4*>(A + 16 * kChunkA) = make_uint4(r.ex[0], r.ex[1], r.ex[2], r.ex[3]);
+		*reinterpret_cast<uint4*>(A + 17 * kChunkA) = make_uint4(r.ex[4], r.ex[5], r.ex[6], r.ex[7]);
+	};
+	if (warp < kMlpWarps) {
+		stage(0, threadIdx.x, fetch(blockIdx.x, threadIdx.x));
+		stage(1, threadIdx.x, fetch(blockIdx.x + gridDim.x, threadIdx.x));
+	}
+	fence_proxy_async();  // the staged weights and expression chunks are read by the tensor core through the async proxy
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp >= kMlpWarps) {
+		// =================================== encoders: tasks w, w + 12, ... ===================================
+		const uint4* table = reinterpret_cast<const uint4*>(a.params + kOffGrid);
+		for (uint32_t id = warp - kMlpWarps;; id += kEncWarpsP) {
+			const uint32_t it = id / kTasksPerTile, sub = id % kTasksPerTile;
+			if ((uint64_t)blockIdx.x + (uint64_t)it * gridDim.x >= n_tiles) break;
+			const uint32_t b = it & 1u, level = sub & 15u, hf = sub >> 4;
+			mbar_wait(bar_empty0 + 8 * b, ((it >> 1) & 1u) ^ 1u);
+			unsigned char* A0 = smem + kSmA0 + b * kBytesA0;
+			const float* P = pos + b * kTileM * 3u;
+			if (level < a.L.n_levels) {
+				if (a.L.hashed[level]) encoder_task<true>(a.L, table, level, P, hf, lane, A0);
+				else encoder_task<false>(a.L, table, level, P, hf, lane, A0);
+			} else {
+#pragma unroll
+				for (int p = 0; p < 4; ++p)
+					*reinterpret_cast<uint2*>(A0 + level * kChunkA + (64u * hf + (lane >> 1) + 16u * p) * 16u + 8u * (lane & 1u)) = make_uint2(0u, 0u);
+			}
+			fence_proxy_async();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(bar_full0 + 8 * b);
+		}
+	} else {
+		// =================================== MLP warps ===================================
+		const uint32_t row = threadIdx.x;                        // == TMEM lane
+		const uint32_t taddr = tmem_base + ((warp * 32u) << 16);  // this warp's lane quadrant
+		const uint32_t tH = tmem_base + kColH, tA3 = tmem_base + kColA3;
+		uint32_t mma_phase = 0, it = 0;
+		const bool issuer = threadIdx.x == 0;
+#define STAGE_DONE()   \
+	tmem_st_wait();    \
+	tc_fence_before(); \
+	mlp_bar_sync();    \
+	tc_fence_after()
+#define MMA_WAIT()                 \
+	mbar_wait(bar_mma, mma_phase); \
+	mma_phase ^= 1u;               \
+	tc_fence_after()
+		for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+			const uint32_t b = it & 1u;
+			const uint32_t i = tile * kTileM + row;
+			const uint32_t si = (a.index && i < n_samples) ? __ldg(a.index + i) : i;  // record / output slot of this row's sample
+			float dx = 0.5f, dy = 0.5f, dz = 0.5f;
+			if (i < n_samples && !a.density_only) {
+				const float* rec = a.records + (size_t)si * a.stride;
+				dx = __ldg(rec + 8); dy = __ldg(rec + 9); dz = __ldg(rec + 10);
+			}
+			const RowIn next = fetch(tile + 2 * gridDim.x, row);  // the tile that will use this tile's buffers; consumed behind the first epilogue
+			// ---- density layer 1: A0 (144, shared memory) -> 64 ----
+			mbar_wait(bar_full0 + 8 * b, (it >> 1) & 1u);
+			tc_fence_after();
+			if (issuer) issue_gemm<kWidth, kInDensity>(tmem_base, sbase + kSmA0 + b * kBytesA0, sbase + kSmW1, bar_mma);
+			{
+				uint4 lo, hi;
+				sh4(dx * 2.f - 1.f, dy * 2.f - 1.f, dz * 2.f - 1.f, lo, hi);
+				const uint32_t p[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+				tmem_st8(taddr + kColA3 + 8, p);
+			}
+			MMA_WAIT();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			// A0[b] and its positions have been consumed (all 32 tasks arrived before the GEMM was issued, and the GEMM is complete): restage them for tile + 2 * grid
+			stage(b, row, next);
+			fence_proxy_async();
+			STAGE_DONE();
+			if (issuer) {
+				mbar_arrive(bar_empty0 + 8 * b);
+				issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sbase + kSmW2, bar_mma);
+			}
+			MMA_WAIT();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
+			// ---- density output: 64 -> 16, no activation; column 0 is the density logit ----
+			if (issuer) issue_gemm_ts<kOutPad, kWidth>(tmem_base, tH, sbase + kSmW3, bar_mma);
+			MMA_WAIT();
+			float sigma = 0.f;
+			epilogue_to_tmem<kOutPad, false>(taddr, taddr + kColA3, &sigma);
+			STAGE_DONE();
+			// ---- colour layer 1: (16 density | 16 SH) -> 64 ----
+			if (issuer) issue_gemm_ts<kWidth, kInRgb>(tmem_base, tA3, sbase + kSmV1, bar_mma);
+			MMA_WAIT();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
+			// ---- colour layers 2, 3 ----
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sbase + kSmV2, bar_mma);
+			MMA_WAIT();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
+			if (issuer) issue_gemm_ts<kWidth, kWidth>(tmem_base, tH, sbase + kSmV3, bar_mma);
+			MMA_WAIT();
+			epilogue_to_tmem<kWidth, true>(taddr, taddr + kColH, nullptr);
+			STAGE_DONE();
+			// ---- colour output: 64 -> 16 (3 used) ----
+			if (issuer) issue_gemm_ts<kOutPad, kWidth>(tmem_base, tH, sbase + kSmV4, bar_mma);
+			MMA_WAIT();
+			float o[16];
+			tmem_ld16(taddr, o);
+			tc_fence_before();
+			if (i < n_samples) {
+				const __half2 rg = __floats2half2_rn(o[0], o[1]), bs = __floats2half2_rn(o[2], sigma);
+				if (a.density_only) {
+					a.out[si] = __high2half(bs);
+				} else if (a.out_stride == 0) {
+					*reinterpret_cast<uint2*>(a.out + (size_t)si * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&bs));
+				} else {
+					a.out[si] = __low2half(rg);
+					a.out[si + (size_t)a.out_stride] = __high2half(rg);
+					a.out[si + 2 * (size_t)a.out_stride] = __low2half(bs);
+					a.out[si + 3 * (size_t)a.out_stride] = __high2half(bs);
+				}
+			}
+			// the next tile's first GEMM overwrites the accumulator columns: all reads above must have completed
+			mlp_bar_sync();
+		}
+#undef STAGE_DONE
+#undef MMA_WAIT
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
+// both launchers: the lane-pair kernel unless INSTA_NET_FWD=v1
+static int launch_net(const NetArgs& a, uint32_t grid, cudaStream_t s) {
+	static const bool v1 = [] { const char* e = getenv("INSTA_NET_FWD"); return e && e[0] == 'v'; }();
+	if (v1) {
+		INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
+		nerf_network_fwd_kernel<<<grid, kNetThreads, kSmTotal, s>>>(a);
+	} else {
+		INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotalP));
+		nerf_network_fwd_pairs_kernel<<<grid, kNetThreadsP, kSmTotalP, s>>>(a);
+	}
+	return INSTA_OK;
+}
+
 }  // namespace
 
 uint32_t network_n_params(const insta_ctx* ctx) { return kOffGrid + ctx->levels.offset[ctx->levels.n_levels] * 8u; }
@@ -381,10 +629,9 @@ int launch_network_fwd(insta_ctx* ctx, const float* d_records, uint32_t stride, 
 	a.index = d_index;
 	a.L = ctx->levels;
 	if (a.n_extra > 16) INSTA_FAIL(INSTA_ERR_INVALID, "network: more than 16 extra dims are not supported by the density MLP input (144 = 128 + 16)");
-	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
 	const uint32_t n_tiles = (n + kTileM - 1) / kTileM;
 	const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
-	nerf_network_fwd_kernel<<<grid, kNetThreads, kSmTotal, s>>>(a);
+	if (int rc = launch_net(a, grid, s)) return rc;
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
@@ -407,9 +654,8 @@ int launch_network_density(insta_ctx* ctx, const float* d_xyz, uint32_t stride, 
 	a.density_only = 1;
 	a.L = ctx->levels;
 	if (a.n_extra > 16) INSTA_FAIL(INSTA_ERR_INVALID, "network: more than 16 extra dims are not supported by the density MLP input (144 = 128 + 16)");
-	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
 	const uint32_t n_tiles = (n + kTileM - 1) / kTileM;
-	nerf_network_fwd_kernel<<<std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), kNetThreads, kSmTotal, s>>>(a);
+	if (int rc = launch_net(a, std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count), s)) return rc;
 	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
