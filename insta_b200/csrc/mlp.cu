@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kNetThreads, 1) nerf_network_fwd_kernel(const 
 // 4 gathers per lane), a warp takes the tasks w, w + 12, w + 24, ... of the endless sequence tile 0 task 0..31, tile 1 task 0..31, ... -- no assignment problem (32 is not
 // a multiple of 12) and no atomics; a tile is complete when its 32 tasks have arrived on its mbarrier.  Positions and the 16 expression inputs of a tile are staged by the
 // MLP threads (thread = row; they read the record anyway for the view direction), two tiles ahead, behind the first layer's epilogue.
-constexpr int kEncWarpsP = 12, kNetThreadsP = kMlpThreads + kEncWarpsP * 32;
+constexpr int kEncWarpsDefault = 12;
 constexpr uint32_t kTasksPerTile = 32;
 constexpr uint32_t kSmPos = kSmBar + 64, kSmTotalP = kSmPos + 2 * kTileM * 3 * 4;
 
@@ -405,7 +405,8 @@ __device__ __forceinline__ void encoder_task(const GridLevels& L, const uint4* _
 	}
 }
 
-__global__ void __launch_bounds__(kNetThreadsP, 1) nerf_network_fwd_pairs_kernel(const __grid_constant__ NetArgs a) {
+template <int kEncWarpsP>
+__global__ void __launch_bounds__(kMlpThreads + kEncWarpsP * 32, 1) nerf_network_fwd_pairs_kernel(const __grid_constant__ NetArgs a) {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	const uint32_t sbase = smem_u32(smem);
 	const uint32_t bar_full0 = sbase + kSmBar, bar_empty0 = sbase + kSmBar + 16, bar_mma = sbase + kSmBar + 32;
@@ -603,8 +604,16 @@ static int launch_net(const NetArgs& a, uint32_t grid, cudaStream_t s) {
 		INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotal));
 		nerf_network_fwd_kernel<<<grid, kNetThreads, kSmTotal, s>>>(a);
 	} else {
-		INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotalP));
-		nerf_network_fwd_pairs_kernel<<<grid, kNetThreadsP, kSmTotalP, s>>>(a);
+		static const int enc = [] { const char* e = getenv("INSTA_NET_ENC_WARPS"); return e ? atoi(e) : kEncWarpsDefault; }();  // A/B: 8, 10, 12, 14, 16
+#define LAUNCH_P(W)                                                                                                                       \
+	INSTA_CUDA(cudaFuncSetAttribute(nerf_network_fwd_pairs_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmTotalP)); \
+	nerf_network_fwd_pairs_kernel<W><<<grid, kMlpThreads + W * 32, kSmTotalP, s>>>(a)
+		if (enc == 8) { LAUNCH_P(8); }
+		else if (enc == 10) { LAUNCH_P(10); }
+		else if (enc == 14) { LAUNCH_P(14); }
+		else if (enc == 16) { LAUNCH_P(16); }
+		else { LAUNCH_P(12); }
+#undef LAUNCH_P
 	}
 	return INSTA_OK;
 }
