@@ -428,6 +428,9 @@ def run_ours(args):
             gather = {"l2_16B_gbs": ctx.microbench_gather(tb, 16), "l2_128B_gbs": ctx.microbench_gather(tb, 128),
                       "hbm_16B_gbs": ctx.microbench_gather(1 << 30, 16), "buffer_bytes": tb,
                       "how": "insta_microbench_gather: every lane loads 16 B (or 8 lanes one 128-B line) from pseudo-random offsets, 8 loads in flight per lane, best of 5"}
+            # the scatter side (kernel_grid_backward): divergent 16-byte fp16 vector reductions at L2, alone and with two lanes sharing a 32-byte sector
+            gather["l2_scatter_16B_gbs"] = ctx.microbench_scatter(tb, 16)
+            gather["l2_scatter_32B_pair_gbs"] = ctx.microbench_scatter(tb, 32)
         except Exception as e:
             gather = {"error": repr(e)}
     stress = None
@@ -491,6 +494,15 @@ def run_ours(args):
                 line["speedup_vs_ref_cuda"]["training step"] = trn["ref_cuda"]["ms_per_step"] / float(np.mean(trn["ms_steps"][-4:]))
             if net and refc.get("network_inference_ms"):
                 line["speedup_vs_ref_cuda"]["network inference"] = refc["network_inference_ms"] / net["ms"]
+            if net and refc.get("network_forward_backward_ms_2p18"):
+                line["speedup_vs_ref_cuda"]["network forward+backward (2^18)"] = refc["network_forward_backward_ms_2p18"] / net["forward_backward_ms_2p18"]
+            if refc.get("ours_hash_bwd_ms_2p18"):
+                line["speedup_vs_ref_cuda"]["hash backward (2^18)"] = refc["kernel_grid_backward_ms_2p18"] / refc["ours_hash_bwd_ms_2p18"]
+                g = line.get("l2_gather_roofline")
+                if g and g.get("l2_scatter_32B_pair_gbs"):
+                    # 2^18 samples x 16 levels x 8 corners x 16 bytes reduced at L2, over the measured ceiling of pair-shared reductions (memset included in our time)
+                    g["hash_bwd_reduced_gbs"] = (1 << 18) * 128 * 16 / (refc["ours_hash_bwd_ms_2p18"] * 1e-3) / 1e9
+                    g["hash_bwd_frac"] = g["hash_bwd_reduced_gbs"] / g["l2_scatter_32B_pair_gbs"]
         if not args.no_render:
             line["network"] = net
             line["render"] = rnd

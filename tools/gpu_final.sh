@@ -1,11 +1,21 @@
-# final pass of a round: GPU parity tests, the default bench line, the comparison with the reference's own CUDA code (no profiler)
+# final pass of a round: the whole GPU suite, the default bench line, the launch list of the bench command (kernel shares), one full capture of the dominant kernel
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/gpu_tests_v14.log
-timeout 300 python bench.py > gpurun_out/bench_default_v14.json 2> gpurun_out/bench_v14.err
-timeout 300 python tests/bench_ref_cuda.py > gpurun_out/vs_ref_cuda_v14.json 2> gpurun_out/vs_v14.err
-cat gpurun_out/gpu_tests_v14.log; tail -n 2 gpurun_out/bench_v14.err; tail -n 2 gpurun_out/vs_v14.err
-python - <<'PY'
+T=${TAG:-r2_final}
+date +%T
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread 2>&1 | tail -6 > gpurun_out/${T}_gpu_tests.log; cat gpurun_out/${T}_gpu_tests.log
+date +%T
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; tail -2 gpurun_out/${T}_bench.err
+date +%T
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${T}_ncu_bench.log 2>&1
+date +%T
+timeout 300 ncu --set full --import-source on --clock-control none -k "regex:deform_pf|transform_kernel|hash_fwd_pairs" -s 6 -c 3 -o gpurun_out/${T}_headline python tools/prof_deform.py 1700 > gpurun_out/${T}_ncu_headline.log 2>&1; tail -2 gpurun_out/${T}_ncu_headline.log
+date +%T
+python - <<PY
 import json
-j=json.load(open("gpurun_out/bench_default_v14.json")); print("%.1f M/s"%(j["value"]/1e6), j["kernels_ms"], "e2e %.1f"%(j["e2e"]["value"]/1e6), "render", j["render"]["ms_per_frame"], "train", j["train_step"]["ms_per_step"], "roof", j["roofline"]["frac"])
-v=json.load(open("gpurun_out/vs_ref_cuda_v14.json")); print(v["speedup"])
+j=json.loads(open("gpurun_out/${T}_bench.json").read().strip().splitlines()[-1])
+print("%.1f M/s"%(j["value"]/1e6), "ms/step %.3f"%j["ms_per_step"], j["kernels_ms"], "e2e %.1f M/s"%(j["e2e"]["value"]/1e6), "roof", j["roofline"]["frac"], "launches", j["gpu_launches"], j["clocks"])
+for k in ("network","render","train_step","speedup_vs_ref_cuda"):
+    v=j.get(k)
+    if isinstance(v,dict): print(k, {a:b for a,b in v.items() if not isinstance(b,(list,dict,str))})
 PY
