@@ -91,6 +91,35 @@ def test_backward_against_exact_sum(gpu_ctx, oracle, layout):
     assert np.abs(got2[big] / want[big] - 2).max() < 0.05
 
 
+@pytest.mark.parametrize("n", [1, 3, 63, 65, 4097, 4099])
+def test_backward_ragged_sizes(gpu_ctx, oracle, layout, n):
+    """The scatter kernel's lanes take four consecutive samples each and read dL/dy eight bytes at a time when the row pitch allows it: sizes that are not a multiple
+    of 4 (scalar loads), a single sample, one sample past a 64-sample tile.  Against the exact fp64 sum like the test above."""
+    import torch
+
+    pos = positions(n, 3)
+    rng = np.random.default_rng(80 + n)
+    dy = (rng.standard_normal((128, n)) * 0.02).astype(np.float16)
+    grad = torch.full((int(layout[0][-1]), 8), -1.0, dtype=torch.float16, device="cuda")
+    gpu_ctx.hash_encode_bwd(torch.from_numpy(pos).cuda(), torch.from_numpy(dy).cuda(), grad, zero_first=True)
+    want, hits = oracle.grid_backward(pos, 3, layout, dy, want_hits=True)
+    got = grad.cpu().numpy().astype(np.float64)
+    assert (got[hits == 0] == 0).all() and (np.abs(got[hits > 0]).sum(axis=1) > 0).mean() > 0.9  # the touched entries, and only those (a tiny product may underflow fp16)
+    mag = np.maximum(np.abs(want), 1e-3)
+    bound = (np.maximum(hits, 1)[:, None] ** 0.5) * mag * 2.0 ** -10 * 4 + 1e-6
+    assert (np.abs(got - want) <= bound).mean() > 0.999
+    assert np.abs(got - want).max() < 0.05 * max(np.abs(want).max(), 1e-3)
+
+
+def test_scatter_microbenchmark_runs(gpu_ctx):
+    """insta_microbench_scatter (the reduction twin of the gather roofline): a positive figure, argument checks."""
+    g16 = gpu_ctx.microbench_scatter(1 << 22, 16, iters=1)
+    g32 = gpu_ctx.microbench_scatter(1 << 22, 32, iters=1)
+    assert g16 > 10 and g32 > 10
+    with pytest.raises(Exception):
+        gpu_ctx.microbench_scatter(1 << 22, 24)
+
+
 def test_full_size_forward_properties(gpu_ctx, oracle, layout):
     """4,194,304 samples: subsample against the oracle + two size-independent properties (a sample's encoding does not
     depend on its neighbours in the batch; a table of constant c encodes to ~c everywhere)."""
