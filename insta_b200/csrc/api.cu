@@ -354,6 +354,7 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	tracer_destroy(ctx);
 	recorder_destroy(ctx);
 	network_bwd_destroy(ctx);
+	if (ctx->d_adam_lr_table) cudaFree(ctx->d_adam_lr_table);
 	trainer_destroy(ctx);
 	comm_destroy(ctx);
 	occupancy_destroy(ctx);

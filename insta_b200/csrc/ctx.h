@@ -192,6 +192,7 @@ struct insta_ctx {
 	std::mutex mu;
 	void* tracer = nullptr;           // insta::Tracer (nerf.cu)
 	void* bwd_scratch = nullptr;      // insta::BwdScratch (mlp_bwd.cu)
+	float* d_adam_lr_table = nullptr; // bias-corrected learning rate per parameter step count (train.cu optimizer_step), kAdamLrTable floats
 	void* d_train_images = nullptr;   // insta::ImageDev[n_train_images] (train.cu)
 	uint32_t n_train_images = 0;
 	void* trainer = nullptr;          // insta::Trainer (trainer.cu)
