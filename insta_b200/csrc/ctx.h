@@ -243,7 +243,8 @@ int launch_network_fwd_bwd(insta_ctx* ctx, const float* d_records, uint32_t stri
 // train.cu
 void pcg_seed(uint64_t seed, uint64_t advance_steps, uint64_t& state, uint64_t& inc);  // pcg32{seed} advanced `advance_steps` x advance()
 int training_set_images(insta_ctx* ctx, const insta_train_image* h, uint32_t n);
-int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s);
+int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s, bool emit = true);
+int train_emit_round(insta_ctx* ctx, const insta_train_step* t, const uint32_t* d_index, const uint32_t* d_count, uint32_t bound, cudaStream_t s);
 int train_round(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out, uint32_t out_width, uint32_t prev_lo, uint32_t prev_hi, uint32_t lo, uint32_t hi,
                 float* d_ray_T, uint32_t* d_index, uint32_t* d_count, cudaStream_t s);
 int train_loss(insta_ctx* ctx, const insta_train_step* t, const void* d_net_out, uint32_t out_width, float* d_coords_compacted, void* d_dloss, float* d_loss,

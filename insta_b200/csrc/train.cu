@@ -82,6 +82,8 @@ struct GenArgs {
 	uint32_t* ray_indices;
 	float* rays;       // 6 floats per accepted ray
 	uint32_t* numsteps;  // (count, base) per accepted ray
+	const uint32_t* emit_index;  // train_emit_kernel<true>: the records to expand (a round's list) ...
+	const uint32_t* emit_count;  // ... and how many
 };
 
 __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
@@ -184,19 +186,24 @@ __global__ void __launch_bounds__(128) train_generate_kernel(const GenArgs a) {
 
 // Expands (t, ray slot) into the NerfCoordinate records (testbed_nerf.cu:1262-1272).  A warp owns 32 consecutive records: every lane
 // computes the fields of one sample, the 32 x stride floats leave through shared memory as full-line stores.
+// INDEXED: only the records a round of insta_train_nerf is about to evaluate (emit_index / emit_count: the list train_round_kernel wrote).  The loss kernel, the
+// compaction and the backward pass never read a sample behind the one where a ray became opaque, and with a trained model that is most of them: expanding
+// all 2.6 M generated samples cost 280 MB of record writes per step for 0.9 M that are read.
 constexpr uint32_t kEmitWarps = 4;
+template <bool INDEXED>
 __global__ void __launch_bounds__(kEmitWarps * 32) train_emit_kernel(const GenArgs a) {
 	extern __shared__ float emit_smem[];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 	float* tile = emit_smem + (size_t)warp * 32u * a.stride;
-	const uint32_t n = min(*a.numsteps_counter, a.max_samples);
+	const uint32_t n = INDEXED ? min(*a.emit_count, a.max_samples) : min(*a.numsteps_counter, a.max_samples);
 	const uint32_t first = (blockIdx.x * kEmitWarps + warp) * 32u;
 	if (first >= n) return;
 	const uint32_t cnt = min(32u, n - first);
 	float* rec0 = a.coords + (size_t)first * a.stride;
+	const uint32_t my_id = INDEXED ? (lane < cnt ? a.emit_index[first + lane] : 0u) : first + lane;
 	bool valid = false;
 	if (lane < cnt) {
-		const float* rec = rec0 + (size_t)lane * a.stride;
+		const float* rec = a.coords + (size_t)my_id * a.stride;
 		const float t = rec[0];
 		const uint32_t ray_idx = reinterpret_cast<const uint32_t*>(rec)[1];
 		valid = ray_idx != 0xffffffffu;
@@ -229,6 +236,15 @@ __global__ void __launch_bounds__(kEmitWarps * 32) train_emit_kernel(const GenAr
 	}
 	const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
 	__syncwarp();
+	if (INDEXED) {
+		// the list holds runs of a ray's consecutive samples, not one contiguous range: one record (stride contiguous floats) per store instruction
+		for (uint32_t r = 0; r < cnt; ++r) {
+			const uint32_t id = __shfl_sync(0xffffffffu, my_id, r);
+			if ((vmask >> r) & 1u)
+				for (uint32_t k = lane; k < a.stride; k += 32) a.coords[(size_t)id * a.stride + k] = tile[(size_t)r * a.stride + k];
+		}
+		return;
+	}
 	if (vmask == (cnt == 32u ? 0xffffffffu : ((1u << cnt) - 1u))) {
 		for (uint32_t k = lane; k < cnt * a.stride; k += 32) rec0[k] = tile[k];
 	} else {
@@ -694,7 +710,7 @@ void pcg_seed(uint64_t seed, uint64_t advance_steps, uint64_t& state, uint64_t& 
 	}
 }
 
-int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s) {
+static GenArgs gen_args(insta_ctx* ctx, const insta_train_step* t) {
 	GenArgs a{};
 	a.n_rays = t->n_rays;
 	a.n_rays_total = t->n_rays_total;
@@ -715,14 +731,38 @@ int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s) {
 	a.ray_indices = t->d_ray_indices;
 	a.rays = t->d_rays;
 	a.numsteps = t->d_numsteps;
+	return a;
+}
+
+// emit = false: the records stay (ray parameter, ray slot) pairs; insta_train_nerf expands them round by round (train_emit_round)
+int train_generate(insta_ctx* ctx, const insta_train_step* t, cudaStream_t s, bool emit) {
+	const GenArgs a = gen_args(ctx, t);
 	INSTA_CUDA(cudaMemsetAsync(t->d_counters, 0, 3 * sizeof(uint32_t), s));
 	if (a.n_rays == 0) return INSTA_OK;
 	train_generate_kernel<<<(a.n_rays + 127) / 128, 128, 0, s>>>(a);
-	// the sample count is only known on the device: the emit grid covers the capacity, warps past the count exit at once
+	ctx->launches++;
+	if (emit) {
+		// the sample count is only known on the device: the emit grid covers the capacity, warps past the count exit at once
+		const size_t emit_smem = (size_t)kEmitWarps * 32u * a.stride * sizeof(float);
+		if (emit_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(train_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+		train_emit_kernel<false><<<(a.max_samples + kEmitWarps * 32 - 1) / (kEmitWarps * 32), kEmitWarps * 32, emit_smem, s>>>(a);
+		ctx->launches++;
+	}
+	INSTA_CUDA(cudaGetLastError());
+	return INSTA_OK;
+}
+
+// the records of one round's list (d_index[0 .. *d_count), at most `bound`)
+int train_emit_round(insta_ctx* ctx, const insta_train_step* t, const uint32_t* d_index, const uint32_t* d_count, uint32_t bound, cudaStream_t s) {
+	if (t->n_rays == 0 || bound == 0) return INSTA_OK;
+	GenArgs a = gen_args(ctx, t);
+	a.emit_index = d_index;
+	a.emit_count = d_count;
+	a.max_samples = bound;
 	const size_t emit_smem = (size_t)kEmitWarps * 32u * a.stride * sizeof(float);
-	if (emit_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(train_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
-	train_emit_kernel<<<(a.max_samples + kEmitWarps * 32 - 1) / (kEmitWarps * 32), kEmitWarps * 32, emit_smem, s>>>(a);
-	ctx->launches += 2;
+	if (emit_smem > 48 * 1024) INSTA_CUDA(cudaFuncSetAttribute(train_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+	train_emit_kernel<true><<<(bound + kEmitWarps * 32 - 1) / (kEmitWarps * 32), kEmitWarps * 32, emit_smem, s>>>(a);
+	ctx->launches++;
 	INSTA_CUDA(cudaGetLastError());
 	return INSTA_OK;
 }

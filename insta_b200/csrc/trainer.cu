@@ -511,7 +511,9 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 
 	auto mark = [&](int k) { if (t->profile) cudaEventRecord(t->pev[k], s); };
 	mark(0);
-	int rc = train_generate(ctx, &st, s);
+	// with lazily evaluated rounds the generator leaves (ray parameter, ray slot) pairs and every round expands the records it is about to evaluate
+	const bool lazy_rounds = !(ctx->train_all_samples || !deform_supports_index(ctx));
+	int rc = train_generate(ctx, &st, s, /*emit=*/!lazy_rounds);
 	if (rc) return rc;
 	mark(1);
 	// rta::Core::surface_closest_point on the generated records (testbed_nerf.cu:3290), then the network on the same records (3292)
@@ -537,6 +539,8 @@ int train_nerf(insta_ctx* ctx, const insta_optimizer* opt, const void* d_bitfiel
 			if (rc) return rc;
 			// upper bound of the round's size for the launch geometry; the kernels read the real count on the device
 			const uint64_t bound = edges[r + 1] != 0xffffffffu ? std::min<uint64_t>((uint64_t)n_rays * (edges[r + 1] - edges[r]), st.max_samples) : st.max_samples;
+			rc = train_emit_round(ctx, &st, t->round_index, t->round_count + r, (uint32_t)bound, s);
+			if (rc) return rc;
 			rc = launch_deform(ctx, t->coords, (uint32_t)bound, stride, -1, nullptr, false, nullptr, s, t->round_count + r, false, false, t->round_index);
 			if (rc) return rc;
 			rc = launch_network_fwd(ctx, t->coords, stride, (uint32_t)bound, opt->d_params_f16, t->mlp_out, 0, s, t->round_count + r, nullptr, t->round_index);
