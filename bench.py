@@ -30,8 +30,8 @@ BYTES_ENCODE = 2316
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the 4,194,304-sample batch, from `ncu --set full` captures of THIS command's configuration
 # (1,700 frames; profiles/r2_deform_ncu_summary.txt: deform_pf_kernel + transform_kernel, profiles/r2_hash_fwd_ncu_summary.txt; tools/ncu_summary.py adds
 # the two counters in bytes)
-NCU_TRAFFIC_BYTES = {"deform_kernel": 1788951832 + 1182424280, "hash_fwd_kernel": 1585464640}  # deform = deform_pf_kernel + transform_kernel
-NCU_TRAFFIC_SOURCE = {"deform_kernel": "profiles/r2_deform_ncu_summary.txt", "hash_fwd_kernel": "profiles/r2_hash_fwd_ncu_summary.txt"}
+NCU_TRAFFIC_BYTES = {"deform_kernel": 1608628104 + 1182040616, "hash_fwd_kernel": 1585464640}  # deform = deform_pf_kernel + transform_kernel
+NCU_TRAFFIC_SOURCE = {"deform_kernel": "profiles/r2_final_deform_ncu_summary.txt", "hash_fwd_kernel": "profiles/r2_hash_fwd_ncu_summary.txt"}
 METRIC = "deformed+encoded samples/s (BVH+TBN+hash)"
 UNIT = "samples/s"
 
@@ -455,7 +455,7 @@ def run_ours(args):
                          "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "ncu --set full of this configuration, %s" % NCU_TRAFFIC_SOURCE.get(dom),
                          "algorithmic_bytes": dom_bytes, "algorithmic_bytes_per_sample": dom_bytes // N_SAMPLES,
                          "note": ("stage 1 = deform_pf_kernel (closest triangle) + transform_kernel (TBN): bound by instruction issue and the LSU / shared-memory pipe, "
-                                  "not by HBM (ncu: profiles/r2_deform_ncu_summary.txt); traffic = the record buffer read twice + written once; the 1,012 algorithmic "
+                                  "not by HBM (ncu: profiles/r2_final_deform_ncu_summary.txt); traffic = the record buffer read twice + written once; the 1,012 algorithmic "
                                   "bytes are mostly BVH node / triangle gathers served by L2 (see l2_gather_roofline)") if dom == "deform_kernel" else
                                  "hash_fwd_kernel is bound by L1 gather wavefronts (16-byte entries from the L2-resident table), see l2_gather_roofline",
                          "step_algorithmic_gbs": (BYTES_DEFORM + BYTES_ENCODE) * N_SAMPLES / (float(step_ms.mean()) * 1e-3) / 1e9},

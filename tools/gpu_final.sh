@@ -9,7 +9,7 @@ timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_benc
 date +%T
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${T}_ncu_bench.log 2>&1
 date +%T
-timeout 300 ncu --set full --import-source on --clock-control none -k "regex:deform_pf|transform_kernel|hash_fwd_pairs" -s 6 -c 3 -o gpurun_out/${T}_headline python tools/prof_deform.py 1700 > gpurun_out/${T}_ncu_headline.log 2>&1; tail -2 gpurun_out/${T}_ncu_headline.log
+timeout 300 ncu --set full --import-source on --clock-control none -k "regex:deform_pf|transform_kernel" -s 6 -c 3 -o gpurun_out/${T}_headline python tools/prof_deform.py 1700 > gpurun_out/${T}_ncu_headline.log 2>&1; tail -2 gpurun_out/${T}_ncu_headline.log
 date +%T
 python - <<PY
 import json
