@@ -647,6 +647,8 @@ def train_leg(ctx, verts, fv, args, rank, world, ref_hook=None):
     # step and every rank count does the same work (rays beyond the 16 x 2^18-sample workspace are dropped by the generator, as in the reference) ----
     fixed = {}
     modes = ("overlap", "serial", "none") if world > 1 else ("none",)
+    if world > 1 and os.environ.get("INSTA_BENCH_P2P"):  # opt-in: this library's own reduce kernel over peer memory (trainer.cu peer_exchange_run)
+        modes = ("p2p",) + modes
     for mode in modes:
         os.environ["INSTA_GRAD_EXCHANGE"] = mode
         ctx.trainer_create(target_batch_size=1 << 18, rays_per_batch=1 << 18, fixed_rays_per_batch=1 << 18, freeze_parameters=1, depth_weight=1.25, seg_weight=40.0)
