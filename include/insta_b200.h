@@ -525,6 +525,21 @@ INSTA_API int insta_snapshot_save(const char* path, const insta_params* p, const
 INSTA_API int insta_snapshot_open(const char* path, insta_snapshot_file** file, insta_snapshot* s);
 INSTA_API void insta_snapshot_close(insta_snapshot_file* file);
 
+/* rta::Core::raycast_flame (src/core.cu:350-402): the shaded FLAME mesh drawn into the frame buffer -- the viewer's / recorder's mesh overlay.
+ * One ray per pixel through the pixel centre (SphereTracer::init_rays_from_camera, ngp src/testbed_sdf.cu:493-577: normalised, advanced to the render box),
+ * first hit on the mesh of frame `frame_id` (>= 0: m_meshes[frame], the `m_render_deformed` case; -1: m_canonical_shape) with the reference's BVH traversal
+ * (SphereTracer::trace_bvh -> raytrace_kernel -> TriangleBvh4::ray_intersect, ngp src/triangle_bvh.cu:271-312, 721-738; rays start with mint = MAX_DIST = 10),
+ * shading as shade_kernel_sdf (src/core.cu:74-109): color_normal = Core::m_raycast_normal (0: three fixed lights around the canonical mesh's centroid, 1: the
+ * normal as a colour), alpha 1, depth = z of the hit.  d_frame_depth is set to 1e10 for every pixel first, like the reference; pixels without a hit keep
+ * their colour.  Render box: the canonical mesh's (insta_set_canonical) unless opts->use_render_aabb.  cam->snap_to_pixel_centers must be 1. */
+INSTA_API int insta_raycast_mesh(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, int color_normal, float* d_frame_rgba,
+                                 float* d_frame_depth, insta_stream stream);
+/* TriangleBvh::ray_trace_gpu (ngp src/triangle_bvh.cu:495-512) as a query: n rays (origin, direction: 3 floats each, directions as given), d_tri_ids[i] = topology
+ * id of the first triangle hit within MAX_DIST = 10 (-1: none), d_t[i] (nullable) = the ray parameter (10 when nothing is hit).  Same traversal order and
+ * IEEE arithmetic as the reference's host build: ids and t are bit-exact against it (tests/test_gpu_raycast.py). */
+INSTA_API int insta_mesh_ray_intersect(insta_ctx* ctx, int32_t frame_id, const float* d_origins, const float* d_dirs, uint32_t n, int32_t* d_tri_ids, float* d_t,
+                                       insta_stream stream);
+
 /* Measurement aid (not on the hot path): bandwidth of fully divergent gathers of chunk_bytes (16 = one hash-table entry, 128 = one BVH quad
  * read by 8 cooperating lanes) from an internal buffer of buffer_bytes -- L2-resident when it fits the 126 MB L2, HBM-bound otherwise.
  * Best of `iters` launches after warm-up, GB/s of gathered bytes.  bench.py reports it as the L2-gather roofline. */

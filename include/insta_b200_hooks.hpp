@@ -95,6 +95,13 @@ public:
 		return st;
 	}
 
+	// rta::Core::raycast_flame (src/core.cu:350-402; called from Testbed::render_frame, ngp/src/testbed.cu:2626-2628): the shaded mesh overlay.
+	// render_deformed / target_deform_frame / raycast_normal = Core::m_render_deformed / m_target_deform_frame / m_raycast_normal
+	void raycast_flame(const insta_camera& cam, const insta_render_opts& opts, bool render_deformed, uint32_t target_deform_frame, bool raycast_normal, float* d_frame_rgba,
+	                   float* d_frame_depth, void* stream) {
+		check(insta_raycast_mesh(m_ctx, &cam, &opts, render_deformed ? (int32_t)target_deform_frame : -1, raycast_normal ? 1 : 0, d_frame_rgba, d_frame_depth, stream));
+	}
+
 	// rta::Recorder::dump_frame_buffer (src/recorder.cu:299-359): the frame as the recorder stores it, converted on the GPU; host buffers valid after the
 	// caller's next stream synchronisation
 	void read_back_frame(const float* d_frame_rgba, const float* d_frame_depth, uint32_t width, uint32_t height, bool normals_mode, uint8_t* h_rgba8,

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libinsta_b200.so")
-SOURCES = ["api.cu", "deform.cu", "hashgrid.cu", "nerf.cu", "mlp.cu", "mlp_bwd.cu", "train.cu", "trainer.cu", "occupancy.cu", "microbench.cu", "recorder.cu", "mesh_host.cpp", "snapshot.cpp"]
+SOURCES = ["api.cu", "deform.cu", "hashgrid.cu", "nerf.cu", "mlp.cu", "mlp_bwd.cu", "train.cu", "trainer.cu", "occupancy.cu", "microbench.cu", "recorder.cu", "raycast.cu", "mesh_host.cpp", "snapshot.cpp"]
 HEADERS = ["ctx.h", "grid_device.cuh", "nerf_device.cuh", "umma.cuh", os.path.join("..", "..", "include", "insta_b200.h")]
 
 

@@ -139,7 +139,7 @@ EXPORTS = [
     "insta_trainer_config_default", "insta_trainer_create", "insta_trainer_destroy", "insta_trainer_state", "insta_train_nerf",
     "insta_update_density_grid", "insta_training_prep_nerf", "insta_update_density_grid_mean_and_bitfield",
     "insta_replace_frames", "insta_refit_frames", "insta_host_write_trajectory_json", "insta_shard_frame_count", "insta_shard_owner", "insta_shard_local_ids",
-    "insta_microbench_gather", "insta_microbench_scatter", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
+    "insta_microbench_gather", "insta_microbench_scatter", "insta_raycast_mesh", "insta_mesh_ray_intersect", "insta_snapshot_save", "insta_snapshot_open", "insta_snapshot_close",
     "insta_comm_unique_id", "insta_comm_init_rank", "insta_comm_destroy", "insta_comm_exchange_mode", "insta_grad_allreduce",
     "insta_render_frame", "insta_tracer_init_rays", "insta_tracer_n_steps", "insta_tracer_generate_samples", "insta_tracer_composite",
 ]
@@ -603,6 +603,19 @@ class Context:
         g = C.c_float(0)
         self._check(self.lib.insta_microbench_gather(self.h, C.c_uint64(buffer_bytes), C.c_uint32(chunk_bytes), C.c_uint32(iters), C.byref(g), _stream(None)))
         return float(g.value)
+
+    def mesh_ray_intersect(self, origins, dirs, tri_ids, t=None, frame_id=-1, stream=None):
+        """origins / dirs: float32 [n, 3] device tensors; tri_ids int32 [n] (topology id of the first hit, -1 = none); t float32 [n] or None."""
+        n = origins.shape[0]
+        self._check(self.lib.insta_mesh_ray_intersect(self.h, C.c_int32(frame_id), _dev(origins), _dev(dirs), C.c_uint32(n), _dev(tri_ids), _dev(t), _stream(stream)))
+
+    def raycast_mesh(self, cam, frame_rgba, frame_depth, frame_id=-1, color_normal=False, render_aabb=None, stream=None):
+        """rta::Core::raycast_flame: the shaded mesh of frame `frame_id` (-1 = canonical) into frame_rgba [h, w, 4] / frame_depth [h, w] (float32, device)."""
+        o = RenderOpts()
+        o.use_render_aabb = int(render_aabb is not None)
+        for k in range(6):
+            o.render_aabb[k] = float(render_aabb[k]) if render_aabb is not None else 0.0
+        self._check(self.lib.insta_raycast_mesh(self.h, C.byref(cam), C.byref(o), C.c_int32(frame_id), C.c_int(int(color_normal)), _dev(frame_rgba), _dev(frame_depth), _stream(stream)))
 
     def microbench_scatter(self, buffer_bytes, chunk_bytes=16, iters=5):
         """GB/s of fully divergent 16-byte fp16 vector reductions into a buffer of buffer_bytes (chunk_bytes 32 / 64: 2 / 4 adjacent lanes on adjacent entries)."""

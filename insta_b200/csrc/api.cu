@@ -355,6 +355,8 @@ void insta_ctx_destroy(insta_ctx* ctx) {
 	recorder_destroy(ctx);
 	network_bwd_destroy(ctx);
 	if (ctx->d_adam_lr_table) cudaFree(ctx->d_adam_lr_table);
+	if (ctx->d_canon_quads) cudaFree(ctx->d_canon_quads);
+	if (ctx->d_canon_tris_bvh) cudaFree(ctx->d_canon_tris_bvh);
 	trainer_destroy(ctx);
 	comm_destroy(ctx);
 	occupancy_destroy(ctx);
@@ -380,6 +382,18 @@ int insta_set_canonical(insta_ctx* ctx, const float* h_verts, uint32_t n_verts, 
 	ctx->n_verts = n_verts;
 	ctx->n_faces = n_faces;
 	ctx->canon_verts.assign(h_verts, h_verts + (size_t)n_verts * 3);
+	{
+		// TinyMesh::m_centorid (tiny_mesh.cu:64-86): the vertices summed in file order in single precision, divided by their number; a new canonical mesh also
+		// invalidates its ray-casting BVH (raycast.cu)
+		float c[3] = {0.f, 0.f, 0.f};
+		for (uint32_t i = 0; i < n_verts; ++i)
+			for (int d = 0; d < 3; ++d) c[d] += h_verts[3 * (size_t)i + d];
+		for (int d = 0; d < 3; ++d) ctx->canon_centroid[d] = c[d] / (float)n_verts;
+		if (ctx->d_canon_quads) cudaFree(ctx->d_canon_quads);
+		if (ctx->d_canon_tris_bvh) cudaFree(ctx->d_canon_tris_bvh);
+		ctx->d_canon_quads = nullptr;
+		ctx->d_canon_tris_bvh = nullptr;
+	}
 	ctx->faces.assign(h_faces, h_faces + (size_t)n_faces * 3);
 	if (h_mask_ids) ctx->mask_ids.assign(h_mask_ids, h_mask_ids + n_faces);
 	else ctx->mask_ids.assign(n_faces, 15u);
@@ -912,6 +926,63 @@ int insta_microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chun
 	if (!ctx || !h_gbs || iters == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_microbench_gather: bad arguments");
 	INSTA_CUDA(cudaSetDevice(ctx->device));
 	return microbench_gather(ctx, buffer_bytes, chunk_bytes, iters, h_gbs, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Mesh ray casting: the FLAME overlay (raycast.cu)
+static int mesh_of(insta_ctx* ctx, int32_t frame_id, const Quad** quads, const Tri** tris, const char* who) {
+	if (ctx->n_faces == 0) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": no canonical mesh (insta_set_canonical)");
+	if (frame_id >= 0) {
+		if ((size_t)frame_id >= ctx->frames.size()) INSTA_FAIL(INSTA_ERR_INVALID, std::string(who) + ": frame_id out of range");
+		*quads = ctx->frames[frame_id].dev.quads;
+		*tris = ctx->frames[frame_id].dev.tris;
+		return INSTA_OK;
+	}
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (!ctx->d_canon_quads) {
+		// m_canonical_shape->triangle_bvh (TinyMesh::build_tries, tiny_mesh.cu:134-178): the same host build as a frame's
+		std::vector<Tri> tris_h(ctx->canon_tris);
+		HostBvh bvh;
+		build_bvh(tris_h, ctx->p.n_primitives_per_leaf, bvh);
+		Quad* dq = nullptr;
+		Tri* dt = nullptr;
+		INSTA_CUDA(cudaMalloc(&dq, bvh.quads.size() * sizeof(Quad)));
+		cudaError_t e = cudaMalloc(&dt, bvh.tris.size() * sizeof(Tri));
+		if (e == cudaSuccess) e = cudaMemcpy(dq, bvh.quads.data(), bvh.quads.size() * sizeof(Quad), cudaMemcpyHostToDevice);
+		if (e == cudaSuccess) e = cudaMemcpy(dt, bvh.tris.data(), bvh.tris.size() * sizeof(Tri), cudaMemcpyHostToDevice);
+		if (e != cudaSuccess) {
+			cudaFree(dq);
+			if (dt) cudaFree(dt);
+			INSTA_CUDA(e);
+		}
+		ctx->d_canon_quads = dq;
+		ctx->d_canon_tris_bvh = dt;
+	}
+	*quads = ctx->d_canon_quads;
+	*tris = ctx->d_canon_tris_bvh;
+	return INSTA_OK;
+}
+
+int insta_mesh_ray_intersect(insta_ctx* ctx, int32_t frame_id, const float* d_origins, const float* d_dirs, uint32_t n, int32_t* d_tri_ids, float* d_t, insta_stream stream) {
+	if (!ctx || !d_origins || !d_dirs || !d_tri_ids) INSTA_FAIL(INSTA_ERR_INVALID, "insta_mesh_ray_intersect: bad arguments");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	const Quad* quads = nullptr;
+	const Tri* tris = nullptr;
+	if (int rc = mesh_of(ctx, frame_id, &quads, &tris, "insta_mesh_ray_intersect")) return rc;
+	return launch_mesh_ray_intersect(ctx, quads, tris, d_origins, d_dirs, n, d_tri_ids, d_t, (cudaStream_t)stream);
+}
+
+int insta_raycast_mesh(insta_ctx* ctx, const insta_camera* cam, const insta_render_opts* opts, int32_t frame_id, int color_normal, float* d_frame_rgba, float* d_frame_depth,
+                       insta_stream stream) {
+	if (!ctx || !cam || !d_frame_rgba || !d_frame_depth) INSTA_FAIL(INSTA_ERR_INVALID, "insta_raycast_mesh: bad arguments");
+	if (cam->resolution[0] == 0 || cam->resolution[1] == 0) INSTA_FAIL(INSTA_ERR_INVALID, "insta_raycast_mesh: empty resolution");
+	if (!cam->snap_to_pixel_centers) INSTA_FAIL(INSTA_ERR_INVALID, "insta_raycast_mesh: the overlay is drawn through pixel centres (snap_to_pixel_centers = 1)");
+	INSTA_CUDA(cudaSetDevice(ctx->device));
+	const Quad* quads = nullptr;
+	const Tri* tris = nullptr;
+	if (int rc = mesh_of(ctx, frame_id, &quads, &tris, "insta_raycast_mesh")) return rc;
+	const float* aabb = opts && opts->use_render_aabb ? opts->render_aabb : ctx->render_aabb;
+	return launch_mesh_overlay(ctx, cam, aabb, ctx->canon_centroid, color_normal, quads, tris, d_frame_rgba, d_frame_depth, (cudaStream_t)stream);
 }
 
 int insta_microbench_scatter(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, insta_stream stream) {

@@ -192,6 +192,9 @@ struct insta_ctx {
 	std::mutex mu;
 	void* tracer = nullptr;           // insta::Tracer (nerf.cu)
 	void* bwd_scratch = nullptr;      // insta::BwdScratch (mlp_bwd.cu)
+	insta::Quad* d_canon_quads = nullptr;  // BVH of the canonical mesh, built at the first insta_raycast_mesh / insta_mesh_ray_intersect with frame_id < 0 (raycast.cu)
+	insta::Tri* d_canon_tris_bvh = nullptr;
+	float canon_centroid[3] = {0, 0, 0};   // TinyMesh::m_centorid (tiny_mesh.cu:64-86): mean of the canonical vertices
 	float* d_adam_lr_table = nullptr; // bias-corrected learning rate per parameter step count (train.cu optimizer_step), kAdamLrTable floats
 	void* d_train_images = nullptr;   // insta::ImageDev[n_train_images] (train.cu)
 	uint32_t n_train_images = 0;
@@ -256,6 +259,11 @@ struct SnapshotFile;
 int snapshot_save(const char* path, const insta_params* p, const insta_snapshot* s);
 int snapshot_open(const char* path, SnapshotFile** out_file, insta_snapshot* s);
 void snapshot_close(SnapshotFile* f);
+// raycast.cu
+int launch_mesh_ray_intersect(insta_ctx* ctx, const Quad* quads, const Tri* tris, const float* d_origins, const float* d_dirs, uint32_t n, int32_t* d_tri_ids, float* d_t,
+                              cudaStream_t s);
+int launch_mesh_overlay(insta_ctx* ctx, const insta_camera* cam, const float* aabb, const float* center, int color_normal, const Quad* quads, const Tri* tris, float* d_rgba,
+                        float* d_depth, cudaStream_t s);
 // microbench.cu
 int microbench_gather(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, cudaStream_t s);
 int microbench_scatter(insta_ctx* ctx, uint64_t buffer_bytes, uint32_t chunk_bytes, uint32_t iters, float* h_gbs, cudaStream_t s);

@@ -160,6 +160,67 @@ inline int closest_tri(V3 p, const orc_node* nodes, const orc_tri* tris, float* 
 	return best_i;
 }
 
+// ---- the mesh ray cast of rta::Core::raycast_flame (src/core.cu:350-402) ------------------------------------------------------------------
+// BoundingBox::ray_intersect(pos, dir).x()  (ngp bounding_box.cuh:163-205): entry parameter of the slab test, FLT_MAX on a miss
+inline float box_ray_tmin(const float* mn, const float* mx, V3 o, V3 d) {
+	float tmin = (mn[0] - o.x) / d.x, tmax = (mx[0] - o.x) / d.x;
+	if (tmin > tmax) std::swap(tmin, tmax);
+	float tymin = (mn[1] - o.y) / d.y, tymax = (mx[1] - o.y) / d.y;
+	if (tymin > tymax) std::swap(tymin, tymax);
+	if (tmin > tymax || tymin > tmax) return std::numeric_limits<float>::max();
+	if (tymin > tmin) tmin = tymin;
+	if (tymax < tmax) tmax = tymax;
+	float tzmin = (mn[2] - o.z) / d.z, tzmax = (mx[2] - o.z) / d.z;
+	if (tzmin > tzmax) std::swap(tzmin, tzmax);
+	if (tmin > tzmax || tzmin > tmax) return std::numeric_limits<float>::max();
+	if (tzmin > tmin) tmin = tzmin;
+	return tmin;
+}
+// Triangle::ray_intersect  (ngp triangle.cuh:66-81)
+inline float tri_ray_t(const orc_tri& t, V3 ro, V3 rd) {
+	V3 v1v0 = v3(t.b) - v3(t.a), v2v0 = v3(t.c) - v3(t.a), rov0 = ro - v3(t.a);
+	V3 n = cross(v1v0, v2v0), q = cross(rov0, rd);
+	float d = 1.0f / dot(rd, n);
+	float u = d * -dot(q, v2v0), v = d * dot(q, v1v0), tt = d * -dot(n, rov0);
+	if (u < 0.0f || u > 1.0f || v < 0.0f || (u + v) > 1.0f || tt < 0.0f) tt = std::numeric_limits<float>::max();
+	return tt;
+}
+// TriangleBvh4::ray_intersect  (ngp src/triangle_bvh.cu:271-312; INSTA's header copy of the same loop: ngp bvh.cuh:98-144); mint starts at MAX_DIST = 10
+// (triangle_bvh.cu:49).  Returns the BVH-order index of the first hit, -1 = none.
+inline int ray_tri(V3 ro, V3 rd, const orc_node* nodes, const orc_tri* tris, float* t_out) {
+	int stack[64];
+	int sp = 0;
+	stack[sp++] = 0;
+	float mint = 10.0f;
+	int best = -1;
+	while (sp > 0) {
+		int idx = stack[--sp];
+		const orc_node& nd = nodes[idx];
+		if (nd.left_idx < 0) {
+			int end = -nd.right_idx - 1;
+			for (int i = -nd.left_idx - 1; i < end; ++i) {
+				float t = tri_ray_t(tris[i], ro, rd);
+				if (t < mint) { mint = t; best = i; }
+			}
+		} else {
+			float cd[4];
+			uint32_t ci[4];
+			for (uint32_t k = 0; k < 4; ++k) {
+				cd[k] = box_ray_tmin(nodes[nd.left_idx + k].mn, nodes[nd.left_idx + k].mx, ro, rd);
+				ci[k] = nd.left_idx + k;
+			}
+			auto cas = [&](int i, int j) {  // swap iff values[i] < values[j]  (descending)
+				if (cd[i] < cd[j]) { std::swap(cd[i], cd[j]); std::swap(ci[i], ci[j]); }
+			};
+			cas(0, 2); cas(1, 3); cas(0, 1); cas(2, 3); cas(1, 2);
+			for (int k = 0; k < 4; ++k)
+				if (cd[k] < mint && sp < 63) stack[sp++] = (int)ci[k];
+		}
+	}
+	if (t_out) *t_out = mint;
+	return best;
+}
+
 // triangle.cuh:43-57 ; 3x3 column-major (col0 tangent, col1 bitangent, col2 normal)
 inline void tbn(const orc_tri& tr, float* m9) {
 	V3 t = v3(tr.b) - v3(tr.a);
@@ -546,6 +607,15 @@ void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const 
 	}
 }
 
+
+void orc_ray_intersect(const float* ro, const float* rd, int n, const orc_node* nodes, const orc_tri* tris, int* out_idx, float* out_t) {
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; ++i) {
+		float t;
+		out_idx[i] = ray_tri(v3(ro + 3 * i), v3(rd + 3 * i), nodes, tris, &t);
+		if (out_t) out_t[i] = t;
+	}
+}
 
 void orc_closest_triangle_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, int* out_idx, int n_threads) {
 #pragma omp parallel for schedule(static) num_threads(n_threads)

@@ -52,6 +52,8 @@ int orc_bvh_build(orc_tri* tris_inout, int n_tris, int leaf_size, orc_node* node
 void orc_closest_triangle(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, int* out_idx, float* out_dist,
                           int n_threads);
 /* closest_triangle started from max_distance_sq = init_best[i] instead of FLT_MAX (bvh.cuh:48) */
+/* TriangleBvh4::ray_intersect (ngp src/triangle_bvh.cu:271-312): first hit of n rays, BVH-order index (-1 = none within MAX_DIST = 10) and ray parameter */
+void orc_ray_intersect(const float* ro, const float* rd, int n, const orc_node* nodes, const orc_tri* tris, int* out_idx, float* out_t);
 void orc_closest_triangle_bounded(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, const float* init_best, int* out_idx, int n_threads);
 /* diagnostic: traversal statistics (see oracle.cpp) */
 void orc_closest_stats(const float* pts, int n, const orc_node* nodes, const orc_tri* tris, double* out8);

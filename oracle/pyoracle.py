@@ -68,6 +68,15 @@ class _Lib:
         self._fn("closest_triangle")(_p(pts), C.c_int(n), _p(nodes), _p(tris), _p(idx), _p(dist), C.c_int(n_threads or self.max_threads))
         return idx, dist
 
+    def ray_intersect(self, origins, dirs, nodes, tris):
+        """TriangleBvh4::ray_intersect per ray: (BVH-order index of the first hit or -1, ray parameter; 10 = MAX_DIST when nothing is hit)."""
+        ro = np.ascontiguousarray(origins, np.float32)
+        rd = np.ascontiguousarray(dirs, np.float32)
+        idx = np.empty(len(ro), np.int32)
+        t = np.empty(len(ro), np.float32)
+        self._fn("ray_intersect")(_p(ro), _p(rd), C.c_int(len(ro)), _p(nodes), _p(tris), _p(idx), _p(t))
+        return idx, t
+
     def closest_triangle_bounded(self, pts, nodes, tris, init_best, n_threads=None):
         """closest_triangle with max_distance_sq = init_best[i] (bvh.cuh:48) instead of FLT_MAX; oracle only."""
         pts = np.ascontiguousarray(pts, np.float32)

@@ -5,6 +5,7 @@
 // It exposes, unmodified:
 //   * ngp::TriangleBvh::make()/build()          instant-ngp/src/triangle_bvh.cu:548-631
 //   * closest_triangle()                        instant-ngp/include/neural-graphics-primitives/bvh.cuh:48-96
+//   * ray_intersect()                           instant-ngp/include/neural-graphics-primitives/bvh.cuh:98-144
 //   * ngp::Triangle::{distance_sq,tbn,centroid} instant-ngp/include/neural-graphics-primitives/triangle.cuh:43-107,220
 //   * tri2projection / interpolate_transformation / transform_point / transform_direction
 //                                               include/rta/affine.cuh:26-116
@@ -86,6 +87,20 @@ int ref_bvh_build(void* tris_inout, int n_tris, int leaf_size, void* nodes_out, 
 	memcpy(nodes_out, nodes, sizeof(ngp::TriangleBvhNode) * n_nodes);
 	memcpy(tris_inout, tris.data(), sizeof(ngp::Triangle) * n_tris);
 	return n_nodes;
+}
+
+// TriangleBvh4::ray_intersect (instant-ngp/src/triangle_bvh.cu:271-312, what raycast_flame's trace_bvh runs) is local to its translation unit; INSTA's header
+// copy of the same loop (include/neural-graphics-primitives/bvh.cuh:98-144) is callable and takes the start value of mint as a parameter:
+// 10 = MAX_DIST (triangle_bvh.cu:49).  Triangle::ray_intersect and BoundingBox::ray_intersect are the reference's own (triangle.cuh:66-81, bounding_box.cuh:163-205).
+void ref_ray_intersect(const float* ro, const float* rd, int n, const void* nodes, const void* tris, int* out_idx, float* out_t) {
+	const auto* N = (const ngp::TriangleBvhNode*)nodes;
+	const auto* T = (const ngp::Triangle*)tris;
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < n; ++i) {
+		auto r = ray_intersect(Vector3f(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), Vector3f(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]), N, T, 10.0f);
+		out_idx[i] = r.first;
+		if (out_t) out_t[i] = r.second;
+	}
 }
 
 void ref_closest_triangle(const float* pts, int n, const void* nodes, const void* tris, int* out_idx, float* out_dist, int n_threads) {
