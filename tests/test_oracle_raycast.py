@@ -7,9 +7,10 @@ import pytest
 from oracle import pyoracle
 from raycast_common import make_rays
 
-pytestmark = pytest.mark.skipif(not pyoracle.have_ref_host(), reason="oracle/_ref/libref_host.so not built")
+needs_ref = pytest.mark.skipif(not pyoracle.have_ref_host(), reason="oracle/_ref/libref_host.so not built")
 
 
+@needs_ref
 @pytest.mark.parametrize("frame", [0, 1])
 def test_ray_intersect_bit_exact_vs_reference_host_code(oracle, scene, frame):
     ref = pyoracle.RefHost()
@@ -24,3 +25,17 @@ def test_ray_intersect_bit_exact_vs_reference_host_code(oracle, scene, frame):
     assert (t1[hit] >= 0).all() and (t1[hit] < 10).all()
     # the tie-heavy block really produces ties: rays through shared vertices hit several triangles at (nearly) the same parameter
     assert hit[20000:20000 + 2000].mean() > 0.3
+
+
+@pytest.mark.parametrize("frame", [0, 1])
+def test_ray_intersect_against_committed_reference_outputs(oracle, scene, frame):
+    """The same pin without the reference build: tests/golden/raycast_ref.npz holds what the reference's host code returned for these rays
+    (tests/golden/make_golden_raycast.py) -- topology id of the first hit and the ray parameter, bit for bit."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "raycast_ref.npz"))
+    ro, rd = make_rays(scene, frame, n_random=4000)
+    idx, t = oracle.ray_intersect(ro, rd, scene.nodes[frame], scene.tbvh[frame])
+    ids = np.where(idx >= 0, scene.tbvh[frame]["id"][np.maximum(idx, 0)].astype(np.int64), -1)
+    assert (ids == g["tri_id_%d" % frame]).all()
+    assert (t.view(np.uint32) == g["t_%d" % frame].view(np.uint32)).all()
