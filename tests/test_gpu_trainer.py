@@ -306,7 +306,7 @@ def test_k_steps_vs_the_step_composed_from_reference_code(train_ctx, dataset, sc
         # Counters::update_after_training (testbed_nerf.cu:2889-2914)
         lsum = float(loss[:n_rays].sum())
         nxt = min((int(np.float32(n_rays) * np.float32(target) / np.float32(comp)) + 127) // 128 * 128, 1 << 18)
-        ref_hist.append(dict(n_rays=n_rays, accepted=int(cnt[0]), generated=gen, compacted=comp, next_rays=nxt, loss=lsum * comp / target))
+        ref_hist.append(dict(n_rays=n_rays, accepted=int(cnt[0]), generated=gen, compacted=comp, next_rays=nxt, loss=lsum * comp / target, capacity=int(max_inference)))
         max_inference = min((min(gen, max_samples) + 127) // 128 * 128, max_samples)
         assert comp < target, "pick fewer rays: the compacted batch must stay below the target for a deterministic comparison"
     # ---- ours ----
@@ -322,7 +322,13 @@ def test_k_steps_vs_the_step_composed_from_reference_code(train_ctx, dataset, sc
     for it, (o, r) in enumerate(zip(ours, ref_hist)):
         print("step %d ours %s | reference %s" % (it, {k: o[k] for k in ("n_rays", "n_rays_accepted", "measured_batch_size_before_compaction", "measured_batch_size", "rays_per_batch", "loss")}, r))
         assert o["n_rays"] == r["n_rays"], it
-        assert o["n_rays_accepted"] == r["accepted"], it
+        if r["generated"] <= r["capacity"]:
+            assert o["n_rays_accepted"] == r["accepted"], it
+        else:
+            # more samples requested than the step's capacity (last step's count rounded up, testbed_nerf.cu:3217-3222): the rays whose span ends beyond it are
+            # dropped (1248-1251), and WHICH rays those are follows the order of the generator's atomicAdd in the reference as much as here -- seen to differ
+            # by one ray under compute-sanitizer's timing
+            assert abs(o["n_rays_accepted"] - r["accepted"]) <= max(2, 0.02 * r["accepted"]), it
         assert o["measured_batch_size_before_compaction"] == r["generated"], it
         assert abs(o["measured_batch_size"] - r["compacted"]) <= max(8, 0.01 * r["compacted"]), it
         assert abs(o["loss"] - r["loss"]) <= 0.02 * abs(r["loss"]) + 1e-5, it
