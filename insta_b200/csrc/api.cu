@@ -1133,7 +1133,8 @@ int insta_deform_encode_host(insta_ctx* ctx, float* h_coords, uint32_t n, uint32
 	if (!ctx || !h_coords || !d_table_f16 || !h_out_soa_f16) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_encode_host: bad arguments");
 	if (ctx->frames.empty()) INSTA_FAIL(INSTA_ERR_INVALID, "insta_deform_encode_host: no frames loaded");
 	INSTA_CUDA(cudaSetDevice(ctx->device));
-	const uint32_t chunk = 1u << 19;  // 524,288 samples: 56.6 MB of records, 134 MB of encodings per chunk
+	static const uint32_t chunk_log2 = [] { const char* e = getenv("INSTA_HOST_CHUNK_LOG2"); const int v = e ? atoi(e) : 19; return (uint32_t)(v >= 12 && v <= 22 ? v : 19); }();
+	const uint32_t chunk = 1u << chunk_log2;  // default 524,288 samples: 56.6 MB of records, 134 MB of encodings per chunk
 	int rc = ensure_stage(ctx, std::min(chunk, std::max(n, 1u)), stride_floats);
 	if (rc) return rc;
 	rc = sync_frame_table(ctx, ctx->streams[0]);
